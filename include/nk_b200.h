@@ -1,0 +1,199 @@
+/*
+ * nk_b200.h -- C ABI of the B200-native k-mer coverage-normalisation path.
+ *
+ * Drop-in boundary for the hot path of normalise_kmers_multi_large.c ("C:n" =
+ * line n of the reference's single source file).  The reference has no
+ * plugin/FFI API; its seam is the set of C functions main() calls per file
+ * (C:2239-2409).  Each entry point below names the reference function it
+ * replaces.  Plain C types only; all buffers are caller-owned host memory.
+ *
+ * Two layers, both exported from libnk_b200.so:
+ *   nk_*   host pipeline: byte ranges -> record index -> pinned staging ->
+ *          device steps -> accepted records written per partition.  This is
+ *          what a maintainer of the reference binds.
+ *   nkd_*  one device engine per GPU: HBM-resident per-partition tables and
+ *          the sm_100a kernels (extract / probe / resolve / decide / rehash).
+ *          Used by nk_*, by the parity tests and by bench.py's kernel-only leg.
+ *
+ * Every function returns 0 on success and a negative NK_E* code otherwise;
+ * nk_last_error() / nkd_last_error() give the message.  There is no CPU
+ * fallback: without a CUDA device nkd_create() fails with NK_ENODEVICE.
+ */
+#ifndef NK_B200_H
+#define NK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NK_VERSION 20240823 /* same version number the reference prints, C:1 */
+
+#define NK_MAX_PARTITIONS 256 /* C:142 */
+#define NK_MAX_LINE 1024      /* C:139: lines are cut at 1023 chars */
+#define NK_DEFAULT_SLOTS 67108879ULL /* C:137 */
+
+enum
+{
+    NK_OK = 0,
+    NK_EINVAL = -1,    /* bad argument / configuration (reference: usage + exit 1) */
+    NK_ENODEVICE = -2, /* no CUDA device or CUDA error */
+    NK_ENOMEM = -3,    /* host or device allocation failed (reference: exit 1, C:1073) */
+    NK_EDATA = -4,     /* input is not DNA / malformed (reference: FATAL + exit 1, C:1418) */
+    NK_EIO = -5,       /* cannot open / write a file */
+    NK_EINTERNAL = -6
+};
+
+/* ---------------------------------------------------------------- device engine */
+
+/* One read of a step.  Reads of a step are ordered exactly as the reference's
+ * worker visits them (C:1605-1631): partition-major, record order, forward mate
+ * before reverse mate.  op_base numbers the read's first k-mer window within
+ * its partition's step (window i of the read is operation op_base + i), which
+ * is the sequential order store_kmer() sees (C:1464, C:1559-1563). */
+typedef struct
+{
+    uint32_t seq_off; /* byte offset of the sequence line in the step's buffer, 16-aligned */
+    uint32_t op_base;
+    uint16_t len;  /* bases (>= k; shorter records are dropped by the caller, C:1430-1443) */
+    uint16_t part; /* engine-local partition index */
+    uint32_t reserved;
+} nkd_read;
+
+typedef struct
+{
+    uint64_t capacity; /* slots (C:167) */
+    uint64_t used;     /* stored k-mers (C:166) */
+    uint64_t processed, printed, skipped; /* C:179-181 */
+    uint64_t ops;        /* table operations issued (non-zero-key windows) */
+    uint64_t touches;    /* slots visited: ops + extra probe steps */
+    uint64_t expansions; /* C:1055 calls that grew the table */
+    uint64_t slow_events; /* events that needed time-ordered resolution */
+} nkd_part_stats;
+
+typedef struct nkd_engine nkd_engine;
+
+typedef struct
+{
+    int device;          /* CUDA ordinal */
+    int k;               /* 5..31 (C:724); 32 is accepted as an extension with no reference result */
+    int canonical;       /* C:1472-1476 */
+    int depth_per_part;  /* cfg.depth_per_cpu, C:674 */
+    float coverage;      /* cfg.coverage as float32, C:216 */
+    int n_parts;         /* partitions resident on this GPU */
+    uint64_t capacity0;  /* cfg.initial_hash_size, C:676-684 */
+    uint64_t max_step_reads; /* staging limits of one step */
+    uint64_t max_step_bytes;
+    uint64_t max_step_ops;
+} nkd_config;
+
+/* init_hash_table (C:890): allocates the zeroed seed table of capacity0 slots and the step scratch */
+int nkd_create(const nkd_config *cfg, nkd_engine **out);
+void nkd_destroy(nkd_engine *e);
+const char *nkd_last_error(const nkd_engine *e);
+
+/* sequence_to_hash_zero over a batch of seed reads (C:1501-1537, C:1352); reads[i].part is ignored.
+ * n_ops = op_base + windows of the last read. */
+int nkd_seed_step(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads);
+/* copy_hash_table for every resident partition (C:908-927, C:2279); frees the seed table */
+int nkd_seed_finish(nkd_engine *e);
+int nkd_seed_stats(nkd_engine *e, nkd_part_stats *out);
+/* print_kmer_table's data source for the "_seeds" dump (C:2251-2252): slot-ordered table copy */
+int nkd_seed_export(nkd_engine *e, uint64_t *keys, int32_t *counts, uint64_t capacity);
+
+/* process_sequence_pair / process_sequence_single + the print decision for a step of records
+ * (C:1539-1566, C:1641-1674, C:1988-2014).  stage = host->device copy of the step's inputs,
+ * run = kernels only, fetch = device->host copy of the accept flags (1 byte per record:
+ * 1 = emit, 0 = skip) and first_invalid (record index of the first non-ACGT sequence or -1,
+ * which the caller turns into the reference's FATAL exit, C:1445-1454). */
+int nkd_stage(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads, int paired);
+int nkd_run(nkd_engine *e);
+int nkd_fetch(nkd_engine *e, uint8_t *accept, size_t n_records, int64_t *first_invalid);
+/* time of the last nkd_run on the device, from CUDA events on the engine's stream */
+int nkd_last_run_ms(nkd_engine *e, float *total_ms, float *probe_ms);
+
+int nkd_part_stats_get(nkd_engine *e, int part, nkd_part_stats *out);
+/* print_kmer_table's data source (C:354-385): slot-ordered copy of partition's table */
+int nkd_export(nkd_engine *e, int part, uint64_t *keys, int32_t *counts, uint64_t capacity);
+
+/* test hooks: the codec alone (encode_kmer_plain / get_canonical_kmer, C:1118-1126, C:1175-1180).
+ * keys_out receives one key per window of every read (0 = ignored window), in op order. */
+int nkd_extract_keys(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
+                     uint64_t *keys_out, size_t n_ops, uint8_t *invalid_out);
+
+/* ---------------------------------------------------------------- host pipeline */
+
+typedef struct
+{
+    int k;              /* -k */
+    int depth;          /* -d */
+    float coverage;     /* -g */
+    int canonical;      /* -c */
+    int in_fastq;       /* -t: 1 fastq, 0 fasta */
+    int out_fastq;      /* -o */
+    int memory_gb;      /* -m, 0 = default capacity */
+    int partitions;     /* -p */
+    int dump_tables;    /* -P */
+    int verbose;        /* -e */
+    int n_forward_files; /* cfg.forward_file_count: sets records_to_seed, C:2242 */
+    int have_reverse;   /* cfg.reverse_file_count != 0: open output_reverse files, C:2294 */
+    const char *out_dir; /* NULL = current directory (the reference always writes to CWD) */
+    /* placement (not in the reference): which GPUs, and which slice of the partitions this
+     * process owns (part_first .. part_first+part_count-1; 0,0 = all) */
+    int n_devices;
+    const int *devices; /* NULL = 0..n_devices-1 */
+    int part_first, part_count;
+    uint32_t step_pairs; /* records per partition per step, 0 = default */
+} nk_config;
+
+typedef struct nk_ctx nk_ctx;
+
+/* parse_arguments' derived values + init_hash_table + output files opened "w" (C:674-684, C:890, C:2286-2302) */
+int nk_create(const nk_config *cfg, nk_ctx **out);
+void nk_destroy(nk_ctx *c);
+const char *nk_last_error(const nk_ctx *c);
+/* error text of the most recent failed nk_create */
+const char *nk_create_error(void);
+
+/* cfg.initial_hash_size for (-m, -p, -k): memoryGB2capacity in float32 and the 4^k clamp (C:416-422, C:676-684) */
+uint64_t nk_initial_capacity(int memory_gb, int partitions, int k);
+
+/* seed_kmer_hash (C:1322-1373) on an in-memory file image */
+int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed);
+/* the per-thread copy_hash_table loop + "_seeds" dump (C:2251-2279) */
+int nk_seed_finish(nk_ctx *c);
+
+/* multithreaded_process_files_paired (C:1772-1920) / _single (C:2113-2217) on in-memory file images:
+ * partition byte ranges, score every record, append accepted records to the partition outputs,
+ * accumulate counters. */
+int nk_process_paired(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size);
+int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size);
+
+typedef struct
+{
+    uint64_t processed, printed, skipped; /* reporting.total_* (C:198-205) */
+    uint64_t max_used;                    /* reporting.max_total_kmers */
+    double seed_seconds, process_seconds, index_seconds, device_seconds, write_seconds;
+    uint64_t h2d_bytes, d2h_bytes;
+} nk_totals;
+
+int nk_totals_get(nk_ctx *c, nk_totals *out);
+int nk_partition_stats(nk_ctx *c, int partition, nkd_part_stats *out);
+/* closes outputs; writes output_kmer.k{K}_norm{D}_thread{t}.tsv when dump_tables (C:2398-2413) */
+int nk_finish(nk_ctx *c);
+
+/* the byte ranges the reference gives each partition (C:1240-1300), for tests: starts/ends have
+ * `partitions` entries.  mode 0 = by size (calculate_thread_positions), 1 = by records. */
+int nk_partition_ranges(const char *data, size_t size, int partitions, int fastq, int mode, uint64_t records,
+                        uint64_t *starts, uint64_t *ends);
+uint64_t nk_count_records(const char *data, size_t size, int fastq);
+
+/* the whole program: same argv contract, stdout lines and exit status as the reference's main (C:2223-2455) */
+int nk_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NK_B200_H */

@@ -1,0 +1,618 @@
+/*
+ * nk_core.h -- per-operation logic of the exact parallel emulation of the reference's
+ * sequential k-mer table (normalise_kmers_multi_large.c, "C:n").
+ *
+ * Everything here is __host__ __device__ so that the sm_100a kernels (nk_engine.cu) and the
+ * shuffled-order CPU emulation used ONLY by tests/ (tests/emu/nk_emu.cpp) execute the same
+ * statements.  The product library contains the CUDA instantiation only.
+ *
+ * The reference processes one partition's k-mer windows strictly in order (C:1464, C:1559-1563):
+ *     store(x): i = x % cap
+ *               empty        -> claim: key=x, count=1, used++                    C:948-971
+ *               key == x     -> count++                                          C:972-1008
+ *               otherwise    -> walk i=(i+c*c)%cap, count++ on EVERY landed slot,
+ *                               stop at an empty slot or at x; x is never stored  C:1009-1048
+ *     then tests count[returned slot] >= depth                                   C:1494-1497
+ *
+ * Parallel restatement for one step of T operations with times t = 0..T-1:
+ *   claim time   a slot that is empty at step start can only be taken by the earliest
+ *                operation whose home it is -> 64-bit atomicMax of TAG|~t|open-index on the key field
+ *   occupancy    "slot s is occupied at time t" = stored before the step, or claim time < t
+ *   counters     every slot has a counter `count`; a slot claimed inside the step has a second
+ *                one (`aux`, the count after its claim, offset 1) because the claim resets it (C:963)
+ *   saturation   counts only grow, the test is a threshold: a counter whose value at step start
+ *                is >= depth-1 makes every test on it true -> fire-and-forget RED
+ *   pending      events on the other counters are listed, applied after all probing, and the
+ *                tests on counters that end < depth are all false
+ *   slow path    only counters that cross depth inside the step need their events ranked by
+ *                time: sort by (slot, counter, t) and rank inside the segment
+ */
+#ifndef NK_CORE_H
+#define NK_CORE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define NK_HD __host__ __device__ __forceinline__
+#else
+#define NK_HD static inline
+#endif
+
+#define NK_TAG (1ull << 63)
+#define NK_TMAX 0x7FFFFFFFu
+#define NK_T_BITS 28 /* operations per partition per step < 2^28 (slow-path sort key budget) */
+
+/* 16-byte table entry: same footprint as the reference's kmer_t {u64 hash; int count; pad} (C:157-161);
+ * the pad carries step-local state and is 0 between steps. */
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#endif
+        NkSlot
+{
+    unsigned long long key; /* 0 empty; bit 63 set = claim attempt inside the current step */
+    int count;
+    unsigned aux;
+};
+
+struct NkPart
+{
+    NkSlot *tab;
+    unsigned long long cap;
+    unsigned long long magic; /* floor((2^64-1)/cap) */
+    unsigned long long gbase; /* first global slot number (slow-path sort key) */
+    unsigned lo, hi;          /* operations [lo,hi) of this partition are live in this run */
+    unsigned pad0, pad1;
+};
+
+struct NkRead /* layout == nkd_read (include/nk_b200.h) */
+{
+    unsigned seq_off, op_base;
+    unsigned short len, part;
+    unsigned reserved;
+};
+
+struct NkOpen /* an operation that met a slot which was empty at step start */
+{
+    unsigned long long key;
+    unsigned t, read, slot, part;
+    unsigned c;     /* walk step at which it stopped (0 = at home) */
+    unsigned flags; /* bit0: stopped at its home slot (claim candidate) */
+};
+
+struct NkPend /* an increment of a counter that was not saturated at step start */
+{
+    unsigned slot;
+    unsigned tw; /* t<<2 | which<<1 | terminal */
+    int base;    /* counter value at step start (1 for the post-claim counter) */
+    unsigned read;
+};
+
+struct NkClaim
+{
+    unsigned long long key;
+    unsigned slot, t, part, pad;
+};
+
+#define NK_OVF_OPEN 1u
+#define NK_OVF_PEND 2u
+#define NK_OVF_CLAIM 4u
+#define NK_OVF_WALK 8u
+
+struct NkCounters
+{
+    unsigned n_open, n_pend, n_claim, n_slow;
+    unsigned overflow;
+    unsigned inv_max; /* max over invalid records of NK_TMAX - record index; 0 = none */
+    unsigned pad[2];
+    unsigned long long touches[256]; /* per partition, slots visited */
+    unsigned long long real_ops[256];
+    unsigned claims[256];
+};
+
+enum
+{
+    NK_MODE_SCORE = 0,
+    NK_MODE_SEED = 1,
+    NK_MODE_COUNT = 2,
+    NK_MODE_KEYS = 3
+};
+
+struct NkRun
+{
+    const unsigned char *seq;
+    const NkRead *reads;
+    unsigned n_reads;
+    const NkPart *parts;
+    int k, canonical, depth, mode;
+    int delta;  /* +1 forward, -1 undo */
+    int record; /* 0 in undo runs: no list appends, no claim attempts */
+    unsigned *high, *total;
+    unsigned char *invalid;
+    NkOpen *open;
+    unsigned open_cap;
+    NkPend *pend;
+    unsigned pend_cap;
+    NkClaim *claim;
+    unsigned claim_cap;
+    unsigned long long *slow_key, *slow_val;
+    unsigned slow_cap;
+    NkCounters *ctr;
+    unsigned long long *keys_out; /* NK_MODE_KEYS */
+};
+
+/* ---------------------------------------------------------------- primitives */
+
+#if defined(__CUDA_ARCH__)
+#define NK_DEVICE_CODE 1
+#else
+#define NK_DEVICE_CODE 0
+#endif
+
+NK_HD unsigned long long nk_atomic_max64(unsigned long long *p, unsigned long long v)
+{
+#if NK_DEVICE_CODE
+    return atomicMax(p, v);
+#else
+    unsigned long long o = *p;
+    if (v > o)
+        *p = v;
+    return o;
+#endif
+}
+NK_HD unsigned nk_atomic_max32(unsigned *p, unsigned v)
+{
+#if NK_DEVICE_CODE
+    return atomicMax(p, v);
+#else
+    unsigned o = *p;
+    if (v > o)
+        *p = v;
+    return o;
+#endif
+}
+NK_HD void nk_red_add32(int *p, int v)
+{
+#if NK_DEVICE_CODE
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+NK_HD void nk_red_add64(unsigned long long *p, unsigned long long v)
+{
+#if NK_DEVICE_CODE
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+NK_HD void nk_red_or32(unsigned *p, unsigned v)
+{
+#if NK_DEVICE_CODE
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+/* reserve one list entry; on the device the lanes of a warp that call together share one atomic */
+NK_HD unsigned nk_append(unsigned *ctr)
+{
+#if NK_DEVICE_CODE
+    unsigned mask = __activemask();
+    int leader = __ffs(mask) - 1;
+    unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if ((int)lane == leader)
+        base = atomicAdd(ctr, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1));
+#else
+    return (*ctr)++;
+#endif
+}
+NK_HD NkSlot nk_load_slot(const NkSlot *p)
+{
+#if NK_DEVICE_CODE
+    /* L2-only (no L1 allocation): random 16-byte gathers never hit L1 */
+    uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    NkSlot s;
+    s.key = ((unsigned long long)v.y << 32) | v.x;
+    s.count = (int)v.z;
+    s.aux = v.w;
+    return s;
+#else
+    return *p;
+#endif
+}
+NK_HD unsigned long long nk_mulhi64(unsigned long long a, unsigned long long b)
+{
+#if NK_DEVICE_CODE
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+/* x % d with d's reciprocal m = floor((2^64-1)/d): the reference's per-probe 64-bit modulo (C:936, C:1028) */
+NK_HD unsigned long long nk_mod(unsigned long long x, unsigned long long d, unsigned long long m)
+{
+    unsigned long long q = nk_mulhi64(x, m);
+    unsigned long long r = x - q * d;
+    while (r >= d)
+        r -= d;
+    return r;
+}
+
+NK_HD bool nk_is_real(unsigned long long f) { return f != 0 && !(f & NK_TAG); }
+NK_HD unsigned nk_tag_time(unsigned long long f) { return NK_TMAX - (unsigned)((f >> 32) & NK_TMAX); }
+NK_HD unsigned nk_tag_open(unsigned long long f) { return (unsigned)f; }
+NK_HD unsigned long long nk_make_tag(unsigned t, unsigned idx)
+{
+    return NK_TAG | ((unsigned long long)(NK_TMAX - t) << 32) | idx;
+}
+
+/* ---------------------------------------------------------------- codec (C:1118-1126, C:1160-1180) */
+
+/* encoding of the reverse complement of a k-mer: complement, reverse the 2-bit groups */
+NK_HD unsigned long long nk_revcomp(unsigned long long x, int k)
+{
+    x = ~x;
+#if NK_DEVICE_CODE
+    x = __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = __builtin_bswap64(x);
+#endif
+    x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+    return x >> (64 - 2 * k);
+}
+
+/* scalar reference of the packed path: A0 C1 G2 T3, anything else (incl. N) 0, MSB-first */
+NK_HD unsigned long long nk_window_key_ascii(const unsigned char *s, int k, int canonical)
+{
+    unsigned long long x = 0;
+    for (int i = 0; i < k; i++)
+    {
+        unsigned b = s[i];
+        unsigned code = (b == 'C') ? 1u : (b == 'G') ? 2u
+                                      : (b == 'T')   ? 3u
+                                                     : 0u;
+        x = (x << 2) | code;
+    }
+    if (canonical)
+    {
+        unsigned long long r = nk_revcomp(x, k);
+        if (r < x)
+            x = r;
+    }
+    return x;
+}
+
+/* ---------------------------------------------------------------- events */
+
+/* one increment of counter (slot, which) by the operation at time t.  which: 0 = count, 1 = aux
+ * (count after an in-step claim, value = 1 + aux).  base = the counter's value at step start. */
+NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int which, int base, int terminal, unsigned t,
+                    unsigned read, int &high_acc)
+{
+    if (base >= P.depth - 1)
+    { /* saturated: all tests on this counter are true this step; counts commute */
+        int *ctr = which ? reinterpret_cast<int *>(&pd.tab[slot].aux) : &pd.tab[slot].count;
+        nk_red_add32(ctr, P.delta);
+        if (terminal)
+            high_acc += P.delta;
+    }
+    else if (P.record)
+    {
+        unsigned idx = nk_append(&P.ctr->n_pend);
+        if (idx < P.pend_cap)
+        {
+            NkPend r;
+            r.slot = slot;
+            r.tw = (t << 2) | ((unsigned)which << 1) | (unsigned)terminal;
+            r.base = base;
+            r.read = read;
+            P.pend[idx] = r;
+        }
+        else
+            nk_red_or32(&P.ctr->overflow, NK_OVF_PEND);
+    }
+}
+
+NK_HD void nk_defer(const NkRun &P, unsigned long long key, unsigned t, unsigned read, unsigned part, unsigned slot,
+                    unsigned c, unsigned at_home, NkSlot *home_slot)
+{
+    if (!P.record)
+        return;
+    unsigned idx = nk_append(&P.ctr->n_open);
+    if (idx >= P.open_cap)
+    {
+        nk_red_or32(&P.ctr->overflow, NK_OVF_OPEN);
+        return;
+    }
+    NkOpen o;
+    o.key = key;
+    o.t = t;
+    o.read = read;
+    o.slot = slot;
+    o.part = part;
+    o.c = c;
+    o.flags = at_home;
+    P.open[idx] = o;
+    if (at_home) /* claim attempt: earliest operation wins, payload finds its key later */
+        nk_atomic_max64(&home_slot->key, nk_make_tag(t, idx));
+}
+
+#define NK_MAX_WALK 40000 /* c*c is int arithmetic in the reference (C:1028): stay below overflow */
+
+/* phase 1: everything about operation (key,t) that does not depend on in-step claims.
+ * Returns the number of slots visited (touches).  */
+NK_HD unsigned nk_probe_op(const NkRun &P, const NkPart &pd, unsigned part, unsigned long long key, unsigned t,
+                           unsigned read, int &high_acc)
+{
+    unsigned long long i = nk_mod(key, pd.cap, pd.magic);
+    NkSlot e = nk_load_slot(&pd.tab[i]);
+    if (P.mode == NK_MODE_SEED)
+    { /* init mode changes no count (all are 0): only claims are observable (C:963, C:994-1000, C:1046) */
+        if (!nk_is_real(e.key))
+            nk_defer(P, key, t, read, part, (unsigned)i, 0, 1, &pd.tab[i]);
+        return 1;
+    }
+    if (e.key == key)
+    {
+        nk_event(P, pd, (unsigned)i, 0, e.count, 1, t, read, high_acc);
+        return 1;
+    }
+    if (!nk_is_real(e.key))
+    {
+        nk_defer(P, key, t, read, part, (unsigned)i, 0, 1, &pd.tab[i]);
+        return 1;
+    }
+    unsigned touches = 1;
+    for (unsigned c = 1;; c++)
+    {
+        if (c > NK_MAX_WALK)
+        {
+            nk_red_or32(&P.ctr->overflow, NK_OVF_WALK);
+            break;
+        }
+        i = nk_mod(i + (unsigned long long)c * c, pd.cap, pd.magic);
+        e = nk_load_slot(&pd.tab[i]);
+        if (!nk_is_real(e.key))
+        { /* empty at step start: whether it is still empty at time t is decided in phase 2 */
+            nk_defer(P, key, t, read, part, (unsigned)i, c, 0, nullptr);
+            break;
+        }
+        touches++;
+        int term = e.key == key;
+        nk_event(P, pd, (unsigned)i, 0, e.count, term, t, read, high_acc);
+        if (term)
+            break;
+    }
+    return touches;
+}
+
+/* phase 2: finish a deferred operation now that every claim time is known */
+NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc)
+{
+    NkOpen o = P.open[idx];
+    const NkPart &pd = P.parts[o.part];
+    unsigned long long i = o.slot;
+    unsigned c = o.c;
+    unsigned touches = 0;
+    bool landed = true; /* slot i has been reached but not evaluated yet */
+    if (o.flags & 1u)
+    {
+        unsigned long long f = nk_load_slot(&pd.tab[i]).key;
+        unsigned tc = nk_tag_time(f);
+        if (tc == o.t)
+        { /* this operation stores the key: count becomes 1 (0 when seeding), test is false (depth >= 2) */
+            if (P.record)
+            {
+                unsigned ci = nk_append(&P.ctr->n_claim);
+                if (ci < P.claim_cap)
+                {
+                    NkClaim cl;
+                    cl.key = o.key;
+                    cl.slot = (unsigned)i;
+                    cl.t = o.t;
+                    cl.part = o.part;
+                    cl.pad = 0;
+                    P.claim[ci] = cl;
+                }
+                else
+                    nk_red_or32(&P.ctr->overflow, NK_OVF_CLAIM);
+                nk_red_add32(reinterpret_cast<int *>(&P.ctr->claims[o.part]), 1);
+            }
+            return 0;
+        }
+        if (P.mode == NK_MODE_SEED)
+            return 0;
+        /* an earlier operation of this step owns the home slot */
+        unsigned long long owner = P.open[nk_tag_open(f)].key;
+        if (owner == o.key)
+        {
+            nk_event(P, pd, (unsigned)i, 1, 1, 1, o.t, o.read, high_acc);
+            return 0;
+        }
+        landed = false; /* collision at home: walk */
+    }
+    for (;;)
+    {
+        if (!landed)
+        {
+            c++;
+            if (c > NK_MAX_WALK)
+            {
+                nk_red_or32(&P.ctr->overflow, NK_OVF_WALK);
+                break;
+            }
+            i = nk_mod(i + (unsigned long long)c * c, pd.cap, pd.magic);
+        }
+        landed = false;
+        touches++;
+        NkSlot e = nk_load_slot(&pd.tab[i]);
+        if (nk_is_real(e.key))
+        {
+            int term = e.key == o.key;
+            nk_event(P, pd, (unsigned)i, 0, e.count, term, o.t, o.read, high_acc);
+            if (term)
+                break;
+            continue;
+        }
+        if (e.key == 0 || nk_tag_time(e.key) > o.t)
+        { /* empty at time t: the walk ends on a ghost counter (C:1015, C:1043-1044) */
+            nk_event(P, pd, (unsigned)i, 0, e.count, 1, o.t, o.read, high_acc);
+            break;
+        }
+        /* claimed earlier in this step by another key (a walker never meets its own key here:
+         * keys are stored at their home slot only, and this walker's home holds a different key) */
+        nk_event(P, pd, (unsigned)i, 1, 1, 0, o.t, o.read, high_acc);
+    }
+    return touches;
+}
+
+/* phase 3: apply a pending increment */
+NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
+{
+    NkPend r = P.pend[idx];
+    const NkPart &pd = P.parts[P.reads[r.read].part];
+    int *ctr = (r.tw & 2u) ? reinterpret_cast<int *>(&pd.tab[r.slot].aux) : &pd.tab[r.slot].count;
+    nk_red_add32(ctr, 1);
+}
+
+/* phase 4: a counter that ends below depth has only false tests; otherwise its events need ranking */
+NK_HD void nk_classify_op(const NkRun &P, unsigned idx)
+{
+    NkPend r = P.pend[idx];
+    const NkPart &pd = P.parts[P.reads[r.read].part];
+    NkSlot e = nk_load_slot(&pd.tab[r.slot]);
+    int which = (r.tw >> 1) & 1;
+    long long v = which ? 1ll + (long long)e.aux : (long long)e.count;
+    if (v < P.depth)
+        return;
+    unsigned si = nk_append(&P.ctr->n_slow);
+    if (si >= P.slow_cap)
+        return; /* cannot happen: slow_cap == pend_cap */
+    unsigned t = r.tw >> 2;
+    P.slow_key[si] = ((pd.gbase + r.slot) << (NK_T_BITS + 2)) | ((unsigned long long)which << (NK_T_BITS + 1)) |
+                     ((unsigned long long)t << 1) | (r.tw & 1u);
+    P.slow_val[si] = ((unsigned long long)(unsigned)r.base << 32) | r.read;
+}
+
+/* phase 5: rank of event i inside its (slot,counter) segment of the time-sorted list */
+NK_HD void nk_rank_op(const NkRun &P, const unsigned long long *keys, const unsigned long long *vals, unsigned n,
+                      unsigned i)
+{
+    unsigned long long key = keys[i];
+    if (!(key & 1))
+        return; /* only the terminal landing is tested (C:1494) */
+    unsigned long long seg = key >> (NK_T_BITS + 1);
+    unsigned lo = 0, hi = i; /* first index whose segment is >= seg */
+    while (lo < hi)
+    {
+        unsigned mid = (lo + hi) >> 1;
+        if ((keys[mid] >> (NK_T_BITS + 1)) < seg)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    long long after = (long long)(int)(vals[i] >> 32) + (long long)(i - lo + 1);
+    if (after >= P.depth)
+    {
+#if NK_DEVICE_CODE
+        atomicAdd(&P.high[(unsigned)vals[i]], 1u);
+#else
+        P.high[(unsigned)vals[i]] += 1u;
+#endif
+    }
+}
+
+/* phase 6: store the claimed keys (C:962-965) */
+NK_HD void nk_commit_op(const NkRun &P, unsigned idx)
+{
+    NkClaim cl = P.claim[idx];
+    NkSlot *s = &P.parts[cl.part].tab[cl.slot];
+    NkSlot n;
+    n.key = cl.key;
+    n.count = (P.mode == NK_MODE_SEED) ? 0 : (int)(1u + s->aux);
+    n.aux = 0;
+    *s = n;
+}
+
+/* undo: forget the claim attempts of an abandoned run */
+NK_HD void nk_untag_op(const NkRun &P, unsigned idx)
+{
+    NkOpen o = P.open[idx];
+    if (!(o.flags & 1u))
+        return;
+    NkSlot *s = &P.parts[o.part].tab[o.slot];
+    if (s->key & NK_TAG)
+        s->key = 0;
+    s->aux = 0;
+}
+
+/* ---------------------------------------------------------------- growth (C:1055-1108) */
+
+/* Sequential re-insertion in old-slot order with linear probing == linear probing with
+ * priority "lower old index wins" (history-independent layout).  aux of the new table holds
+ * 0xFFFFFFFF - old index of the current occupant while placing. */
+NK_HD void nk_rehash_place_op(const NkSlot *old_tab, unsigned long long old_i, NkSlot *new_tab, unsigned long long ncap,
+                              unsigned long long nmagic)
+{
+    unsigned long long key = old_tab[old_i].key;
+    if (key == 0)
+        return;
+    unsigned cur = 0xFFFFFFFFu - (unsigned)old_i;
+    unsigned long long j = nk_mod(key, ncap, nmagic);
+    for (;;)
+    {
+        unsigned prev = nk_atomic_max32(&new_tab[j].aux, cur);
+        if (prev == 0)
+            return;
+        if (prev < cur)
+            cur = prev; /* displaced a later key: carry it on */
+        j = (j + 1 == ncap) ? 0 : j + 1;
+    }
+}
+
+NK_HD void nk_rehash_fill_op(const NkSlot *old_tab, NkSlot *new_tab, unsigned long long j)
+{
+    unsigned a = new_tab[j].aux;
+    if (a == 0)
+        return;
+    NkSlot s = old_tab[0xFFFFFFFFu - a];
+    s.aux = 0; /* ghost counts of empty slots are not carried (C:1079) */
+    new_tab[j] = s;
+}
+
+/* ---------------------------------------------------------------- decision (C:1641-1646, C:1988-1992) */
+
+NK_HD int nk_keep_mate(unsigned high, unsigned total, float coverage)
+{
+#if NK_DEVICE_CODE
+    float r = total > 0 ? __fdiv_rn((float)high, (float)total) : 0.0f;
+#else
+    float r = total > 0 ? (float)high / (float)total : 0.0f;
+#endif
+    return r < coverage;
+}
+
+/* one record: both mates must stay below the coverage (C:1646); a record with a non-ACGTN byte is
+ * reported instead (the reference aborts on it, C:1445-1454) */
+NK_HD void nk_decide_op(const NkRun &P, unsigned rec, int paired, float coverage, unsigned char *accept)
+{
+    unsigned r0 = paired ? 2 * rec : rec;
+    bool bad = P.invalid[r0] || (paired && P.invalid[r0 + 1]);
+    if (bad)
+        nk_atomic_max32(&P.ctr->inv_max, NK_TMAX - rec);
+    int keep = nk_keep_mate(P.high[r0], P.total[r0], coverage);
+    if (paired)
+        keep = keep && nk_keep_mate(P.high[r0 + 1], P.total[r0 + 1], coverage);
+    accept[rec] = (unsigned char)keep;
+}
+
+#endif /* NK_CORE_H */

@@ -1,0 +1,98 @@
+/*
+ * nk_engine_api.h -- the extern "C" nkd_* entry points (include/nk_b200.h) over NkEngine<NK_BACKEND>.
+ * Included once by nk_engine.cu (NK_BACKEND = CudaBackend) and once by tests/emu/nk_emu.cpp
+ * (NK_BACKEND = the test-only CPU emulation).
+ */
+#ifndef NK_ENGINE_API_H
+#define NK_ENGINE_API_H
+
+#include "nk_orchestrate.h"
+
+struct nkd_engine
+{
+    NkEngine<NK_BACKEND> e;
+};
+
+static_assert(sizeof(nkd_read) == sizeof(NkRead), "nkd_read layout");
+
+extern "C" {
+
+int nkd_create(const nkd_config *cfg, nkd_engine **out)
+{
+    if (!cfg || !out)
+        return NK_EINVAL;
+    nkd_engine *h = new nkd_engine();
+    int rc = h->e.create(*cfg);
+    *out = h; /* kept on failure so that nkd_last_error can be read; caller still destroys it */
+    return rc;
+}
+
+void nkd_destroy(nkd_engine *h)
+{
+    if (!h)
+        return;
+    h->e.destroy();
+    delete h;
+}
+
+const char *nkd_last_error(const nkd_engine *h) { return h ? h->e.err.c_str() : "null engine"; }
+
+int nkd_seed_step(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads)
+{
+    return h->e.seed_step(seq, seq_bytes, reads, n_reads);
+}
+int nkd_seed_finish(nkd_engine *h) { return h->e.seed_finish(); }
+int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)
+{
+    *out = h->e.seed.st;
+    out->capacity = h->e.seed.cap;
+    out->used = h->e.seed.used;
+    return NK_OK;
+}
+int nkd_seed_export(nkd_engine *h, uint64_t *keys, int32_t *counts, uint64_t capacity)
+{
+    return h->e.export_table(h->e.seed, keys, counts, capacity);
+}
+int nkd_stage(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads, int paired)
+{
+    if (!h->e.seeded)
+        return h->e.fail(NK_EINVAL, "nkd_stage before nkd_seed_finish");
+    return h->e.stage(seq, seq_bytes, reads, n_reads, paired, h->e.cfg.n_parts, false);
+}
+int nkd_run(nkd_engine *h) { return h->e.run_step(); }
+int nkd_fetch(nkd_engine *h, uint8_t *accept, size_t n_records, int64_t *first_invalid)
+{
+    return h->e.fetch(accept, n_records, first_invalid);
+}
+int nkd_last_run_ms(nkd_engine *h, float *total_ms, float *probe_ms)
+{
+    if (total_ms)
+        *total_ms = h->e.last_total_ms;
+    if (probe_ms)
+        *probe_ms = h->e.last_probe_ms;
+    return NK_OK;
+}
+int nkd_part_stats_get(nkd_engine *h, int part, nkd_part_stats *out)
+{
+    if (part < 0 || part >= (int)h->e.parts.size())
+        return h->e.fail(NK_EINVAL, "no such partition");
+    *out = h->e.parts[part].st;
+    out->capacity = h->e.parts[part].cap;
+    out->used = h->e.parts[part].used;
+    return NK_OK;
+}
+int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_t capacity)
+{
+    if (part < 0 || part >= (int)h->e.parts.size())
+        return h->e.fail(NK_EINVAL, "no such partition");
+    return h->e.export_table(h->e.parts[part], keys, counts, capacity);
+}
+int nkd_extract_keys(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
+                     uint64_t *keys_out, size_t n_ops, uint8_t *invalid_out)
+{
+    return h->e.extract_keys(seq, seq_bytes, reads, n_reads, keys_out, n_ops, invalid_out);
+}
+
+} /* extern "C" */
+
+#endif

@@ -1,0 +1,599 @@
+/*
+ * nk_orchestrate.h -- step orchestration of one device engine, templated on a backend.
+ *
+ * The product instantiates NkEngine<CudaBackend> (nk_engine.cu).  tests/emu instantiates it with
+ * a CPU backend that executes the per-operation functions of nk_core.h in shuffled order, to check
+ * the parallel algorithm against the oracle without a GPU.  No CPU backend is compiled into the
+ * product library.
+ *
+ * A backend provides: alloc/release/zero/h2d/d2h/d2d/sync, the launches probe/open_ops/apply/
+ * classify/sort_pairs/rank/commit/untag/rehash/decide, and begin_timer/end_timer.
+ */
+#ifndef NK_ORCHESTRATE_H
+#define NK_ORCHESTRATE_H
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nk_core.h"
+#include "../../include/nk_b200.h"
+
+struct NkTable
+{
+    NkSlot *tab = nullptr;
+    uint64_t cap = 0, used = 0, thr = 0, magic = 0;
+    nkd_part_stats st{};
+};
+
+/* smallest used for which the reference's `used >= capacity * 0.8` (double) holds, C:933 */
+static inline uint64_t nk_expand_threshold(uint64_t cap)
+{
+    double lim = (double)cap * 0.8;
+    uint64_t u = (uint64_t)lim;
+    while ((double)u < lim)
+        u++;
+    while (u > 0 && (double)(u - 1) >= lim)
+        u--;
+    return u;
+}
+static inline uint64_t nk_grown_capacity(uint64_t cap) { return (uint64_t)((double)cap + (double)cap * 0.5); } /* C:1058 */
+static inline uint64_t nk_magic(uint64_t cap) { return ~0ull / cap; }
+
+static inline double nk_env_double(const char *name, double dflt)
+{
+    const char *s = getenv(name);
+    return s && *s ? atof(s) : dflt;
+}
+
+template <class B>
+class NkEngine
+{
+  public:
+    B be;
+    nkd_config cfg{};
+    std::string err;
+
+    NkTable seed;
+    std::vector<NkTable> parts;
+    bool seeded = false;
+
+    /* step buffers */
+    unsigned char *d_seq = nullptr;
+    NkRead *d_reads = nullptr;
+    unsigned *d_high = nullptr, *d_total = nullptr;
+    unsigned char *d_invalid = nullptr, *d_accept = nullptr;
+    NkOpen *d_open = nullptr;
+    NkPend *d_pend = nullptr;
+    NkClaim *d_claim = nullptr;
+    unsigned long long *d_skey[2] = {nullptr, nullptr}, *d_sval[2] = {nullptr, nullptr};
+    unsigned long long *d_keys_out = nullptr;
+    NkCounters *d_ctr = nullptr;
+    NkPart *d_parts = nullptr;
+    unsigned open_cap = 0, pend_cap = 0, claim_cap = 0;
+
+    NkCounters h_ctr{};
+    std::vector<NkPart> h_parts;
+    std::vector<NkClaim> h_claims;
+
+    /* staged step */
+    size_t n_reads = 0, n_records = 0;
+    int paired = 0;
+    std::vector<unsigned> T;
+    const nkd_read *h_reads = nullptr;
+    bool staged = false, ran = false;
+    float last_total_ms = 0, last_probe_ms = 0;
+
+    int fail(int code, const std::string &m)
+    {
+        err = m;
+        return code;
+    }
+
+    int create(const nkd_config &c)
+    {
+        cfg = c;
+        if (c.k < 5 || c.k > 32 || c.n_parts < 1 || c.n_parts > NK_MAX_PARTITIONS || c.depth_per_part < 2 ||
+            c.capacity0 < 1 || c.capacity0 >= 0xFFFFFFFFull)
+            return fail(NK_EINVAL, "nkd_create: bad configuration");
+        if (c.max_step_ops >= (1ull << NK_T_BITS) || c.max_step_reads >= (1ull << 31))
+            return fail(NK_EINVAL, "nkd_create: step limits too large (ops per step must stay below 2^28)");
+        int rc = be.init(c.device, err);
+        if (rc)
+            return rc;
+        if (!alloc_table(seed, c.capacity0))
+            return fail(NK_ENOMEM, "nkd_create: cannot allocate the seed table");
+        uint64_t ops = std::max<uint64_t>(c.max_step_ops, 1024);
+        open_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_OPEN_FRAC", 1.0) + 1024);
+        pend_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_PEND_FRAC", 2.0) + 1024);
+        claim_cap = open_cap;
+        bool ok = true;
+        ok &= dalloc(d_seq, c.max_step_bytes + 64);
+        ok &= dalloc(d_reads, c.max_step_reads + 1);
+        ok &= dalloc(d_high, c.max_step_reads + 1);
+        ok &= dalloc(d_total, c.max_step_reads + 1);
+        ok &= dalloc(d_invalid, c.max_step_reads + 1);
+        ok &= dalloc(d_accept, c.max_step_reads + 1);
+        ok &= dalloc(d_open, open_cap);
+        ok &= dalloc(d_pend, pend_cap);
+        ok &= dalloc(d_claim, claim_cap);
+        for (int i = 0; i < 2; i++)
+        {
+            ok &= dalloc(d_skey[i], pend_cap);
+            ok &= dalloc(d_sval[i], pend_cap);
+        }
+        ok &= dalloc(d_ctr, 1);
+        ok &= dalloc(d_parts, NK_MAX_PARTITIONS);
+        if (!ok)
+            return fail(NK_ENOMEM, "nkd_create: cannot allocate step scratch");
+        if (!be.prepare_sort(pend_cap, err))
+            return NK_ENOMEM;
+        h_parts.resize(NK_MAX_PARTITIONS);
+        T.assign(NK_MAX_PARTITIONS, 0);
+        return NK_OK;
+    }
+
+    void destroy()
+    {
+        be.sync();
+        be.release(seed.tab);
+        for (auto &p : parts)
+            be.release(p.tab);
+        be.release(d_seq);
+        be.release(d_reads);
+        be.release(d_high);
+        be.release(d_total);
+        be.release(d_invalid);
+        be.release(d_accept);
+        be.release(d_open);
+        be.release(d_pend);
+        be.release(d_claim);
+        for (int i = 0; i < 2; i++)
+        {
+            be.release(d_skey[i]);
+            be.release(d_sval[i]);
+        }
+        be.release(d_keys_out);
+        be.release(d_ctr);
+        be.release(d_parts);
+        be.shutdown();
+    }
+
+    template <class X>
+    bool dalloc(X *&p, size_t n)
+    {
+        p = (X *)be.alloc(n * sizeof(X));
+        return p != nullptr;
+    }
+
+    bool alloc_table(NkTable &t, uint64_t cap)
+    {
+        t.tab = (NkSlot *)be.alloc(cap * sizeof(NkSlot));
+        if (!t.tab)
+            return false;
+        be.zero(t.tab, cap * sizeof(NkSlot));
+        t.cap = cap;
+        t.used = 0;
+        t.thr = nk_expand_threshold(cap);
+        t.magic = nk_magic(cap);
+        t.st.capacity = cap;
+        return true;
+    }
+
+    /* expand_local_hash_table, C:1055-1108 */
+    int expand(NkTable &t)
+    {
+        uint64_t ncap = nk_grown_capacity(t.cap);
+        if (ncap <= t.cap)
+            return NK_OK;
+        if (ncap >= 0xFFFFFFFFull)
+            return fail(NK_ENOMEM, "table growth beyond 2^32 slots is not supported on one partition");
+        NkSlot *nt = (NkSlot *)be.alloc(ncap * sizeof(NkSlot));
+        if (!nt)
+        {
+            char m[160];
+            snprintf(m, sizeof m, "Error: Memory allocation failed to expand local hash table, from %llu to %llu",
+                     (unsigned long long)t.cap, (unsigned long long)ncap);
+            return fail(NK_ENOMEM, m);
+        }
+        be.zero(nt, ncap * sizeof(NkSlot));
+        be.rehash(t.tab, t.cap, nt, ncap, nk_magic(ncap));
+        be.sync();
+        be.release(t.tab);
+        t.tab = nt;
+        t.cap = ncap;
+        t.thr = nk_expand_threshold(ncap);
+        t.magic = nk_magic(ncap);
+        t.st.capacity = ncap;
+        t.st.expansions++;
+        return NK_OK;
+    }
+
+    NkRun make_run(int mode, int delta, int record)
+    {
+        NkRun P{};
+        P.seq = d_seq;
+        P.reads = d_reads;
+        P.n_reads = (unsigned)n_reads;
+        P.parts = d_parts;
+        P.k = cfg.k;
+        P.canonical = cfg.canonical;
+        P.depth = cfg.depth_per_part;
+        P.mode = mode;
+        P.delta = delta;
+        P.record = record;
+        P.high = d_high;
+        P.total = d_total;
+        P.invalid = d_invalid;
+        P.open = d_open;
+        P.open_cap = open_cap;
+        P.pend = d_pend;
+        P.pend_cap = pend_cap;
+        P.claim = d_claim;
+        P.claim_cap = claim_cap;
+        P.slow_key = d_skey[0];
+        P.slow_val = d_sval[0];
+        P.slow_cap = pend_cap;
+        P.ctr = d_ctr;
+        P.keys_out = d_keys_out;
+        return P;
+    }
+
+    void upload_parts(std::vector<NkTable *> &tabs, const std::vector<unsigned> &lo, const std::vector<unsigned> &hi)
+    {
+        uint64_t g = 0;
+        for (size_t p = 0; p < tabs.size(); p++)
+        {
+            NkPart &d = h_parts[p];
+            d.tab = tabs[p]->tab;
+            d.cap = tabs[p]->cap;
+            d.magic = tabs[p]->magic;
+            d.gbase = g;
+            d.lo = lo[p];
+            d.hi = hi[p];
+            g += tabs[p]->cap;
+        }
+        be.h2d(d_parts, h_parts.data(), tabs.size() * sizeof(NkPart));
+    }
+
+    void fetch_counters()
+    {
+        be.d2h(&h_ctr, d_ctr, sizeof(NkCounters));
+        be.sync();
+    }
+
+    /* The sequential semantics of all operations [0,T[p]) of every table in tabs.
+     * mode: NK_MODE_SCORE or NK_MODE_SEED. */
+    int run_ops(int mode, std::vector<NkTable *> &tabs)
+    {
+        size_t np = tabs.size();
+        std::vector<unsigned> lo(np, 0), hi(np);
+        for (size_t p = 0; p < np; p++)
+            hi[p] = T[p];
+        uint64_t gsum = 0;
+        for (auto *t : tabs)
+            gsum += t->cap;
+        for (;;)
+        {
+            bool live = false;
+            for (size_t p = 0; p < np; p++)
+                live |= lo[p] < T[p];
+            if (!live)
+                break;
+            /* the load-factor test precedes every operation (C:933): a table at its threshold grows
+             * as soon as one more non-ignored window arrives */
+            bool need_count = false;
+            for (size_t p = 0; p < np; p++)
+                need_count |= (lo[p] < hi[p] && tabs[p]->used >= tabs[p]->thr);
+            if (need_count)
+            {
+                upload_parts(tabs, lo, hi);
+                be.zero(d_ctr, sizeof(NkCounters));
+                be.probe(make_run(NK_MODE_COUNT, 0, 0));
+                fetch_counters();
+                for (size_t p = 0; p < np; p++)
+                    if (lo[p] < hi[p] && tabs[p]->used >= tabs[p]->thr && h_ctr.real_ops[p] > 0)
+                    {
+                        int rc = expand(*tabs[p]);
+                        if (rc)
+                            return rc;
+                    }
+                gsum = 0;
+                for (auto *t : tabs)
+                    gsum += t->cap;
+            }
+            if (gsum >= (1ull << 34))
+                return fail(NK_ENOMEM, "tables of one device exceed 2^34 slots");
+
+            /* forward run: probe (claim-independent part), then the deferred operations */
+            upload_parts(tabs, lo, hi);
+            be.zero(d_ctr, sizeof(NkCounters));
+            NkRun F = make_run(mode, +1, 1);
+            be.begin_timer(1);
+            be.probe(F);
+            be.end_timer(1);
+            be.open_ops(F);
+            fetch_counters();
+            if (h_ctr.overflow & NK_OVF_WALK)
+                return fail(NK_EINTERNAL, "probe walk exceeded the supported length (table degenerate)");
+            bool ovf = (h_ctr.overflow & (NK_OVF_OPEN | NK_OVF_PEND | NK_OVF_CLAIM)) != 0;
+            bool cut = false;
+            std::vector<unsigned> nhi(hi);
+            if (ovf)
+            {
+                for (size_t p = 0; p < np; p++)
+                    if (hi[p] > lo[p])
+                    {
+                        unsigned w = hi[p] - lo[p];
+                        if (w > 1)
+                        {
+                            nhi[p] = lo[p] + w / 2;
+                            cut = true;
+                        }
+                    }
+                if (!cut)
+                    return fail(NK_ENOMEM, "step scratch too small for a single operation");
+            }
+            else
+            {
+                bool fetched = false;
+                for (size_t p = 0; p < np; p++)
+                {
+                    NkTable &t = *tabs[p];
+                    if (t.used >= t.thr || t.used + h_ctr.claims[p] < t.thr)
+                        continue;
+                    /* the claim that brings `used` to the threshold; the next non-ignored window grows the table */
+                    if (!fetched)
+                    {
+                        h_claims.resize(h_ctr.n_claim);
+                        if (h_ctr.n_claim)
+                            be.d2h(h_claims.data(), d_claim, (size_t)h_ctr.n_claim * sizeof(NkClaim));
+                        be.sync();
+                        fetched = true;
+                    }
+                    std::vector<unsigned> times;
+                    for (auto &c : h_claims)
+                        if (c.part == p)
+                            times.push_back(c.t);
+                    uint64_t m = t.thr - t.used;
+                    std::nth_element(times.begin(), times.begin() + (m - 1), times.end());
+                    unsigned tstar = times[m - 1] + 1;
+                    if (tstar < hi[p])
+                    {
+                        nhi[p] = tstar;
+                        cut = true;
+                    }
+                }
+            }
+            if (cut)
+            { /* abandon this run: replay it with -1 (the decisions are stable), forget the claim attempts */
+                NkRun U = make_run(mode, -1, 0);
+                be.probe(U);
+                be.open_ops(U);
+                be.untag(U, std::min(h_ctr.n_open, open_cap));
+                hi = nhi;
+                continue;
+            }
+            /* commit */
+            if (mode == NK_MODE_SCORE)
+            {
+                unsigned np_ = h_ctr.n_pend;
+                if (np_)
+                {
+                    be.apply(F, np_);
+                    be.classify(F, np_);
+                    be.d2h(&h_ctr.n_slow, &d_ctr->n_slow, sizeof(unsigned));
+                    be.sync();
+                    if (h_ctr.n_slow)
+                    {
+                        be.sort_pairs(d_skey[0], d_skey[1], d_sval[0], d_sval[1], h_ctr.n_slow);
+                        be.rank(F, d_skey[1], d_sval[1], h_ctr.n_slow);
+                    }
+                }
+            }
+            if (h_ctr.n_claim)
+                be.commit(F, h_ctr.n_claim);
+            for (size_t p = 0; p < np; p++)
+            {
+                NkTable &t = *tabs[p];
+                t.used += h_ctr.claims[p];
+                t.st.used = t.used;
+                t.st.ops += h_ctr.real_ops[p];
+                t.st.touches += h_ctr.touches[p];
+                lo[p] = hi[p];
+                hi[p] = T[p];
+            }
+            if (mode == NK_MODE_SCORE && np > 0)
+                tabs[0]->st.slow_events += h_ctr.n_slow; /* device-wide figure, kept on partition 0 */
+        }
+        return NK_OK;
+    }
+
+    int stage(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr, int is_paired, int n_tabs,
+              bool ignore_part)
+    {
+        if (nr > cfg.max_step_reads || seq_bytes > cfg.max_step_bytes)
+            return fail(NK_EINVAL, "step exceeds the limits given to nkd_create");
+        if (is_paired && (nr & 1))
+            return fail(NK_EINVAL, "paired step with an odd number of reads");
+        std::fill(T.begin(), T.end(), 0u);
+        for (size_t i = 0; i < nr; i++)
+        {
+            unsigned p = ignore_part ? 0 : reads[i].part;
+            if ((int)p >= n_tabs)
+                return fail(NK_EINVAL, "read names a partition that is not resident");
+            if ((int)reads[i].len < cfg.k)
+                return fail(NK_EINVAL, "read shorter than k in a step (the caller drops those, C:1430-1443)");
+            if ((reads[i].seq_off & 15u) || (size_t)reads[i].seq_off + reads[i].len > seq_bytes)
+                return fail(NK_EINVAL, "read offset not 16-byte aligned or out of the step buffer");
+            unsigned end = reads[i].op_base + (unsigned)(reads[i].len - cfg.k + 1);
+            if (end > T[p])
+                T[p] = end;
+        }
+        uint64_t tot = 0;
+        for (int p = 0; p < n_tabs; p++)
+            tot += T[p];
+        if (tot > cfg.max_step_ops)
+            return fail(NK_EINVAL, "step has more operations than max_step_ops");
+        be.h2d(d_seq, seq, seq_bytes);
+        be.h2d(d_reads, reads, nr * sizeof(nkd_read));
+        n_reads = nr;
+        paired = is_paired;
+        n_records = is_paired ? nr / 2 : nr;
+        h_reads = reads;
+        staged = true;
+        ran = false;
+        return NK_OK;
+    }
+
+    int seed_step(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr)
+    {
+        if (seeded)
+            return fail(NK_EINVAL, "nkd_seed_step after nkd_seed_finish");
+        int rc = stage(seq, seq_bytes, reads, nr, 0, 1, true);
+        if (rc)
+            return rc;
+        be.zero(d_invalid, n_reads + 1);
+        std::vector<NkTable *> tabs{&seed};
+        rc = run_ops(NK_MODE_SEED, tabs);
+        staged = false;
+        return rc;
+    }
+
+    int seed_finish()
+    {
+        if (seeded)
+            return fail(NK_EINVAL, "nkd_seed_finish called twice");
+        parts.resize(cfg.n_parts);
+        for (int p = 0; p < cfg.n_parts; p++)
+        {
+            NkTable &t = parts[p];
+            t = seed;
+            t.st = nkd_part_stats{};
+            t.st.capacity = seed.cap;
+            t.st.used = seed.used;
+            if (p == cfg.n_parts - 1)
+            { /* the last partition takes the seed table itself */
+                seed.tab = nullptr;
+                break;
+            }
+            t.tab = (NkSlot *)be.alloc(seed.cap * sizeof(NkSlot));
+            if (!t.tab)
+                return fail(NK_ENOMEM, "Memory allocation failed (partition table copy)");
+            be.d2d(t.tab, seed.tab, seed.cap * sizeof(NkSlot));
+        }
+        be.sync();
+        seeded = true;
+        return NK_OK;
+    }
+
+    int run_step()
+    {
+        if (!seeded)
+            return fail(NK_EINVAL, "nkd_run before nkd_seed_finish");
+        if (!staged)
+            return fail(NK_EINVAL, "nkd_run without nkd_stage");
+        be.begin_timer(0);
+        be.reset_timer(1);
+        be.zero(d_high, (n_reads + 1) * sizeof(unsigned));
+        be.zero(d_total, (n_reads + 1) * sizeof(unsigned));
+        be.zero(d_invalid, n_reads + 1);
+        std::vector<NkTable *> tabs;
+        for (auto &p : parts)
+            tabs.push_back(&p);
+        int rc = run_ops(NK_MODE_SCORE, tabs);
+        if (rc)
+            return rc;
+        be.zero(d_ctr, sizeof(NkCounters));
+        be.decide(make_run(NK_MODE_SCORE, 0, 0), (unsigned)n_records, paired, cfg.coverage, d_accept);
+        be.end_timer(0);
+        ran = true;
+        return NK_OK;
+    }
+
+    int fetch(uint8_t *accept, size_t nrec, int64_t *first_invalid)
+    {
+        if (!ran)
+            return fail(NK_EINVAL, "nkd_fetch without nkd_run");
+        if (nrec != n_records)
+            return fail(NK_EINVAL, "nkd_fetch: record count differs from the staged step");
+        be.d2h(accept, d_accept, nrec);
+        be.d2h(&h_ctr, d_ctr, 32);
+        be.sync();
+        last_total_ms = be.timer_ms(0);
+        last_probe_ms = be.timer_ms(1);
+        int stride = paired ? 2 : 1;
+        int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
+        if (first_invalid)
+            *first_invalid = (inv >= 0 && (size_t)inv < nrec) ? inv : -1;
+        for (size_t r = 0; r < nrec; r++)
+        {
+            if (inv >= 0 && (size_t)inv < nrec && r >= (size_t)inv)
+                break; /* the reference stops at the first non-DNA record */
+            nkd_part_stats &st = parts[h_reads[r * stride].part].st;
+            st.processed++;
+            if (accept[r])
+                st.printed++;
+            else
+                st.skipped++;
+        }
+        staged = false;
+        ran = false;
+        return NK_OK;
+    }
+
+    int export_table(const NkTable &t, uint64_t *keys, int32_t *counts, uint64_t capacity)
+    {
+        if (!t.tab)
+            return fail(NK_EINVAL, "table not resident");
+        if (capacity != t.cap)
+            return fail(NK_EINVAL, "export: capacity differs from the table's");
+        const size_t chunk = 1u << 20;
+        std::vector<NkSlot> buf(chunk);
+        for (uint64_t o = 0; o < t.cap; o += chunk)
+        {
+            size_t n = (size_t)std::min<uint64_t>(chunk, t.cap - o);
+            be.d2h(buf.data(), t.tab + o, n * sizeof(NkSlot));
+            be.sync();
+            for (size_t i = 0; i < n; i++)
+            {
+                keys[o + i] = buf[i].key;
+                counts[o + i] = buf[i].count;
+            }
+        }
+        return NK_OK;
+    }
+
+    int extract_keys(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr, uint64_t *keys_out,
+                     size_t n_ops, uint8_t *invalid_out)
+    {
+        int rc = stage(seq, seq_bytes, reads, nr, 0, 1, true);
+        if (rc)
+            return rc;
+        if (n_ops != T[0])
+            return fail(NK_EINVAL, "nkd_extract_keys: n_ops differs from the reads' window count");
+        be.release(d_keys_out);
+        d_keys_out = (unsigned long long *)be.alloc((n_ops + 1) * sizeof(unsigned long long));
+        if (!d_keys_out)
+            return fail(NK_ENOMEM, "nkd_extract_keys: allocation failed");
+        be.zero(d_keys_out, (n_ops + 1) * sizeof(unsigned long long));
+        be.zero(d_invalid, n_reads + 1);
+        be.zero(d_ctr, sizeof(NkCounters));
+        NkTable dummy = seed.tab ? seed : parts[0];
+        std::vector<NkTable *> tabs{&dummy};
+        std::vector<unsigned> lo(1, 0), hi(1, T[0]);
+        upload_parts(tabs, lo, hi);
+        be.probe(make_run(NK_MODE_KEYS, 0, 0));
+        be.d2h(keys_out, d_keys_out, n_ops * sizeof(unsigned long long));
+        if (invalid_out)
+            be.d2h(invalid_out, d_invalid, nr);
+        be.sync();
+        staged = false;
+        return NK_OK;
+    }
+};
+
+#endif /* NK_ORCHESTRATE_H */

@@ -1,0 +1,160 @@
+/*
+ * nk_emu.cpp -- TEST-ONLY CPU emulation backend for NkEngine (never part of the product library).
+ *
+ * It executes the same per-operation functions the sm_100a kernels execute (nk_core.h) and the same
+ * step orchestration (nk_orchestrate.h), but every "launch" visits its operations in a seeded random
+ * order, which is the freedom the GPU has.  Passing the oracle comparison under many seeds shows the
+ * parallel restatement is order-independent and equals the reference's sequential semantics.
+ * Built by tests/emu/Makefile into tests/emu/libnk_emu.so and loaded by tests/ only.
+ */
+#include <algorithm>
+#include <numeric>
+#include <random>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../nomalise_kmers_multi_large_b200/csrc/nk_core.h"
+
+struct EmuBackend
+{
+    std::mt19937_64 rng;
+    int init(int, std::string &)
+    {
+        const char *s = getenv("NK_EMU_SEED");
+        rng.seed(s ? strtoull(s, nullptr, 10) : 12345ull);
+        return 0;
+    }
+    void shutdown() {}
+    void *alloc(size_t n) { return malloc(n ? n : 1); }
+    void release(void *p) { free(p); }
+    void zero(void *p, size_t n) { memset(p, 0, n); }
+    void h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); }
+    void d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); }
+    void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+    void sync() {}
+    bool prepare_sort(size_t, std::string &) { return true; }
+    void begin_timer(int) {}
+    void end_timer(int) {}
+    void reset_timer(int) {}
+    float timer_ms(int) { return 0.f; }
+
+    std::vector<unsigned> order(size_t n)
+    {
+        std::vector<unsigned> v(n);
+        std::iota(v.begin(), v.end(), 0u);
+        std::shuffle(v.begin(), v.end(), rng);
+        return v;
+    }
+
+    void probe(const NkRun &P)
+    {
+        struct Op
+        {
+            unsigned read, w;
+        };
+        std::vector<Op> ops;
+        for (unsigned r = 0; r < P.n_reads; r++)
+        {
+            const NkRead &rd = P.reads[r];
+            if (P.mode != NK_MODE_COUNT)
+                for (unsigned i = 0; i < rd.len; i++)
+                {
+                    unsigned char b = P.seq[rd.seq_off + i];
+                    if (b != 'A' && b != 'C' && b != 'G' && b != 'T' && b != 'N')
+                        P.invalid[r] = 1;
+                }
+            for (unsigned w = 0; w + P.k <= rd.len; w++)
+                ops.push_back({r, w});
+        }
+        std::shuffle(ops.begin(), ops.end(), rng);
+        for (auto &op : ops)
+        {
+            const NkRead &rd = P.reads[op.read];
+            unsigned part = (P.mode == NK_MODE_SEED || P.mode == NK_MODE_KEYS) ? 0u : rd.part;
+            const NkPart &pd = P.parts[part];
+            unsigned t = rd.op_base + op.w;
+            if (t < pd.lo || t >= pd.hi)
+                continue;
+            unsigned long long key = nk_window_key_ascii(P.seq + rd.seq_off + op.w, P.k, P.canonical);
+            if (P.mode == NK_MODE_KEYS)
+            {
+                P.keys_out[t] = key;
+                continue;
+            }
+            if (key == 0)
+                continue;
+            P.ctr->real_ops[part] += 1;
+            if (P.mode == NK_MODE_COUNT)
+                continue;
+            P.total[op.read] += (unsigned)P.delta;
+            int high = 0;
+            P.ctr->touches[part] += nk_probe_op(P, pd, part, key, t, op.read, high);
+            P.high[op.read] += (unsigned)high;
+        }
+    }
+    void open_ops(const NkRun &P)
+    {
+        unsigned n = std::min(P.ctr->n_open, P.open_cap);
+        for (unsigned idx : order(n))
+        {
+            int high = 0;
+            unsigned touches = nk_open_op(P, idx, high);
+            P.ctr->touches[P.open[idx].part] += touches;
+            P.high[P.open[idx].read] += (unsigned)high;
+        }
+    }
+    void apply(const NkRun &P, unsigned n)
+    {
+        for (unsigned i : order(n))
+            nk_apply_op(P, i);
+    }
+    void classify(const NkRun &P, unsigned n)
+    {
+        for (unsigned i : order(n))
+            nk_classify_op(P, i);
+    }
+    void sort_pairs(unsigned long long *kin, unsigned long long *kout, unsigned long long *vin, unsigned long long *vout,
+                    unsigned n)
+    {
+        std::vector<unsigned> idx(n);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::sort(idx.begin(), idx.end(), [&](unsigned a, unsigned b) { return kin[a] < kin[b]; });
+        for (unsigned i = 0; i < n; i++)
+        {
+            kout[i] = kin[idx[i]];
+            vout[i] = vin[idx[i]];
+        }
+    }
+    void rank(const NkRun &P, const unsigned long long *keys, const unsigned long long *vals, unsigned n)
+    {
+        for (unsigned i : order(n))
+            nk_rank_op(P, keys, vals, n, i);
+    }
+    void commit(const NkRun &P, unsigned n)
+    {
+        for (unsigned i : order(n))
+            nk_commit_op(P, i);
+    }
+    void untag(const NkRun &P, unsigned n)
+    {
+        for (unsigned i : order(n))
+            nk_untag_op(P, i);
+    }
+    void rehash(const NkSlot *old_tab, unsigned long long cap, NkSlot *nt, unsigned long long ncap, unsigned long long nmagic)
+    {
+        for (unsigned i : order((size_t)cap))
+            nk_rehash_place_op(old_tab, i, nt, ncap, nmagic);
+        for (unsigned long long j = 0; j < ncap; j++)
+            nk_rehash_fill_op(old_tab, nt, j);
+    }
+    void decide(const NkRun &P, unsigned n_records, int paired, float coverage, unsigned char *accept)
+    {
+        for (unsigned r : order(n_records))
+            nk_decide_op(P, r, paired, coverage, accept);
+    }
+};
+
+#define NK_BACKEND EmuBackend
+#include "../../nomalise_kmers_multi_large_b200/csrc/nk_engine_api.h"

@@ -1,0 +1,108 @@
+"""Shared scenarios: drive a device engine (CUDA build or the test-only emulation) and the oracle's
+sequential table with the same reads and compare everything observable: accept flags in record
+order, the whole table (keys AND counts of every slot, ghost counts included), used, capacity."""
+import numpy as np
+
+from nomalise_kmers_multi_large_b200 import capi
+from tests import oracle_lib as ol
+
+BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def make_genome(rng, n, repeat_frac=0.2):
+    g = BASES[rng.integers(0, 4, n)].copy()
+    # low-complexity stretches give zero keys (poly-A; poly-T under --canonical) and hot k-mers
+    for _ in range(int(n * repeat_frac / 40)):
+        p = int(rng.integers(0, n - 40))
+        g[p:p + 40] = BASES[int(rng.integers(0, 4))]
+    return g
+
+
+def sample_read(rng, genome, lo, hi, err=0.01, n_rate=0.01):
+    L = int(rng.integers(lo, hi + 1))
+    p = int(rng.integers(0, len(genome) - L))
+    r = genome[p:p + L].copy()
+    e = rng.random(L) < err
+    r[e] = BASES[rng.integers(0, 4, int(e.sum()))]
+    if rng.random() < n_rate:
+        r[int(rng.integers(0, L))] = ord("N")
+    return r.tobytes()
+
+
+def revcomp(s: bytes) -> bytes:
+    return s.translate(bytes.maketrans(b"ACGTN", b"TGCAN"))[::-1]
+
+
+def run_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_parts=2, cap0=4099, genome_len=3000,
+             n_seed_reads=200, steps=4, records_per_step=150, paired=True, read_len=(40, 120), err=0.01,
+             max_step_ops=None):
+    rng = np.random.default_rng(seed)
+    genome = make_genome(rng, genome_len)
+    lo, hi = read_len
+    lo = max(lo, k)  # records shorter than k never reach the engine (C:1430-1443)
+    ops_bound = (records_per_step * n_parts * 2 + n_seed_reads) * (hi - k + 1) + 64
+    eng = capi.Engine(k=k, canonical=canonical, depth_per_part=depth, coverage=coverage, n_parts=n_parts,
+                      capacity0=cap0, max_step_reads=4 * (records_per_step * n_parts * 2 + n_seed_reads) + 8,
+                      max_step_bytes=(records_per_step * n_parts * 2 + n_seed_reads) * (hi + 32) + 64,
+                      max_step_ops=max_step_ops or ops_bound, lib=lib)
+    try:
+        # ---- seeding: one shared table, count 0 (C:1322-1373, C:1501-1537)
+        seed_reads = [sample_read(rng, genome, max(lo, k + 1), hi, err) for _ in range(n_seed_reads)]
+        otab = ol.OracleTable(cap0)
+        half = n_seed_reads // 2
+        for chunk in (seed_reads[:half], seed_reads[half:]):
+            if chunk:
+                buf, descs, _ = capi.pack_reads(chunk, None, k)
+                eng.seed_step(buf, descs)
+            for s in chunk:
+                otab.seed(s, k, canonical)
+        st = eng.seed_stats()
+        assert (st["capacity"], st["used"]) == (otab.cap, otab.used), ("seed table", st, otab.cap, otab.used)
+        ek, ec = eng.seed_export()
+        okk, okc = otab.export()
+        assert np.array_equal(ek, okk), "seed keys differ"
+        assert np.array_equal(ec, okc), "seed counts differ"
+        eng.seed_finish()
+        otabs = [otab.clone() for _ in range(n_parts)]
+        # ---- steps
+        info = {"slow_events": 0, "expansions": 0, "ops": 0, "touches": 0}
+        for step in range(steps):
+            seqs, parts, per_part = [], [], []
+            for p in range(n_parts):
+                recs = []
+                for _ in range(records_per_step):
+                    f = sample_read(rng, genome, lo, hi, err)
+                    if paired:
+                        recs.append((f, revcomp(sample_read(rng, genome, lo, hi, err))))
+                        seqs += [recs[-1][0], recs[-1][1]]
+                        parts += [p, p]
+                    else:
+                        recs.append(f)
+                        seqs.append(f)
+                        parts.append(p)
+                per_part.append(recs)
+            buf, descs, _ = capi.pack_reads(seqs, parts, k)
+            acc, inv = eng.step(buf, descs, paired)
+            assert inv == -1
+            want = np.concatenate([ol.oracle_records(otabs[p], per_part[p], k, canonical, depth, coverage, paired)
+                                   for p in range(n_parts)])
+            assert np.array_equal(acc, want), f"accept flags differ at step {step}: {np.flatnonzero(acc != want)[:10]}"
+            for p in range(n_parts):
+                st = eng.part_stats(p)
+                assert (st["capacity"], st["used"]) == (otabs[p].cap, otabs[p].used), (step, p, st)
+                ek, ec = eng.export(p)
+                okk, okc = otabs[p].export()
+                assert np.array_equal(ek, okk), f"keys differ step {step} part {p}"
+                bad = np.flatnonzero(ec != okc)
+                assert bad.size == 0, f"counts differ step {step} part {p}: slots {bad[:8]} got {ec[bad[:8]]} want {okc[bad[:8]]}"
+        for p in range(n_parts):
+            st = eng.part_stats(p)
+            info["slow_events"] += st["slow_events"]
+            info["expansions"] += st["expansions"]
+            info["ops"] += st["ops"]
+            info["touches"] += st["touches"]
+            assert st["ops"] == otabs[p].ops, ("ops", st["ops"], otabs[p].ops)  # clones count from 0
+            assert st["touches"] == otabs[p].touches, ("touches", st["touches"], otabs[p].touches)
+        return info
+    finally:
+        eng.close()
