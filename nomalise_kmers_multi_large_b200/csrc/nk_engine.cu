@@ -1,0 +1,396 @@
+/*
+ * nk_engine.cu -- sm_100a kernels and the CUDA backend of the device engine (nkd_* in include/nk_b200.h).
+ *
+ * Kernels (all integer, HBM/L2-latency bound; no tensor-core work exists on this path):
+ *   k_probe    warp per read: coalesced 16-byte loads of the ASCII sequence, 2-bit packing in shared
+ *              memory, per-lane window extraction (+ reverse-complement minimum), then the table probe
+ *              of nk_core.h: one 16-byte L2-only gather per visited slot, fire-and-forget REDs on
+ *              saturated counters                       [encode_kmer_plain C:1118, get_canonical_kmer
+ *                                                        C:1175, is_valid_sequence_* C:1404-1457,
+ *                                                        store_kmer C:929-1053, sequence_to_hash C:1459]
+ *   k_open     thread per deferred operation (met a slot that was empty at step start)
+ *   k_apply / k_classify / k_rank   pending increments, threshold classification, time ranking
+ *   k_commit / k_untag              store claimed keys / forget an abandoned run
+ *   k_rehash_place / k_rehash_fill  exact table growth                  [expand_local_hash_table C:1055]
+ *   k_decide   float32 ratio test per record                                          [C:1641-1646]
+ * The only library call is cub::DeviceRadixSort for the (rare) time-ordered slow path.
+ */
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "nk_core.h"
+#include "../../include/nk_b200.h"
+
+#define NK_WARPS 8
+#define NK_THREADS (NK_WARPS * 32)
+#define NK_WORDS 68 /* 64 packed words (1024 bases) + zero padding read by the last windows */
+
+/* 16 ASCII bases -> 32 bits, first base in the top bits.  A0 C1 G2 T3; N packs as A (C:1406); bytes
+ * beyond nb are ignored.  bad collects bytes outside ACGTN (C:1144-1158). */
+__device__ __forceinline__ unsigned nk_pack16(uint4 v, int nb, unsigned &bad)
+{
+    unsigned in[4] = {v.x, v.y, v.z, v.w};
+    unsigned out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        int n = nb - 4 * j;
+        unsigned mask = n >= 4 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
+        unsigned x = in[j] & mask;
+        unsigned ok = __vcmpeq4(x, 0x41414141u) | __vcmpeq4(x, 0x43434343u) | __vcmpeq4(x, 0x47474747u) |
+                      __vcmpeq4(x, 0x54545454u) | __vcmpeq4(x, 0x4E4E4E4Eu);
+        bad |= (~ok) & mask;
+        unsigned codes = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+        unsigned y = __byte_perm(codes, 0, 0x0123);
+        unsigned p = (y | (y >> 6) | (y >> 12) | (y >> 18)) & 0xFFu;
+        out = (out << 8) | p;
+    }
+    return out;
+}
+
+__device__ __forceinline__ unsigned long long nk_window_key_packed(const unsigned *words, int w, int k, int canonical)
+{
+    int wi = w >> 4, s = (w & 15) * 2;
+    unsigned long long hi = ((unsigned long long)words[wi] << 32) | words[wi + 1];
+    unsigned long long v = s ? ((hi << s) | ((unsigned long long)words[wi + 2] >> (32 - s))) : hi;
+    unsigned long long x = v >> (64 - 2 * k);
+    if (canonical)
+    {
+        unsigned long long r = nk_revcomp(x, k);
+        x = r < x ? r : x;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
+{
+    __shared__ unsigned s_words[NK_WARPS][NK_WORDS];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned *words = s_words[warp];
+    const unsigned nwarps = gridDim.x * NK_WARPS;
+    const bool one_part = (P.mode == NK_MODE_SEED || P.mode == NK_MODE_KEYS);
+    for (unsigned r = blockIdx.x * NK_WARPS + warp; r < P.n_reads; r += nwarps)
+    {
+        const uint4 rraw = __ldg(reinterpret_cast<const uint4 *>(P.reads + r));
+        const unsigned seq_off = rraw.x, op_base = rraw.y, len = rraw.z & 0xFFFFu;
+        const unsigned part = one_part ? 0u : (rraw.z >> 16);
+        const NkPart pd = P.parts[part];
+        const int nwin = (int)len - P.k + 1;
+        if (op_base + (unsigned)nwin <= pd.lo || op_base >= pd.hi)
+            continue;
+        const unsigned nchunks = (len + 15u) >> 4;
+        unsigned bad = 0;
+        for (unsigned c = lane; c < nchunks + 2u; c += 32u)
+        {
+            unsigned w = 0;
+            if (c < nchunks)
+            {
+                uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.seq + seq_off) + c);
+                w = nk_pack16(v, (int)len - 16 * (int)c, bad);
+            }
+            words[c] = w;
+        }
+        __syncwarp();
+        if (P.mode != NK_MODE_COUNT && __any_sync(0xFFFFFFFFu, bad != 0) && lane == 0)
+            P.invalid[r] = 1;
+        unsigned n_real = 0, touches = 0;
+        int high = 0;
+        for (int w0 = 0; w0 < nwin; w0 += 32)
+        {
+            const int w = w0 + (int)lane;
+            const unsigned t = op_base + (unsigned)w;
+            const bool live = w < nwin && t >= pd.lo && t < pd.hi;
+            if (!live)
+                continue;
+            const unsigned long long key = nk_window_key_packed(words, w, P.k, P.canonical);
+            if (P.mode == NK_MODE_KEYS)
+            {
+                P.keys_out[t] = key;
+                continue;
+            }
+            if (key == 0) /* all-A window (or all-T under --canonical): ignored entirely, C:1483 */
+                continue;
+            n_real++;
+            if (P.mode != NK_MODE_COUNT)
+                touches += nk_probe_op(P, pd, part, key, t, r, high);
+        }
+        __syncwarp();
+        n_real = __reduce_add_sync(0xFFFFFFFFu, n_real);
+        touches = __reduce_add_sync(0xFFFFFFFFu, touches);
+        high = __reduce_add_sync(0xFFFFFFFFu, high);
+        if (lane == 0 && P.mode != NK_MODE_KEYS)
+        {
+            if (n_real)
+                atomicAdd(&P.ctr->real_ops[part], (unsigned long long)n_real);
+            if (P.mode != NK_MODE_COUNT)
+            {
+                if (touches)
+                    atomicAdd(&P.ctr->touches[part], (unsigned long long)touches);
+                if (n_real)
+                    atomicAdd(&P.total[r], (unsigned)(P.delta * (int)n_real));
+                if (high)
+                    atomicAdd(&P.high[r], (unsigned)high);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_open(const NkRun P)
+{
+    const unsigned n = min(P.ctr->n_open, P.open_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        int high = 0;
+        unsigned touches = nk_open_op(P, i, high);
+        if (touches)
+            atomicAdd(&P.ctr->touches[P.open[i].part], (unsigned long long)touches);
+        if (high)
+            atomicAdd(&P.high[P.open[i].read], (unsigned)high);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_apply(const NkRun P, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        nk_apply_op(P, i);
+}
+__global__ void __launch_bounds__(256) k_classify(const NkRun P, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        nk_classify_op(P, i);
+}
+__global__ void __launch_bounds__(256) k_rank(const NkRun P, const unsigned long long *keys, const unsigned long long *vals,
+                                             unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        nk_rank_op(P, keys, vals, n, i);
+}
+__global__ void __launch_bounds__(256) k_commit(const NkRun P, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        nk_commit_op(P, i);
+}
+__global__ void __launch_bounds__(256) k_untag(const NkRun P, unsigned n)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        nk_untag_op(P, i);
+}
+__global__ void __launch_bounds__(256) k_rehash_place(const NkSlot *old_tab, unsigned long long cap, NkSlot *nt,
+                                                     unsigned long long ncap, unsigned long long nmagic)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        nk_rehash_place_op(old_tab, i, nt, ncap, nmagic);
+}
+__global__ void __launch_bounds__(256) k_rehash_fill(const NkSlot *old_tab, NkSlot *nt, unsigned long long ncap)
+{
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < ncap;
+         j += (unsigned long long)gridDim.x * blockDim.x)
+        nk_rehash_fill_op(old_tab, nt, j);
+}
+__global__ void __launch_bounds__(256) k_decide(const NkRun P, unsigned n_records, int paired, float coverage,
+                                               unsigned char *accept)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_records; i += gridDim.x * blockDim.x)
+        nk_decide_op(P, i, paired, coverage, accept);
+}
+
+/* ------------------------------------------------------------------ backend */
+
+struct CudaBackend
+{
+    int dev = -1, sms = 148;
+    cudaStream_t stream = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    std::string cuda_err;
+    struct Timer
+    {
+        std::vector<cudaEvent_t> ev; /* start/stop pairs */
+        size_t used = 0;
+    } timers[2];
+
+    bool ok(cudaError_t e, const char *what)
+    {
+        if (e == cudaSuccess)
+            return true;
+        if (cuda_err.empty())
+            cuda_err = std::string(what) + ": " + cudaGetErrorString(e);
+        return false;
+    }
+    bool failed(std::string &msg)
+    {
+        ok(cudaGetLastError(), "kernel launch");
+        if (cuda_err.empty())
+            return false;
+        msg = cuda_err;
+        return true;
+    }
+    int init(int device, std::string &err)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        {
+            err = "no CUDA device: the B200 engine has no CPU fallback";
+            return NK_ENODEVICE;
+        }
+        if (device < 0 || device >= n)
+        {
+            err = "CUDA device ordinal out of range";
+            return NK_ENODEVICE;
+        }
+        dev = device;
+        if (!ok(cudaSetDevice(dev), "cudaSetDevice") ||
+            !ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+        {
+            err = cuda_err;
+            return NK_ENODEVICE;
+        }
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return NK_OK;
+    }
+    void shutdown()
+    {
+        if (dev < 0)
+            return;
+        cudaSetDevice(dev);
+        for (auto &t : timers)
+            for (auto e : t.ev)
+                cudaEventDestroy(e);
+        if (sort_tmp)
+            cudaFree(sort_tmp);
+        if (stream)
+            cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+    void *alloc(size_t n)
+    {
+        cudaSetDevice(dev);
+        void *p = nullptr;
+        if (cudaMalloc(&p, n ? n : 16) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    void release(void *p)
+    {
+        if (p)
+        {
+            cudaSetDevice(dev);
+            cudaFree(p);
+        }
+    }
+    void zero(void *p, size_t n) { ok(cudaMemsetAsync(p, 0, n, stream), "cudaMemsetAsync"); }
+    void h2d(void *d, const void *h, size_t n) { ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream), "H2D copy"); }
+    void d2h(void *h, const void *d, size_t n) { ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream), "D2H copy"); }
+    void d2d(void *d, const void *s, size_t n) { ok(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream), "D2D copy"); }
+    void sync() { ok(cudaStreamSynchronize(stream), "stream synchronize"); }
+
+    bool prepare_sort(size_t n, std::string &err)
+    {
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                        (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n, 0, 64,
+                                        stream);
+        sort_tmp = alloc(bytes);
+        sort_tmp_bytes = bytes;
+        if (!sort_tmp)
+        {
+            err = "cannot allocate sort scratch";
+            return false;
+        }
+        return true;
+    }
+
+    void begin_timer(int i)
+    {
+        Timer &t = timers[i];
+        if (t.used + 2 > t.ev.size())
+        {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            t.ev.push_back(a);
+            t.ev.push_back(b);
+        }
+        cudaEventRecord(t.ev[t.used], stream);
+    }
+    void end_timer(int i)
+    {
+        Timer &t = timers[i];
+        cudaEventRecord(t.ev[t.used + 1], stream);
+        t.used += 2;
+    }
+    void reset_timer(int i) { timers[i].used = 0; }
+    float timer_ms(int i)
+    {
+        Timer &t = timers[i];
+        float sum = 0;
+        for (size_t j = 0; j + 1 < t.used; j += 2)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.ev[j], t.ev[j + 1]) == cudaSuccess)
+                sum += ms;
+        }
+        t.used = 0;
+        return sum;
+    }
+
+    /* grids are multiples of the SM count: persistent grid-stride loops, 8 CTAs of 256 threads per SM */
+    unsigned grid_for(unsigned long long n, unsigned per_block)
+    {
+        unsigned long long need = (n + per_block - 1) / per_block;
+        unsigned long long cap = (unsigned long long)sms * 8ull;
+        if (need >= cap)
+            return (unsigned)cap;
+        unsigned long long g = ((need + sms - 1) / sms) * sms;
+        return (unsigned)(g ? g : sms);
+    }
+
+    void probe(const NkRun &P)
+    {
+        if (P.n_reads)
+            k_probe<<<grid_for(P.n_reads, NK_WARPS), NK_THREADS, 0, stream>>>(P);
+    }
+    void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P); }
+    void apply(const NkRun &P, unsigned n) { k_apply<<<grid_for(n, 256), 256, 0, stream>>>(P, n); }
+    void classify(const NkRun &P, unsigned n) { k_classify<<<grid_for(n, 256), 256, 0, stream>>>(P, n); }
+    void sort_pairs(unsigned long long *kin, unsigned long long *kout, unsigned long long *vin, unsigned long long *vout,
+                    unsigned n)
+    {
+        size_t bytes = sort_tmp_bytes;
+        ok(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long *)kin, kout,
+                                           (const unsigned long long *)vin, vout, (int)n, 0, 64, stream),
+           "radix sort");
+    }
+    void rank(const NkRun &P, const unsigned long long *keys, const unsigned long long *vals, unsigned n)
+    {
+        k_rank<<<grid_for(n, 256), 256, 0, stream>>>(P, keys, vals, n);
+    }
+    void commit(const NkRun &P, unsigned n) { k_commit<<<grid_for(n, 256), 256, 0, stream>>>(P, n); }
+    void untag(const NkRun &P, unsigned n)
+    {
+        if (n)
+            k_untag<<<grid_for(n, 256), 256, 0, stream>>>(P, n);
+    }
+    void rehash(const NkSlot *old_tab, unsigned long long cap, NkSlot *nt, unsigned long long ncap, unsigned long long nmagic)
+    {
+        k_rehash_place<<<grid_for(cap, 256), 256, 0, stream>>>(old_tab, cap, nt, ncap, nmagic);
+        k_rehash_fill<<<grid_for(ncap, 256), 256, 0, stream>>>(old_tab, nt, ncap);
+    }
+    void decide(const NkRun &P, unsigned n_records, int paired, float coverage, unsigned char *accept)
+    {
+        if (n_records)
+            k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept);
+    }
+};
+
+#define NK_BACKEND CudaBackend
+#include "nk_engine_api.h"

@@ -15,6 +15,21 @@ struct nkd_engine
 
 static_assert(sizeof(nkd_read) == sizeof(NkRead), "nkd_read layout");
 
+/* a CUDA error anywhere in the call turns the result into NK_ENODEVICE (there is nothing to fall back to) */
+static inline int nkd_done(nkd_engine *h, int rc)
+{
+    std::string m;
+    if (h->e.be.failed(m))
+    {
+        if (rc == NK_OK)
+        {
+            h->e.err = m;
+            rc = NK_ENODEVICE;
+        }
+    }
+    return rc;
+}
+
 extern "C" {
 
 int nkd_create(const nkd_config *cfg, nkd_engine **out)
@@ -23,6 +38,7 @@ int nkd_create(const nkd_config *cfg, nkd_engine **out)
         return NK_EINVAL;
     nkd_engine *h = new nkd_engine();
     int rc = h->e.create(*cfg);
+    rc = nkd_done(h, rc);
     *out = h; /* kept on failure so that nkd_last_error can be read; caller still destroys it */
     return rc;
 }
@@ -39,9 +55,9 @@ const char *nkd_last_error(const nkd_engine *h) { return h ? h->e.err.c_str() : 
 
 int nkd_seed_step(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads)
 {
-    return h->e.seed_step(seq, seq_bytes, reads, n_reads);
+    return nkd_done(h, h->e.seed_step(seq, seq_bytes, reads, n_reads));
 }
-int nkd_seed_finish(nkd_engine *h) { return h->e.seed_finish(); }
+int nkd_seed_finish(nkd_engine *h) { return nkd_done(h, h->e.seed_finish()); }
 int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)
 {
     *out = h->e.seed.st;
@@ -51,18 +67,18 @@ int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)
 }
 int nkd_seed_export(nkd_engine *h, uint64_t *keys, int32_t *counts, uint64_t capacity)
 {
-    return h->e.export_table(h->e.seed, keys, counts, capacity);
+    return nkd_done(h, h->e.export_table(h->e.seed, keys, counts, capacity));
 }
 int nkd_stage(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads, int paired)
 {
     if (!h->e.seeded)
         return h->e.fail(NK_EINVAL, "nkd_stage before nkd_seed_finish");
-    return h->e.stage(seq, seq_bytes, reads, n_reads, paired, h->e.cfg.n_parts, false);
+    return nkd_done(h, h->e.stage(seq, seq_bytes, reads, n_reads, paired, h->e.cfg.n_parts, false));
 }
-int nkd_run(nkd_engine *h) { return h->e.run_step(); }
+int nkd_run(nkd_engine *h) { return nkd_done(h, h->e.run_step()); }
 int nkd_fetch(nkd_engine *h, uint8_t *accept, size_t n_records, int64_t *first_invalid)
 {
-    return h->e.fetch(accept, n_records, first_invalid);
+    return nkd_done(h, h->e.fetch(accept, n_records, first_invalid));
 }
 int nkd_last_run_ms(nkd_engine *h, float *total_ms, float *probe_ms)
 {
@@ -85,12 +101,12 @@ int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_
 {
     if (part < 0 || part >= (int)h->e.parts.size())
         return h->e.fail(NK_EINVAL, "no such partition");
-    return h->e.export_table(h->e.parts[part], keys, counts, capacity);
+    return nkd_done(h, h->e.export_table(h->e.parts[part], keys, counts, capacity));
 }
 int nkd_extract_keys(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
                      uint64_t *keys_out, size_t n_ops, uint8_t *invalid_out)
 {
-    return h->e.extract_keys(seq, seq_bytes, reads, n_reads, keys_out, n_ops, invalid_out);
+    return nkd_done(h, h->e.extract_keys(seq, seq_bytes, reads, n_reads, keys_out, n_ops, invalid_out));
 }
 
 } /* extern "C" */

@@ -425,6 +425,8 @@ class NkEngine
             unsigned p = ignore_part ? 0 : reads[i].part;
             if ((int)p >= n_tabs)
                 return fail(NK_EINVAL, "read names a partition that is not resident");
+            if (reads[i].len >= NK_MAX_LINE)
+                return fail(NK_EINVAL, "read longer than 1023 bases (the reference cuts lines there, C:397)");
             if ((int)reads[i].len < cfg.k)
                 return fail(NK_EINVAL, "read shorter than k in a step (the caller drops those, C:1430-1443)");
             if ((reads[i].seq_off & 15u) || (size_t)reads[i].seq_off + reads[i].len > seq_bytes)

@@ -27,6 +27,7 @@ struct EmuBackend
         return 0;
     }
     void shutdown() {}
+    bool failed(std::string &) { return false; }
     void *alloc(size_t n) { return malloc(n ? n : 1); }
     void release(void *p) { free(p); }
     void zero(void *p, size_t n) { memset(p, 0, n); }

@@ -1,0 +1,34 @@
+"""CPU checks of the parallel table algorithm: the per-operation code the sm_100a kernels run
+(nk_core.h) and the step orchestration (nk_orchestrate.h), executed in shuffled order by the
+test-only emulation backend, must equal the oracle's sequential table bit for bit."""
+import os
+
+import pytest
+
+from tests import engine_cases as ec
+
+CASES = [
+    dict(k=15, canonical=False, depth=3, cap0=4099, paired=True, n_parts=2),
+    dict(k=15, canonical=True, depth=2, cap0=2003, paired=False, n_parts=3),
+    dict(k=25, canonical=True, depth=4, cap0=8191, paired=True, n_parts=1),
+    dict(k=5, canonical=False, depth=2, cap0=1024, paired=True, n_parts=2),       # 4^k clamp (C:678-684)
+    dict(k=31, canonical=False, depth=5, cap0=1009, paired=True, n_parts=2),      # growth inside steps
+    dict(k=21, canonical=True, depth=12, cap0=3001, paired=True, n_parts=1),
+    dict(k=7, canonical=True, depth=3, cap0=16384, paired=False, n_parts=2),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"k{c['k']}c{int(c['canonical'])}d{c['depth']}cap{c['cap0']}")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_emulated_engine_matches_oracle(emu_lib, case, seed, monkeypatch):
+    monkeypatch.setenv("NK_EMU_SEED", str(seed * 7919))
+    info = ec.run_case(emu_lib, seed=seed, steps=3, records_per_step=60, **case)
+    assert info["ops"] > 0
+
+
+def test_emulated_engine_scratch_overflow_is_exact(emu_lib, monkeypatch):
+    """Lists too small for a step: the run is undone (replayed with -1), the window halved, results unchanged."""
+    monkeypatch.setenv("NKB200_OPEN_FRAC", "0.02")
+    monkeypatch.setenv("NKB200_PEND_FRAC", "0.03")
+    info = ec.run_case(emu_lib, seed=3, k=15, canonical=True, depth=3, cap0=4099, n_parts=2, steps=2, records_per_step=80)
+    assert info["ops"] > 0
