@@ -96,7 +96,8 @@ const char *nkd_last_error(const nkd_engine *e);
 
 /* sequence_to_hash_zero over a batch of seed reads (C:1501-1537, C:1352); reads[i].part is ignored.
  * n_ops = op_base + windows of the last read. */
-int nkd_seed_step(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads);
+int nkd_seed_step(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
+                  int64_t *first_invalid);
 /* copy_hash_table for every resident partition (C:908-927, C:2279); frees the seed table */
 int nkd_seed_finish(nkd_engine *e);
 int nkd_seed_stats(nkd_engine *e, nkd_part_stats *out);
@@ -109,6 +110,20 @@ int nkd_seed_export(nkd_engine *e, uint64_t *keys, int32_t *counts, uint64_t cap
  * 1 = emit, 0 = skip) and first_invalid (record index of the first non-ACGT sequence or -1,
  * which the caller turns into the reference's FATAL exit, C:1445-1454). */
 int nkd_stage(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads, int paired);
+/* the same for a step gathered from several host segments (one per partition in the host pipeline):
+ * segment s holds reads[s][0..n_reads[s]) whose seq_off index the step-wide buffer `seq_base`, of which
+ * only [seq_lo[s], seq_hi[s]) is copied.  Read/record numbering is the concatenation of the segments. */
+typedef struct
+{
+    const nkd_read *reads;
+    size_t n_reads;
+    size_t seq_lo, seq_hi;
+} nkd_segment;
+int nkd_stage_segments(nkd_engine *e, const uint8_t *seq_base, const nkd_segment *segs, int n_segs, int paired);
+/* page-locked host memory for the staging buffers (cudaMallocHost / cudaFreeHost) */
+void *nkd_alloc_pinned(size_t bytes);
+void nkd_free_pinned(void *p);
+int nkd_device_count(void);
 int nkd_run(nkd_engine *e);
 int nkd_fetch(nkd_engine *e, uint8_t *accept, size_t n_records, int64_t *first_invalid);
 /* time of the last nkd_run on the device, from CUDA events on the engine's stream */

@@ -77,7 +77,8 @@ class Totals(C.Structure):
 
 ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step", "nkd_seed_finish", "nkd_seed_stats",
                   "nkd_seed_export", "nkd_stage", "nkd_run", "nkd_fetch", "nkd_last_run_ms", "nkd_part_stats_get",
-                  "nkd_export", "nkd_extract_keys"]
+                  "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
+                  "nkd_device_count"]
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
                     "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main"]
@@ -90,7 +91,7 @@ def _declare_engine(lib):
     lib.nkd_destroy.restype = None
     lib.nkd_last_error.argtypes = [vp]
     lib.nkd_last_error.restype = C.c_char_p
-    lib.nkd_seed_step.argtypes = [vp, u8p, sz, vp, sz]
+    lib.nkd_seed_step.argtypes = [vp, u8p, sz, vp, sz, C.POINTER(C.c_int64)]
     lib.nkd_seed_finish.argtypes = [vp]
     lib.nkd_seed_stats.argtypes = [vp, C.POINTER(PartStats)]
     lib.nkd_seed_export.argtypes = [vp, vp, vp, C.c_uint64]
@@ -203,7 +204,9 @@ class Engine:
         self.close()
 
     def seed_step(self, buf: np.ndarray, descs: np.ndarray):
-        self._check(self.lib.nkd_seed_step(self.h, buf.ctypes.data, buf.size, descs.ctypes.data, len(descs)))
+        inv = C.c_int64(-1)
+        self._check(self.lib.nkd_seed_step(self.h, buf.ctypes.data, buf.size, descs.ctypes.data, len(descs), C.byref(inv)))
+        return inv.value
 
     def seed_finish(self):
         self._check(self.lib.nkd_seed_finish(self.h))

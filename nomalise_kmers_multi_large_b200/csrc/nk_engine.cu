@@ -394,3 +394,29 @@ struct CudaBackend
 
 #define NK_BACKEND CudaBackend
 #include "nk_engine_api.h"
+
+extern "C" void *nkd_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void nkd_free_pinned(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+extern "C" int nkd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}

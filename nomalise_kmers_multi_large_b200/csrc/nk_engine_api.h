@@ -53,9 +53,16 @@ void nkd_destroy(nkd_engine *h)
 
 const char *nkd_last_error(const nkd_engine *h) { return h ? h->e.err.c_str() : "null engine"; }
 
-int nkd_seed_step(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads)
+int nkd_seed_step(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
+                  int64_t *first_invalid)
 {
-    return nkd_done(h, h->e.seed_step(seq, seq_bytes, reads, n_reads));
+    return nkd_done(h, h->e.seed_step(seq, seq_bytes, reads, n_reads, first_invalid));
+}
+int nkd_stage_segments(nkd_engine *h, const uint8_t *seq_base, const nkd_segment *segs, int n_segs, int paired)
+{
+    if (!h->e.seeded)
+        return h->e.fail(NK_EINVAL, "nkd_stage_segments before nkd_seed_finish");
+    return nkd_done(h, h->e.stage_segments(seq_base, segs, n_segs, paired, h->e.cfg.n_parts, false));
 }
 int nkd_seed_finish(nkd_engine *h) { return nkd_done(h, h->e.seed_finish()); }
 int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)

@@ -83,7 +83,7 @@ class NkEngine
     size_t n_reads = 0, n_records = 0;
     int paired = 0;
     std::vector<unsigned> T;
-    const nkd_read *h_reads = nullptr;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
     bool staged = false, ran = false;
     float last_total_ms = 0, last_probe_ms = 0;
 
@@ -412,46 +412,80 @@ class NkEngine
         return NK_OK;
     }
 
+    std::vector<unsigned short> rec_part; /* partition of every record of the staged step */
+
     int stage(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr, int is_paired, int n_tabs,
               bool ignore_part)
     {
-        if (nr > cfg.max_step_reads || seq_bytes > cfg.max_step_bytes)
-            return fail(NK_EINVAL, "step exceeds the limits given to nkd_create");
-        if (is_paired && (nr & 1))
-            return fail(NK_EINVAL, "paired step with an odd number of reads");
+        nkd_segment s{reads, nr, 0, seq_bytes};
+        return stage_segments(seq, &s, 1, is_paired, n_tabs, ignore_part);
+    }
+
+    int stage_segments(const uint8_t *seq, const nkd_segment *segs, int n_segs, int is_paired, int n_tabs,
+                       bool ignore_part)
+    {
+        size_t nr = 0;
+        for (int s = 0; s < n_segs; s++)
+            nr += segs[s].n_reads;
+        if (nr > cfg.max_step_reads)
+            return fail(NK_EINVAL, "step exceeds the read limit given to nkd_create");
         std::fill(T.begin(), T.end(), 0u);
-        for (size_t i = 0; i < nr; i++)
+        int stride = is_paired ? 2 : 1;
+        rec_part.resize(nr / stride + 1);
+        size_t at = 0;
+        for (int s = 0; s < n_segs; s++)
         {
-            unsigned p = ignore_part ? 0 : reads[i].part;
-            if ((int)p >= n_tabs)
-                return fail(NK_EINVAL, "read names a partition that is not resident");
-            if (reads[i].len >= NK_MAX_LINE)
-                return fail(NK_EINVAL, "read longer than 1023 bases (the reference cuts lines there, C:397)");
-            if ((int)reads[i].len < cfg.k)
-                return fail(NK_EINVAL, "read shorter than k in a step (the caller drops those, C:1430-1443)");
-            if ((reads[i].seq_off & 15u) || (size_t)reads[i].seq_off + reads[i].len > seq_bytes)
-                return fail(NK_EINVAL, "read offset not 16-byte aligned or out of the step buffer");
-            unsigned end = reads[i].op_base + (unsigned)(reads[i].len - cfg.k + 1);
-            if (end > T[p])
-                T[p] = end;
+            const nkd_segment &g = segs[s];
+            if (g.seq_hi > cfg.max_step_bytes || g.seq_lo > g.seq_hi || (g.seq_lo & 15u))
+                return fail(NK_EINVAL, "step segment exceeds the byte limit given to nkd_create");
+            if (is_paired && (g.n_reads & 1))
+                return fail(NK_EINVAL, "paired step with an odd number of reads");
+            for (size_t i = 0; i < g.n_reads; i++)
+            {
+                const nkd_read &rd = g.reads[i];
+                unsigned p = ignore_part ? 0 : rd.part;
+                if ((int)p >= n_tabs)
+                    return fail(NK_EINVAL, "read names a partition that is not resident");
+                if (rd.len >= NK_MAX_LINE)
+                    return fail(NK_EINVAL, "read longer than 1023 bases (the reference cuts lines there, C:397)");
+                if ((int)rd.len < cfg.k)
+                    return fail(NK_EINVAL, "read shorter than k in a step (the caller drops those, C:1430-1443)");
+                if ((rd.seq_off & 15u) || rd.seq_off < g.seq_lo || (size_t)rd.seq_off + rd.len > g.seq_hi)
+                    return fail(NK_EINVAL, "read offset not 16-byte aligned or outside its segment");
+                unsigned end = rd.op_base + (unsigned)(rd.len - cfg.k + 1);
+                if (end > T[p])
+                    T[p] = end;
+                if ((at + i) % stride == 0)
+                    rec_part[(at + i) / stride] = (unsigned short)p;
+            }
+            if (g.n_reads)
+            {
+                /* the last 16-byte chunk of a read may extend past seq_hi: the buffers are padded */
+                size_t hi = std::min<size_t>((g.seq_hi + 15) & ~(size_t)15, cfg.max_step_bytes);
+                be.h2d(d_seq + g.seq_lo, seq + g.seq_lo, hi - g.seq_lo);
+                be.h2d(d_reads + at, g.reads, g.n_reads * sizeof(nkd_read));
+                h2d_bytes += (hi - g.seq_lo) + g.n_reads * sizeof(nkd_read);
+            }
+            at += g.n_reads;
         }
         uint64_t tot = 0;
         for (int p = 0; p < n_tabs; p++)
+        {
+            if (T[p] >= (1u << NK_T_BITS))
+                return fail(NK_EINVAL, "a partition has 2^28 or more operations in one step");
             tot += T[p];
+        }
         if (tot > cfg.max_step_ops)
             return fail(NK_EINVAL, "step has more operations than max_step_ops");
-        be.h2d(d_seq, seq, seq_bytes);
-        be.h2d(d_reads, reads, nr * sizeof(nkd_read));
         n_reads = nr;
         paired = is_paired;
-        n_records = is_paired ? nr / 2 : nr;
-        h_reads = reads;
+        n_records = nr / stride;
         staged = true;
         ran = false;
         return NK_OK;
     }
 
-    int seed_step(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr)
+    int seed_step(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr, int64_t *first_invalid)
     {
         if (seeded)
             return fail(NK_EINVAL, "nkd_seed_step after nkd_seed_finish");
@@ -462,6 +496,16 @@ class NkEngine
         std::vector<NkTable *> tabs{&seed};
         rc = run_ops(NK_MODE_SEED, tabs);
         staged = false;
+        if (rc)
+            return rc;
+        if (first_invalid)
+        { /* the reference aborts at the first seed record that is not DNA (C:1349-1350) */
+            be.zero(d_ctr, sizeof(NkCounters));
+            be.decide(make_run(NK_MODE_SEED, 0, 0), (unsigned)n_reads, 0, cfg.coverage, d_accept);
+            be.d2h(&h_ctr, d_ctr, 32);
+            be.sync();
+            *first_invalid = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
+        }
         return rc;
     }
 
@@ -524,10 +568,10 @@ class NkEngine
             return fail(NK_EINVAL, "nkd_fetch: record count differs from the staged step");
         be.d2h(accept, d_accept, nrec);
         be.d2h(&h_ctr, d_ctr, 32);
+        d2h_bytes += nrec + 32;
         be.sync();
         last_total_ms = be.timer_ms(0);
         last_probe_ms = be.timer_ms(1);
-        int stride = paired ? 2 : 1;
         int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         if (first_invalid)
             *first_invalid = (inv >= 0 && (size_t)inv < nrec) ? inv : -1;
@@ -535,7 +579,7 @@ class NkEngine
         {
             if (inv >= 0 && (size_t)inv < nrec && r >= (size_t)inv)
                 break; /* the reference stops at the first non-DNA record */
-            nkd_part_stats &st = parts[h_reads[r * stride].part].st;
+            nkd_part_stats &st = parts[rec_part[r]].st;
             st.processed++;
             if (accept[r])
                 st.printed++;

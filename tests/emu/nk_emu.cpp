@@ -159,3 +159,7 @@ struct EmuBackend
 
 #define NK_BACKEND EmuBackend
 #include "../../nomalise_kmers_multi_large_b200/csrc/nk_engine_api.h"
+
+extern "C" void *nkd_alloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 16); }
+extern "C" void nkd_free_pinned(void *p) { free(p); }
+extern "C" int nkd_device_count(void) { return 1; }
