@@ -1,0 +1,1863 @@
+/*
+ * nk_host.c -- C host side of the B200 k-mer normalisation path (nk_* in include/nk_b200.h).
+ *
+ * What the reference does per file in main() and its worker threads (normalise_kmers_multi_large.c,
+ * "C:n") is restated here around the device engine:
+ *   partition byte ranges      calculate_thread_positions[_from_records], count_records_seqfile  C:1240-1320
+ *   record indexer             the read_line x4/x2 loop of process_thread_chunk_*                C:394-409, C:1605-1631
+ *   length gate                is_valid_sequence_* (N->A and the alphabet gate run on the GPU)    C:1404-1457
+ *   staging                    sequence lines only, 16-byte aligned, into page-locked buffers
+ *   writer                     accepted records, N->A in the sequence line, fq->fa rewrite        C:1649-1666, C:852-876
+ *   seeding                    seed_kmer_hash's own line splitter and "> K" rule                  C:1322-1373
+ *   CLI                        parse_arguments / main: same flags, files, stdout lines, exit codes C:520-745, C:2223-2455
+ * One pipeline thread per GPU; partitions are independent, so no collective is needed (README:68).
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <fcntl.h>
+#include <getopt.h>
+#include <locale.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdbool.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../include/nk_b200.h"
+
+/* ------------------------------------------------------------------ small helpers */
+
+typedef struct
+{
+    const char *data;
+    size_t size;
+} nk_buf;
+
+static inline char nk_at(const nk_buf *f, size_t i) { return i < f->size ? f->data[i] : '\0'; } /* past EOF reads as NUL */
+
+static double nk_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+typedef void (*nk_task_fn)(int index, void *arg);
+typedef struct
+{
+    nk_task_fn fn;
+    void *arg;
+    int n;
+    int next;
+    pthread_mutex_t mu;
+} nk_pf;
+
+static void *nk_pf_worker(void *a)
+{
+    nk_pf *pf = a;
+    for (;;)
+    {
+        pthread_mutex_lock(&pf->mu);
+        int i = pf->next++;
+        pthread_mutex_unlock(&pf->mu);
+        if (i >= pf->n)
+            break;
+        pf->fn(i, pf->arg);
+    }
+    return NULL;
+}
+
+/* run fn(0..n-1) on up to nthreads threads */
+static void nk_parallel_for(int n, int nthreads, nk_task_fn fn, void *arg)
+{
+    if (nthreads > n)
+        nthreads = n;
+    if (nthreads <= 1)
+    {
+        for (int i = 0; i < n; i++)
+            fn(i, arg);
+        return;
+    }
+    nk_pf pf = {fn, arg, n, 0, PTHREAD_MUTEX_INITIALIZER};
+    pthread_t th[64];
+    if (nthreads > 64)
+        nthreads = 64;
+    int started = 0;
+    for (int t = 0; t < nthreads - 1; t++)
+        if (pthread_create(&th[started], NULL, nk_pf_worker, &pf) == 0)
+            started++;
+    nk_pf_worker(&pf);
+    for (int t = 0; t < started; t++)
+        pthread_join(th[t], NULL);
+}
+
+static int nk_host_threads(void)
+{
+    const char *s = getenv("NKB200_THREADS");
+    if (s && atoi(s) > 0)
+        return atoi(s);
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+/* ------------------------------------------------------------------ capacity (C:416-422, C:676-684) */
+
+static uint64_t nk_pow4_wrapping(int k)
+{
+    uint64_t v = 1;
+    for (int i = 0; i < k && i < 64; i++)
+        v *= 4;
+    return v;
+}
+
+static uint64_t nk_capacity_unclamped(int memory_gb, int partitions)
+{
+    if (memory_gb <= 0)
+        return NK_DEFAULT_SLOTS;
+    /* float32 on purpose: the capacity decides which k-mers collide, so it is part of the results */
+    size_t bytes = (size_t)((float)memory_gb * 1073741824);
+    float total = (float)(bytes / 16);
+    size_t per = (size_t)(total / (float)partitions);
+    return (per % 2 == 0) ? per + 1 : per;
+}
+
+uint64_t nk_initial_capacity(int memory_gb, int partitions, int k)
+{
+    uint64_t cap = nk_capacity_unclamped(memory_gb, partitions > 0 ? partitions : 1);
+    uint64_t lim = k >= 32 ? (uint64_t)1 << 63 : nk_pow4_wrapping(k); /* k = 32 extension: no clamp */
+    return lim < cap ? lim : cap;
+}
+
+/* ------------------------------------------------------------------ partition byte ranges */
+
+typedef struct
+{
+    char msg[256];
+    int failed;
+} nk_diag;
+
+/* find_thread_exact_end, C:1199-1236 */
+static int nk_boundary_before(const nk_buf *f, size_t lo, size_t hi, int fastq, size_t *out, nk_diag *d)
+{
+    if (!fastq)
+    {
+        for (size_t i = hi; i > lo; i--)
+            if (nk_at(f, i) == '>')
+            {
+                *out = i - 1;
+                return 0;
+            }
+    }
+    else
+    {
+        int nl = 0, plus = 0;
+        for (size_t i = hi; i > lo; i--)
+        {
+            if (nk_at(f, i) != '\n')
+                continue;
+            nl++;
+            if (nk_at(f, i + 1) == '+')
+                plus = 1;
+            else if (plus && nk_at(f, i + 1) == '@')
+            {
+                *out = i;
+                return 0;
+            }
+            if (nl == 7)
+            {
+                snprintf(d->msg, sizeof d->msg, "ERROR: after 7 lines, I couldn't find the + and @ headers near this chunk %'zu", i);
+                d->failed = 1;
+                return -1;
+            }
+        }
+    }
+    snprintf(d->msg, sizeof d->msg, "ERROR: i couldn't find the start of sequence before this chunk end %'zu", hi);
+    d->failed = 1;
+    return -1;
+}
+
+/* calculate_thread_positions, C:1240-1262: starts[1] is never assigned and the last end is overwritten,
+ * so partition 1 re-reads partition 0's bytes and the file tail is dropped */
+static int nk_ranges_by_size(const nk_buf *f, int p, int fastq, uint64_t *st, uint64_t *en, nk_diag *d)
+{
+    size_t chunk = f->size / (size_t)p;
+    if (chunk <= (size_t)NK_MAX_LINE * 4)
+    {
+        snprintf(d->msg, sizeof d->msg, "Error: input too small to split by size across %d partitions", p);
+        d->failed = 1;
+        return -1;
+    }
+    size_t approx = chunk - (size_t)NK_MAX_LINE * 4, e;
+    st[0] = 0;
+    if (nk_boundary_before(f, 0, approx, fastq, &e, d))
+        return -1;
+    en[0] = e;
+    en[p - 1] = f->size - 1;
+    for (int t = 1; t < p; t++)
+    {
+        size_t s = en[t - 1] + 1;
+        if (nk_boundary_before(f, s, s + approx, fastq, &e, d))
+            return -1;
+        en[t] = e;
+        if (t < p - 1)
+            st[t + 1] = en[t] + 1;
+    }
+    return 0;
+}
+
+typedef struct
+{
+    const nk_buf *f;
+    size_t chunk;
+    uint64_t *counts;
+} nk_count_job;
+
+static void nk_count_task(int i, void *a)
+{
+    nk_count_job *j = a;
+    size_t lo = (size_t)i * j->chunk, hi = lo + j->chunk;
+    if (hi > j->f->size)
+        hi = j->f->size;
+    uint64_t n = 0;
+    const char *p = j->f->data + lo, *end = j->f->data + hi;
+    while (p < end && (p = memchr(p, '\n', (size_t)(end - p))) != NULL)
+    {
+        n++;
+        p++;
+    }
+    j->counts[i] = n;
+}
+
+/* count_records_seqfile, C:1302-1320 (the newline count is spread over the host cores) */
+uint64_t nk_count_records(const char *data, size_t size, int fastq)
+{
+    nk_buf f = {data, size};
+    int nt = nk_host_threads();
+    size_t chunk = (size_t)8 << 20;
+    int nchunks = (int)((size + chunk - 1) / chunk);
+    uint64_t lines = 0;
+    if (nchunks > 0)
+    {
+        uint64_t *counts = calloc((size_t)nchunks, sizeof *counts);
+        nk_count_job job = {&f, chunk, counts};
+        nk_parallel_for(nchunks, nt, nk_count_task, &job);
+        for (int i = 0; i < nchunks; i++)
+            lines += counts[i];
+        free(counts);
+    }
+    if (size > 0 && data[size - 1] != '\n')
+        lines++;
+    return fastq ? lines / 4 : lines / 2;
+}
+
+/* calculate_thread_positions_from_records, C:1265-1300 */
+static void nk_ranges_by_records(const nk_buf *f, int p, int fastq, uint64_t records, uint64_t *st, uint64_t *en)
+{
+    uint64_t per = records / (uint64_t)p;
+    if (p < 2 || per < 1 || f->size < 1)
+        return;
+    int want = (int)(fastq ? per * 4 : per * 2);
+    st[0] = 0;
+    en[p - 1] = f->size - 1;
+    for (int t = 0; t < p - 1; t++)
+    {
+        uint64_t seen = 0;
+        const char *q = f->data + st[t], *end = f->data + f->size;
+        while (q < end && (q = memchr(q, '\n', (size_t)(end - q))) != NULL)
+        {
+            if (++seen == (uint64_t)want)
+            {
+                en[t] = (uint64_t)(q - f->data);
+                st[t + 1] = en[t] + 1;
+                break;
+            }
+            q++;
+        }
+    }
+}
+
+int nk_partition_ranges(const char *data, size_t size, int partitions, int fastq, int mode, uint64_t records,
+                        uint64_t *starts, uint64_t *ends)
+{
+    nk_buf f = {data, size};
+    nk_diag d = {{0}, 0};
+    memset(starts, 0, sizeof(uint64_t) * (size_t)partitions);
+    memset(ends, 0, sizeof(uint64_t) * (size_t)partitions);
+    if (partitions == 1)
+    {
+        ends[0] = size - 1;
+        return NK_OK;
+    }
+    if (mode == 0)
+        return nk_ranges_by_size(&f, partitions, fastq, starts, ends, &d) ? NK_EDATA : NK_OK;
+    nk_ranges_by_records(&f, partitions, fastq, records, starts, ends);
+    return NK_OK;
+}
+
+/* ------------------------------------------------------------------ line reader (C:394-409) */
+
+/* One line as read_line() sees it: ends at '\n', at a NUL (EOF included) or after 1023 chars.
+ * *more = 0 when the byte after the consumed span is NUL (read_line returns NULL).
+ * *plain = 0 unless the line is simply "text\n" (the writer's verbatim fast path). */
+static inline size_t nk_take_line(const nk_buf *f, size_t pos, uint32_t *len, int *more, int *plain)
+{
+    size_t avail = pos < f->size ? f->size - pos : 0;
+    size_t lim = avail < (size_t)(NK_MAX_LINE - 1) ? avail : (size_t)(NK_MAX_LINE - 1);
+    const char *p = f->data + pos;
+    const char *nl = lim ? memchr(p, '\n', lim) : NULL;
+    size_t n = nl ? (size_t)(nl - p) : lim;
+    const char *z = n ? memchr(p, 0, n) : NULL;
+    if (z)
+    {
+        *plain = 0;
+        *len = (uint32_t)(z - p);
+        *more = 0;
+        return pos + (size_t)(z - p);
+    }
+    pos += n;
+    if (nl)
+        pos++;
+    else
+    {
+        *plain = 0;
+        if (nk_at(f, pos) == '\n')
+            pos++;
+    }
+    *len = (uint32_t)n;
+    *more = nk_at(f, pos) != '\0';
+    return pos;
+}
+
+/* ------------------------------------------------------------------ context */
+
+typedef struct
+{
+    uint64_t start;    /* file offset of the record's first byte */
+    uint32_t nbytes;   /* bytes consumed by its lines */
+    uint16_t seq_rel;  /* offset of the sequence line */
+    uint16_t seq_len;
+    uint32_t plain;    /* all lines are "text\n": the record can be copied verbatim */
+} nk_span;
+
+typedef struct
+{
+    size_t fp, fe, rp, re;
+    int done;
+} nk_cursor;
+
+typedef struct
+{
+    nkd_read *reads; /* page-locked */
+    size_t n_reads, n_records;
+    size_t seq_lo, seq_hi, seq_end; /* region of the step-wide sequence buffer */
+    nk_span *spans;                 /* stride records (fwd, rev) */
+    uint32_t ops;
+    int64_t fatal_record; /* length-gate passed but the engine reported a non-DNA byte */
+} nk_pstep;
+
+typedef struct
+{
+    uint8_t *seq;    /* page-locked, n_parts regions */
+    uint8_t *accept; /* page-locked */
+    nk_pstep *ps;    /* per device-local partition */
+    nkd_segment *segs;
+    size_t n_records;
+} nk_stepbuf;
+
+typedef struct
+{
+    int gid;       /* global partition id (file names, C:2286) */
+    int dev, lidx; /* device slot and engine-local index */
+    FILE *out_f, *out_r;
+    char *wbuf_f, *wbuf_r;
+    nk_cursor cur;
+    uint64_t processed, printed, skipped;
+    double t_start;
+    uint64_t last_processed;
+} nk_part;
+
+typedef struct
+{
+    int ordinal;
+    nkd_engine *eng;
+    int n_parts;
+    int *parts; /* indices into ctx->part */
+    nk_stepbuf sb[2];
+    double index_s, device_s, write_s;
+    uint64_t h2d, d2h;
+    int rc;
+    char err[512];
+} nk_dev;
+
+struct nk_ctx
+{
+    nk_config cfg;
+    char err[768];
+    int depth_part;
+    uint64_t cap0;
+    int part_first, n_local;
+    nk_part *part;
+    int n_dev;
+    nk_dev *dev;
+    int threads;
+    uint32_t step_pairs, step_ops, step_bytes;
+    /* seeding */
+    uint8_t *seed_seq;
+    nkd_read *seed_reads;
+    size_t seed_cap_reads, seed_cap_bytes, seed_cap_ops;
+    int seeded;
+    /* totals */
+    nk_totals tot;
+    uint64_t file_max_used;
+    /* per-file state shared with the device pipelines */
+    nk_buf ff, rf;
+    int paired;
+    uint64_t *fs, *fe, *rs, *re;
+    int finished;
+};
+
+static char g_create_err[768];
+const char *nk_create_error(void) { return g_create_err; }
+const char *nk_last_error(const nk_ctx *c) { return c ? c->err : g_create_err; }
+
+static int nk_fail(nk_ctx *c, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_err, 768, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static char *nk_out_name(const char *dir, const char *base, int k, int depth_part, int t, const char *suffix) /* C:834-850 */
+{
+    size_t n = strlen(base) + 80 + (dir ? strlen(dir) + 1 : 0);
+    char *s = malloc(n);
+    if (t >= 0)
+        snprintf(s, n, "%s%s%s.k%d_norm%d_thread%d.%s", dir ? dir : "", dir ? "/" : "", base, k, depth_part, t, suffix);
+    else
+        snprintf(s, n, "%s%s%s.k%d_norm%d.%s", dir ? dir : "", dir ? "/" : "", base, k, depth_part, suffix);
+    return s;
+}
+
+#define NK_WBUF (4u << 20)
+
+static void nk_free_stepbuf(nk_stepbuf *sb, int n_parts)
+{
+    if (sb->ps)
+        for (int i = 0; i < n_parts; i++)
+        {
+            nkd_free_pinned(sb->ps[i].reads);
+            free(sb->ps[i].spans);
+        }
+    free(sb->ps);
+    free(sb->segs);
+    nkd_free_pinned(sb->seq);
+    nkd_free_pinned(sb->accept);
+    memset(sb, 0, sizeof *sb);
+}
+
+void nk_destroy(nk_ctx *c)
+{
+    if (!c)
+        return;
+    for (int d = 0; d < c->n_dev; d++)
+    {
+        nk_dev *dv = &c->dev[d];
+        for (int b = 0; b < 2; b++)
+            nk_free_stepbuf(&dv->sb[b], dv->n_parts);
+        if (dv->eng)
+            nkd_destroy(dv->eng);
+        free(dv->parts);
+    }
+    for (int i = 0; i < c->n_local; i++)
+    {
+        if (c->part[i].out_f)
+            fclose(c->part[i].out_f);
+        if (c->part[i].out_r)
+            fclose(c->part[i].out_r);
+        free(c->part[i].wbuf_f);
+        free(c->part[i].wbuf_r);
+    }
+    nkd_free_pinned(c->seed_seq);
+    nkd_free_pinned(c->seed_reads);
+    free(c->fs);
+    free(c->fe);
+    free(c->rs);
+    free(c->re);
+    free(c->part);
+    free(c->dev);
+    free(c);
+}
+
+int nk_create(const nk_config *cfg, nk_ctx **out)
+{
+    *out = NULL;
+    /* the limits parse_arguments enforces, C:704-743 (k = 32 is an extension the reference rejects) */
+    if (cfg->partitions <= 0 || cfg->partitions > NK_MAX_PARTITIONS)
+        return nk_fail(NULL, NK_EINVAL, "Error: CPU count (%d) must be a positive integer and up to %d", cfg->partitions, NK_MAX_PARTITIONS);
+    if (cfg->k < 5 || cfg->k > 32)
+        return nk_fail(NULL, NK_EINVAL, "Error: Only kmer sizes (%d) of 5 to 31 are supported", cfg->k);
+    if (cfg->coverage > 1 || cfg->coverage < 0.001)
+        return nk_fail(NULL, NK_EINVAL, "Error: Coverage (%3.f) is the proportion of the sequence covered by high kmers and must be between 0 and 1", cfg->coverage);
+    if (cfg->depth < 2 || cfg->depth / cfg->partitions < 2)
+        return nk_fail(NULL, NK_EINVAL, "Error: Depth (%d) must be at least 2 x number of CPUs", cfg->depth);
+    if (!cfg->in_fastq && cfg->out_fastq)
+        return nk_fail(NULL, NK_EINVAL, "Error: cannot request an output format of FASTQ when input is FASTA");
+    nk_ctx *c = calloc(1, sizeof *c);
+    if (!c)
+        return nk_fail(NULL, NK_ENOMEM, "Memory allocation failed");
+    c->cfg = *cfg;
+    c->depth_part = cfg->depth / cfg->partitions; /* C:674 */
+    c->cap0 = nk_initial_capacity(cfg->memory_gb, cfg->partitions, cfg->k);
+    c->part_first = cfg->part_count > 0 ? cfg->part_first : 0;
+    c->n_local = cfg->part_count > 0 ? cfg->part_count : cfg->partitions;
+    if (c->part_first < 0 || c->part_first + c->n_local > cfg->partitions)
+    {
+        free(c);
+        return nk_fail(NULL, NK_EINVAL, "partition slice outside 0..%d", cfg->partitions);
+    }
+    c->threads = nk_host_threads();
+    int ndev_avail = nkd_device_count();
+    if (ndev_avail <= 0)
+    {
+        free(c);
+        return nk_fail(NULL, NK_ENODEVICE, "no CUDA device: the B200 path has no CPU fallback");
+    }
+    c->n_dev = cfg->n_devices > 0 ? cfg->n_devices : 1;
+    if (c->n_dev > c->n_local)
+        c->n_dev = c->n_local;
+    c->dev = calloc((size_t)c->n_dev, sizeof *c->dev);
+    c->part = calloc((size_t)c->n_local, sizeof *c->part);
+    c->fs = calloc((size_t)cfg->partitions, sizeof(uint64_t));
+    c->fe = calloc((size_t)cfg->partitions, sizeof(uint64_t));
+    c->rs = calloc((size_t)cfg->partitions, sizeof(uint64_t));
+    c->re = calloc((size_t)cfg->partitions, sizeof(uint64_t));
+    for (int d = 0; d < c->n_dev; d++)
+    {
+        c->dev[d].ordinal = cfg->devices ? cfg->devices[d] : d;
+        c->dev[d].parts = calloc((size_t)c->n_local, sizeof(int));
+    }
+    for (int i = 0; i < c->n_local; i++)
+    { /* partition t lives on GPU t mod G: no data moves between GPUs on the hot path */
+        nk_part *p = &c->part[i];
+        p->gid = c->part_first + i;
+        p->dev = i % c->n_dev;
+        nk_dev *dv = &c->dev[p->dev];
+        p->lidx = dv->n_parts;
+        dv->parts[dv->n_parts++] = i;
+    }
+    /* step sizing: records per partition per step; operations and bytes follow from 150-base reads,
+     * longer reads simply end a partition's batch earlier */
+    int max_dev_parts = 0;
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].n_parts > max_dev_parts)
+            max_dev_parts = c->dev[d].n_parts;
+    uint32_t sp = cfg->step_pairs;
+    if (!sp)
+    {
+        const char *e = getenv("NKB200_STEP_PAIRS");
+        sp = e && atoi(e) > 0 ? (uint32_t)atoi(e) : 32768u;
+        while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > (96ull << 20))
+            sp /= 2;
+    }
+    if (sp < 16)
+        sp = 16;
+    c->step_pairs = sp;
+    c->step_ops = sp * 288u < 4096u ? 4096u : sp * 288u;
+    c->step_bytes = (sp * 2u * 176u + 4096u) & ~15u;
+    for (int d = 0; d < c->n_dev; d++)
+    {
+        nk_dev *dv = &c->dev[d];
+        nkd_config ec;
+        memset(&ec, 0, sizeof ec);
+        ec.device = dv->ordinal;
+        ec.k = cfg->k;
+        ec.canonical = cfg->canonical;
+        ec.depth_per_part = c->depth_part;
+        ec.coverage = cfg->coverage;
+        ec.n_parts = dv->n_parts;
+        ec.capacity0 = c->cap0;
+        ec.max_step_reads = (uint64_t)dv->n_parts * sp * 2u + 16;
+        ec.max_step_bytes = (uint64_t)dv->n_parts * c->step_bytes + 64;
+        ec.max_step_ops = (uint64_t)dv->n_parts * c->step_ops + 64;
+        int rc = nkd_create(&ec, &dv->eng);
+        if (rc)
+        {
+            nk_fail(NULL, rc, "%s", dv->eng ? nkd_last_error(dv->eng) : "engine allocation failed");
+            nk_destroy(c);
+            return rc;
+        }
+        for (int b = 0; b < 2; b++)
+        {
+            nk_stepbuf *sb = &dv->sb[b];
+            sb->seq = nkd_alloc_pinned((size_t)ec.max_step_bytes + 64);
+            sb->accept = nkd_alloc_pinned((size_t)dv->n_parts * sp + 16);
+            sb->ps = calloc((size_t)dv->n_parts, sizeof *sb->ps);
+            sb->segs = calloc((size_t)dv->n_parts, sizeof *sb->segs);
+            if (!sb->seq || !sb->accept || !sb->ps || !sb->segs)
+            {
+                nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (staging buffers)");
+                nk_destroy(c);
+                return NK_ENOMEM;
+            }
+            memset(sb->seq, 0, (size_t)ec.max_step_bytes + 64);
+            for (int i = 0; i < dv->n_parts; i++)
+            {
+                sb->ps[i].reads = nkd_alloc_pinned((size_t)sp * 2u * sizeof(nkd_read));
+                sb->ps[i].spans = malloc((size_t)sp * 2u * sizeof(nk_span));
+                sb->ps[i].seq_lo = (size_t)i * c->step_bytes;
+                sb->ps[i].seq_end = sb->ps[i].seq_lo + c->step_bytes;
+                if (!sb->ps[i].reads || !sb->ps[i].spans)
+                {
+                    nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (staging buffers)");
+                    nk_destroy(c);
+                    return NK_ENOMEM;
+                }
+            }
+        }
+    }
+    /* seed staging: as large as the smallest engine's step */
+    int min_dev_parts = max_dev_parts;
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].n_parts < min_dev_parts)
+            min_dev_parts = c->dev[d].n_parts;
+    c->seed_cap_reads = (size_t)min_dev_parts * sp * 2u;
+    c->seed_cap_bytes = (size_t)min_dev_parts * c->step_bytes;
+    c->seed_cap_ops = (size_t)min_dev_parts * c->step_ops;
+    if (c->seed_cap_ops > (1u << 27))
+        c->seed_cap_ops = 1u << 27; /* one table: stay below 2^28 operations per step */
+    c->seed_seq = nkd_alloc_pinned(c->seed_cap_bytes + 64);
+    c->seed_reads = nkd_alloc_pinned(c->seed_cap_reads * sizeof(nkd_read));
+    if (!c->seed_seq || !c->seed_reads)
+    {
+        nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (seed staging)");
+        nk_destroy(c);
+        return NK_ENOMEM;
+    }
+    memset(c->seed_seq, 0, c->seed_cap_bytes + 64);
+    /* every partition's outputs are opened "w" up front and appended to across input files, C:2286-2302 */
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nk_part *p = &c->part[i];
+        char *n = nk_out_name(cfg->out_dir, "output_forward", cfg->k, c->depth_part, p->gid, "fastq");
+        p->out_f = fopen(n, "w");
+        if (!p->out_f)
+        {
+            nk_fail(NULL, NK_EIO, "Error opening file to write: %s", n);
+            free(n);
+            nk_destroy(c);
+            return NK_EIO;
+        }
+        free(n);
+        p->wbuf_f = malloc(NK_WBUF);
+        setvbuf(p->out_f, p->wbuf_f, _IOFBF, NK_WBUF);
+        if (cfg->have_reverse)
+        {
+            n = nk_out_name(cfg->out_dir, "output_reverse", cfg->k, c->depth_part, p->gid, "fastq");
+            p->out_r = fopen(n, "w");
+            if (!p->out_r)
+            {
+                nk_fail(NULL, NK_EIO, "Error opening file to write: %s", n);
+                free(n);
+                nk_destroy(c);
+                return NK_EIO;
+            }
+            free(n);
+            p->wbuf_r = malloc(NK_WBUF);
+            setvbuf(p->out_r, p->wbuf_r, _IOFBF, NK_WBUF);
+        }
+    }
+    *out = c;
+    return NK_OK;
+}
+
+/* ------------------------------------------------------------------ seeding (C:1322-1373) */
+
+typedef struct
+{
+    nk_ctx *c;
+    size_t n_reads, bytes;
+    int64_t inv[64];
+    int rc[64];
+} nk_seed_job;
+
+static void nk_seed_task(int d, void *a)
+{
+    nk_seed_job *j = a;
+    nk_dev *dv = &j->c->dev[d];
+    j->inv[d] = -1;
+    j->rc[d] = nkd_seed_step(dv->eng, j->c->seed_seq, j->bytes, j->c->seed_reads, j->n_reads, &j->inv[d]);
+}
+
+static void nk_scrub_copy(char *dst, const char *src, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+        dst[i] = src[i] == 'N' ? 'A' : src[i];
+    dst[n] = 0;
+}
+
+static int nk_seed_flush(nk_ctx *c, size_t n_reads, size_t bytes, const nk_buf *f, const uint64_t *seq_pos)
+{
+    if (!n_reads)
+        return NK_OK;
+    nk_seed_job job;
+    memset(&job, 0, sizeof job);
+    job.c = c;
+    job.n_reads = n_reads;
+    job.bytes = bytes;
+    nk_parallel_for(c->n_dev, c->n_dev, nk_seed_task, &job); /* every GPU builds the same seed table */
+    for (int d = 0; d < c->n_dev; d++)
+        if (job.rc[d])
+            return nk_fail(c, job.rc[d], "%s", nkd_last_error(c->dev[d].eng));
+    if (job.inv[0] >= 0)
+    { /* is_valid_sequence_single's abort, C:1416-1420 */
+        size_t i = (size_t)job.inv[0];
+        char *s = malloc((size_t)c->seed_reads[i].len + 1);
+        nk_scrub_copy(s, f->data + seq_pos[i], c->seed_reads[i].len);
+        nk_fail(c, NK_EDATA, "FATAL: FWD sequence does not appear to be a DNA sequence\n%s\n", s);
+        free(s);
+        return NK_EDATA;
+    }
+    return NK_OK;
+}
+
+int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed)
+{
+    if (c->seeded)
+        return nk_fail(c, NK_EINVAL, "nk_seed_buffer after nk_seed_finish");
+    double t0 = nk_now();
+    nk_buf f = {data, size};
+    int per = c->cfg.in_fastq ? 4 : 2, k = c->cfg.k;
+    int line = 0, done = 0, rc = NK_OK;
+    size_t line_start = 0, seq_start = 0, seq_len = 0;
+    size_t n_reads = 0, bytes = 0, ops = 0;
+    uint64_t *seq_pos = malloc(c->seed_cap_reads * sizeof *seq_pos);
+    const char *q = data, *end = data + size;
+    /* seed_kmer_hash splits on '\n' only and needs every line of a record terminated */
+    while (q < end && (q = memchr(q, '\n', (size_t)(end - q))) != NULL)
+    {
+        size_t i = (size_t)(q - data);
+        q++;
+        if (line == 1)
+        {
+            seq_start = line_start;
+            seq_len = i - line_start;
+        }
+        line++;
+        line_start = i + 1;
+        if (line < per)
+            continue;
+        line = 0;
+        size_t slen = strnlen(data + seq_start, seq_len);
+        if (slen <= (size_t)k) /* strictly longer than K, C:1347 */
+            continue;
+        if (slen >= NK_MAX_LINE)
+        {
+            rc = nk_fail(c, NK_EDATA, "seed record with a sequence line of %zu chars (limit %d)", slen, NK_MAX_LINE - 1);
+            break;
+        }
+        size_t need = (slen + 15) & ~(size_t)15, nops = slen - (size_t)k + 1;
+        if (n_reads + 1 > c->seed_cap_reads || bytes + need > c->seed_cap_bytes || ops + nops > c->seed_cap_ops)
+        {
+            rc = nk_seed_flush(c, n_reads, bytes, &f, seq_pos);
+            if (rc)
+                break;
+            n_reads = bytes = ops = 0;
+        }
+        memcpy(c->seed_seq + bytes, data + seq_start, slen);
+        memset(c->seed_seq + bytes + slen, 0, need - slen);
+        nkd_read *rd = &c->seed_reads[n_reads];
+        rd->seq_off = (uint32_t)bytes;
+        rd->op_base = (uint32_t)ops;
+        rd->len = (uint16_t)slen;
+        rd->part = 0;
+        rd->reserved = 0;
+        seq_pos[n_reads] = seq_start;
+        n_reads++;
+        bytes += need;
+        ops += nops;
+        if (++done == records_to_seed)
+            break;
+    }
+    if (!rc)
+        rc = nk_seed_flush(c, n_reads, bytes, &f, seq_pos);
+    free(seq_pos);
+    c->tot.seed_seconds += nk_now() - t0;
+    return rc;
+}
+
+static int nk_write_dump(nk_ctx *c, const uint64_t *keys, const int32_t *counts, uint64_t cap, const char *tag, int gid)
+{ /* print_kmer_table, C:354-385: slot order, stored keys only */
+    char base[32];
+    snprintf(base, sizeof base, "output_kmer%s", tag);
+    char *name = nk_out_name(c->cfg.out_dir, base, c->cfg.k, c->depth_part, gid, "tsv");
+    FILE *o = fopen(name, "w");
+    if (!o)
+    {
+        int rc = nk_fail(c, NK_EIO, "cannot open %s", name);
+        free(name);
+        return rc;
+    }
+    free(name);
+    char *wb = malloc(NK_WBUF);
+    setvbuf(o, wb, _IOFBF, NK_WBUF);
+    static const char sym[4] = {'A', 'C', 'G', 'T'};
+    char line[64];
+    int k = c->cfg.k;
+    for (uint64_t i = 0; i < cap; i++)
+    {
+        uint64_t x = keys[i];
+        if (!x)
+            continue;
+        for (int b = k - 1; b >= 0; b--)
+        {
+            line[b] = sym[x & 3];
+            x >>= 2;
+        }
+        int n = k + snprintf(line + k, sizeof line - (size_t)k, "\t%d\n", counts[i]);
+        fwrite(line, 1, (size_t)n, o);
+    }
+    fclose(o);
+    free(wb);
+    return NK_OK;
+}
+
+static void nk_seed_finish_task(int d, void *a)
+{
+    nk_ctx *c = a;
+    c->dev[d].rc = nkd_seed_finish(c->dev[d].eng);
+}
+
+int nk_seed_finish(nk_ctx *c)
+{
+    if (c->seeded)
+        return nk_fail(c, NK_EINVAL, "nk_seed_finish called twice");
+    double t0 = nk_now();
+    if (c->cfg.dump_tables && c->part_first == 0)
+    { /* C:2251-2252 */
+        nkd_part_stats st;
+        nkd_seed_stats(c->dev[0].eng, &st);
+        uint64_t *keys = malloc(st.capacity * sizeof *keys);
+        int32_t *counts = malloc(st.capacity * sizeof *counts);
+        if (!keys || !counts)
+            return nk_fail(c, NK_ENOMEM, "Memory allocation failed (seed dump)");
+        int rc = nkd_seed_export(c->dev[0].eng, keys, counts, st.capacity);
+        if (!rc)
+            rc = nk_write_dump(c, keys, counts, st.capacity, "_seeds", -1);
+        else
+            nk_fail(c, rc, "%s", nkd_last_error(c->dev[0].eng));
+        free(keys);
+        free(counts);
+        if (rc)
+            return rc;
+    }
+    nk_parallel_for(c->n_dev, c->n_dev, nk_seed_finish_task, c);
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].rc)
+            return nk_fail(c, c->dev[d].rc, "%s", nkd_last_error(c->dev[d].eng));
+    c->seeded = 1;
+    c->tot.seed_seconds += nk_now() - t0;
+    return NK_OK;
+}
+
+/* ------------------------------------------------------------------ indexer */
+
+typedef struct
+{
+    nk_ctx *c;
+    nk_dev *dv;
+    nk_stepbuf *sb;
+} nk_step_job;
+
+/* Fill one partition's share of a step: the worker loop's record reader (C:1605-1631) up to the
+ * step's record/byte/operation budget. */
+static void nk_index_task(int li, void *a)
+{
+    nk_step_job *j = a;
+    nk_ctx *c = j->c;
+    nk_part *p = &c->part[j->dv->parts[li]];
+    nk_pstep *ps = &j->sb->ps[li];
+    uint8_t *seqbuf = j->sb->seq;
+    const int per = c->cfg.in_fastq ? 4 : 2, k = c->cfg.k, paired = c->paired;
+    const nk_buf *ff = &c->ff, *rf = &c->rf;
+    nk_cursor *cur = &p->cur;
+    ps->n_reads = ps->n_records = 0;
+    ps->ops = 0;
+    ps->seq_hi = ps->seq_lo;
+    size_t pos = ps->seq_lo;
+    while (!cur->done && cur->fp < cur->fe && (!paired || cur->rp < cur->re))
+    {
+        if (ps->n_records >= c->step_pairs || pos + 2 * NK_MAX_LINE > ps->seq_end || ps->ops + 2 * NK_MAX_LINE > c->step_ops)
+            break;
+        nk_span sf = {cur->fp, 0, 0, 0, 1}, sr = {cur->rp, 0, 0, 0, 1};
+        size_t fp = cur->fp, rp = cur->rp;
+        int more = 1, complete = 1, plain_f = 1, plain_r = 1;
+        for (int i = 0; i < per; i++)
+        {
+            uint32_t lf = 0, lr = 0;
+            int mf = 1, mr = 1;
+            size_t f0 = fp, r0 = rp;
+            fp = nk_take_line(ff, fp, &lf, &mf, &plain_f);
+            if (paired)
+                rp = nk_take_line(rf, rp, &lr, &mr, &plain_r);
+            if (i == 1)
+            {
+                sf.seq_rel = (uint16_t)(f0 - cur->fp);
+                sf.seq_len = (uint16_t)lf;
+                sr.seq_rel = (uint16_t)(r0 - cur->rp);
+                sr.seq_len = (uint16_t)lr;
+            }
+            if (!mf || !mr)
+            {
+                more = 0;
+                complete = (i == per - 1);
+                break;
+            }
+        }
+        if (!complete)
+        { /* a record whose lines cannot all be read is not scored (reference: undefined, C:1616-1629) */
+            cur->done = 1;
+            break;
+        }
+        sf.nbytes = (uint32_t)(fp - cur->fp);
+        sr.nbytes = (uint32_t)(rp - cur->rp);
+        sf.plain = (uint32_t)plain_f;
+        sr.plain = (uint32_t)plain_r;
+        cur->fp = fp;
+        cur->rp = rp;
+        if (!more)
+            cur->done = 1;
+        if ((int)sf.seq_len < k || (paired && (int)sr.seq_len < k))
+            continue; /* dropped silently: no counter moves, the table is untouched, C:1430-1443 */
+        for (int m = 0; m < (paired ? 2 : 1); m++)
+        {
+            const nk_span *s = m ? &sr : &sf;
+            const nk_buf *src = m ? rf : ff;
+            size_t need = ((size_t)s->seq_len + 15) & ~(size_t)15;
+            memcpy(seqbuf + pos, src->data + s->start + s->seq_rel, s->seq_len);
+            memset(seqbuf + pos + s->seq_len, 0, need - s->seq_len);
+            nkd_read *rd = &ps->reads[ps->n_reads];
+            rd->seq_off = (uint32_t)pos;
+            rd->op_base = ps->ops;
+            rd->len = s->seq_len;
+            rd->part = (uint16_t)p->lidx;
+            rd->reserved = 0;
+            ps->spans[ps->n_reads] = *s;
+            ps->n_reads++;
+            ps->ops += (uint32_t)(s->seq_len - k + 1);
+            pos += need;
+        }
+        ps->n_records++;
+    }
+    ps->seq_hi = pos;
+}
+
+/* ------------------------------------------------------------------ writer (C:1649-1666, C:852-876) */
+
+static void nk_emit_lines(FILE *o, const nk_buf *f, const nk_span *s, int per, char *tmp)
+{
+    if (s->plain)
+    { /* verbatim bytes, N -> A inside the sequence line (C:1426-1427 mutates the buffer that is printed) */
+        const char *src = f->data + s->start;
+        const char *seq = src + s->seq_rel;
+        if (!memchr(seq, 'N', s->seq_len))
+        {
+            fwrite(src, 1, s->nbytes, o);
+            return;
+        }
+        memcpy(tmp, src, s->nbytes);
+        for (uint32_t i = 0; i < s->seq_len; i++)
+            if (tmp[s->seq_rel + i] == 'N')
+                tmp[s->seq_rel + i] = 'A';
+        fwrite(tmp, 1, s->nbytes, o);
+        return;
+    }
+    size_t pos = s->start; /* cut, unterminated or NUL-holding lines: print each as the reference's "%s\n" */
+    for (int i = 0; i < per; i++)
+    {
+        uint32_t len;
+        int more, plain = 1;
+        size_t p0 = pos;
+        pos = nk_take_line(f, pos, &len, &more, &plain);
+        memcpy(tmp, f->data + p0, len);
+        if (i == 1)
+            for (uint32_t b = 0; b < len; b++)
+                if (tmp[b] == 'N')
+                    tmp[b] = 'A';
+        tmp[len] = '\n';
+        fwrite(tmp, 1, len + 1, o);
+        if (!more)
+            break;
+    }
+}
+
+static void nk_emit_fasta(FILE *o, const nk_buf *f, const nk_span *s, int fwd, char *tmp)
+{ /* fastq_to_fasta, C:852-876 */
+    uint32_t hlen;
+    int more, plain = 1;
+    nk_take_line(f, s->start, &hlen, &more, &plain);
+    const char *hdr = f->data + s->start;
+    size_t n = 0;
+    tmp[n++] = '>';
+    if (hlen > 1)
+    {
+        memcpy(tmp + n, hdr + 1, hlen - 1);
+        n += hlen - 1;
+    }
+    const char a = '/', b = fwd ? '1' : '2';
+    if (hlen < 2 || hdr[hlen - 2] != a || hdr[hlen - 1] != b)
+    {
+        tmp[n++] = a;
+        tmp[n++] = b;
+    }
+    tmp[n++] = '\n';
+    const char *seq = f->data + s->start + s->seq_rel;
+    for (uint32_t i = 0; i < s->seq_len; i++)
+        tmp[n++] = seq[i] == 'N' ? 'A' : seq[i];
+    tmp[n++] = '\n';
+    fwrite(tmp, 1, n, o);
+}
+
+typedef struct
+{
+    nk_ctx *c;
+    nk_dev *dv;
+    nk_stepbuf *sb;
+    size_t *rec_base; /* first record of each partition inside the step's accept array */
+} nk_write_job;
+
+static void nk_write_task(int li, void *a)
+{
+    nk_write_job *j = a;
+    nk_ctx *c = j->c;
+    nk_part *p = &c->part[j->dv->parts[li]];
+    nk_pstep *ps = &j->sb->ps[li];
+    const uint8_t *acc = j->sb->accept + j->rec_base[li];
+    const int per = c->cfg.in_fastq ? 4 : 2, paired = c->paired, stride = paired ? 2 : 1;
+    const int to_fasta = c->cfg.in_fastq && !c->cfg.out_fastq;
+    char tmp[4 * NK_MAX_LINE + 16];
+    size_t nrec = ps->n_records;
+    if (ps->fatal_record >= 0 && (size_t)ps->fatal_record < nrec)
+        nrec = (size_t)ps->fatal_record; /* the reference stops at the first non-DNA record */
+    for (size_t r = 0; r < nrec; r++)
+    {
+        p->processed++;
+        if (!acc[r])
+        {
+            p->skipped++;
+            continue;
+        }
+        p->printed++;
+        const nk_span *sf = &ps->spans[r * stride];
+        if (to_fasta)
+        {
+            if (paired) /* single-end fq->fa prints nothing although it counts as printed, C:1995-1999 */
+            {
+                nk_emit_fasta(p->out_f, &c->ff, sf, 1, tmp);
+                nk_emit_fasta(p->out_r, &c->rf, sf + 1, 0, tmp);
+            }
+        }
+        else
+        {
+            nk_emit_lines(p->out_f, &c->ff, sf, per, tmp);
+            if (paired)
+                nk_emit_lines(p->out_r, &c->rf, sf + 1, per, tmp);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ per-GPU pipeline */
+
+typedef struct
+{
+    nk_ctx *c;
+    nk_dev *dv;
+    /* hand-off between the pipeline thread (index, write) and its GPU thread (stage, run, fetch) */
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    int submitted, completed, quit; /* step counters */
+    int gpu_rc;
+    int64_t first_invalid[2];
+} nk_pipe;
+
+static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_invalid)
+{
+    int nseg = 0;
+    sb->n_records = 0;
+    for (int i = 0; i < dv->n_parts; i++)
+    {
+        nk_pstep *ps = &sb->ps[i];
+        sb->segs[nseg].reads = ps->reads;
+        sb->segs[nseg].n_reads = ps->n_reads;
+        sb->segs[nseg].seq_lo = ps->seq_lo;
+        sb->segs[nseg].seq_hi = ps->seq_hi;
+        nseg++;
+        sb->n_records += ps->n_records;
+    }
+    double t0 = nk_now();
+    int rc = nkd_stage_segments(dv->eng, sb->seq, sb->segs, nseg, c->paired);
+    if (!rc)
+        rc = nkd_run(dv->eng);
+    if (!rc)
+        rc = nkd_fetch(dv->eng, sb->accept, sb->n_records, first_invalid);
+    dv->device_s += nk_now() - t0;
+    if (rc)
+        snprintf(dv->err, sizeof dv->err, "%s", nkd_last_error(dv->eng));
+    return rc;
+}
+
+static void *nk_gpu_thread(void *a)
+{
+    nk_pipe *pp = a;
+    for (int step = 0;; step++)
+    {
+        pthread_mutex_lock(&pp->mu);
+        while (pp->submitted <= step && !pp->quit)
+            pthread_cond_wait(&pp->cv, &pp->mu);
+        int quit = pp->quit && pp->submitted <= step;
+        pthread_mutex_unlock(&pp->mu);
+        if (quit)
+            break;
+        int rc = nk_gpu_step(pp->c, pp->dv, &pp->dv->sb[step & 1], &pp->first_invalid[step & 1]);
+        pthread_mutex_lock(&pp->mu);
+        if (rc && !pp->gpu_rc)
+            pp->gpu_rc = rc;
+        pp->completed = step + 1;
+        pthread_cond_broadcast(&pp->cv);
+        pthread_mutex_unlock(&pp->mu);
+    }
+    return NULL;
+}
+
+static size_t nk_build_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
+{
+    double t0 = nk_now();
+    nk_step_job job = {c, dv, sb};
+    nk_parallel_for(dv->n_parts, threads, nk_index_task, &job);
+    size_t n = 0;
+    for (int i = 0; i < dv->n_parts; i++)
+    {
+        sb->ps[i].fatal_record = -1;
+        n += sb->ps[i].n_reads;
+    }
+    dv->index_s += nk_now() - t0;
+    return n;
+}
+
+/* turn the engine's "first invalid record" into the reference's FATAL text (C:1445-1454) */
+static int nk_report_invalid(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t rec)
+{
+    size_t base = 0;
+    for (int i = 0; i < dv->n_parts; i++)
+    {
+        nk_pstep *ps = &sb->ps[i];
+        if ((size_t)rec < base + ps->n_records)
+        {
+            size_t r = (size_t)rec - base;
+            ps->fatal_record = (int64_t)r;
+            int stride = c->paired ? 2 : 1;
+            for (int m = 0; m < stride; m++)
+            {
+                const nk_span *s = &ps->spans[r * (size_t)stride + (size_t)m];
+                const nk_buf *f = m ? &c->rf : &c->ff;
+                const char *q = f->data + s->start + s->seq_rel;
+                int bad = 0;
+                for (uint32_t b = 0; b < s->seq_len; b++)
+                    if (!strchr("ACGTN", q[b]) || q[b] == 0)
+                        bad = 1;
+                if (bad)
+                {
+                    char *txt = malloc((size_t)s->seq_len + 1);
+                    nk_scrub_copy(txt, q, s->seq_len);
+                    snprintf(dv->err, sizeof dv->err, "FATAL: %s sequence does not appear to be a DNA sequence\n%s\n", m ? "REV" : "FWD", txt);
+                    free(txt);
+                    return NK_EDATA;
+                }
+            }
+            snprintf(dv->err, sizeof dv->err, "FATAL: sequence does not appear to be a DNA sequence");
+            return NK_EDATA;
+        }
+        base += ps->n_records;
+    }
+    return NK_EINTERNAL;
+}
+
+static void nk_write_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
+{
+    double t0 = nk_now();
+    size_t rec_base[NK_MAX_PARTITIONS];
+    size_t b = 0;
+    for (int i = 0; i < dv->n_parts; i++)
+    {
+        rec_base[i] = b;
+        b += sb->ps[i].n_records;
+    }
+    nk_write_job job = {c, dv, sb, rec_base};
+    nk_parallel_for(dv->n_parts, threads, nk_write_task, &job);
+    dv->write_s += nk_now() - t0;
+}
+
+/* Two staging buffers: while the GPU thread runs step i, this thread indexes step i+1 into the other
+ * buffer, then (once i is back) submits i+1 and writes step i's accepted records. */
+static void *nk_device_pipeline(void *a)
+{
+    nk_pipe *pp = a;
+    nk_ctx *c = pp->c;
+    nk_dev *dv = pp->dv;
+    int threads = c->threads / c->n_dev;
+    if (threads < 1)
+        threads = 1;
+    dv->rc = NK_OK;
+    if (nk_build_step(c, dv, &dv->sb[0], threads) == 0)
+        return NULL;
+    pthread_t gth;
+    pthread_mutex_init(&pp->mu, NULL);
+    pthread_cond_init(&pp->cv, NULL);
+    pp->submitted = 1;
+    pp->completed = pp->quit = 0;
+    pp->gpu_rc = 0;
+    if (pthread_create(&gth, NULL, nk_gpu_thread, pp) != 0)
+    {
+        dv->rc = NK_EINTERNAL;
+        snprintf(dv->err, sizeof dv->err, "cannot start the device thread");
+        return NULL;
+    }
+    for (int step = 0;; step++)
+    {
+        int have_next = nk_build_step(c, dv, &dv->sb[(step + 1) & 1], threads) > 0;
+        pthread_mutex_lock(&pp->mu);
+        while (pp->completed <= step)
+            pthread_cond_wait(&pp->cv, &pp->mu);
+        int rc = pp->gpu_rc;
+        pthread_mutex_unlock(&pp->mu);
+        if (rc)
+        {
+            dv->rc = rc;
+            break;
+        }
+        nk_stepbuf *sb = &dv->sb[step & 1];
+        if (pp->first_invalid[step & 1] >= 0)
+            dv->rc = nk_report_invalid(c, dv, sb, pp->first_invalid[step & 1]);
+        if (have_next && !dv->rc)
+        {
+            pthread_mutex_lock(&pp->mu);
+            pp->submitted = step + 2;
+            pthread_cond_broadcast(&pp->cv);
+            pthread_mutex_unlock(&pp->mu);
+        }
+        nk_write_step(c, dv, sb, threads);
+        if (!have_next || dv->rc)
+            break;
+    }
+    pthread_mutex_lock(&pp->mu);
+    pp->quit = 1;
+    pthread_cond_broadcast(&pp->cv);
+    pthread_mutex_unlock(&pp->mu);
+    pthread_join(gth, NULL);
+    if (!dv->rc && pp->gpu_rc)
+        dv->rc = pp->gpu_rc;
+    pthread_mutex_destroy(&pp->mu);
+    pthread_cond_destroy(&pp->cv);
+    return NULL;
+}
+
+static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev, size_t rsize, int paired)
+{
+    if (!c->seeded)
+        return nk_fail(c, NK_EINVAL, "nk_process_* before nk_seed_finish");
+    if (fsize == 0 || (paired && rsize == 0))
+        return nk_fail(c, NK_EIO, "Error memory mapping input files");
+    double t0 = nk_now();
+    int P = c->cfg.partitions, fastq = c->cfg.in_fastq;
+    c->ff.data = fwd;
+    c->ff.size = fsize;
+    c->rf.data = rev;
+    c->rf.size = rsize;
+    c->paired = paired;
+    memset(c->fs, 0, sizeof(uint64_t) * (size_t)P);
+    memset(c->fe, 0, sizeof(uint64_t) * (size_t)P);
+    memset(c->rs, 0, sizeof(uint64_t) * (size_t)P);
+    memset(c->re, 0, sizeof(uint64_t) * (size_t)P);
+    nk_diag d = {{0}, 0};
+    if (P == 1)
+    { /* C:1796-1803 */
+        c->fe[0] = fsize - 1;
+        if (paired)
+            c->re[0] = rsize - 1;
+    }
+    else if (!paired || fsize == rsize)
+    { /* C:1807-1813, C:2142 */
+        if (nk_ranges_by_size(&c->ff, P, fastq, c->fs, c->fe, &d) || (paired && nk_ranges_by_size(&c->rf, P, fastq, c->rs, c->re, &d)))
+            return nk_fail(c, NK_EDATA, "%s", d.msg);
+    }
+    else
+    { /* C:1815-1828: the forward file's record count is applied to both files */
+        uint64_t recs = nk_count_records(fwd, fsize, fastq);
+        nk_ranges_by_records(&c->ff, P, fastq, recs, c->fs, c->fe);
+        nk_ranges_by_records(&c->rf, P, fastq, recs, c->rs, c->re);
+    }
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nk_part *p = &c->part[i];
+        p->cur.fp = c->fs[p->gid];
+        p->cur.fe = c->fe[p->gid];
+        p->cur.rp = c->rs[p->gid];
+        p->cur.re = c->re[p->gid];
+        p->cur.done = 0;
+        p->t_start = nk_now();
+        p->last_processed = p->processed;
+    }
+    c->tot.index_seconds += nk_now() - t0;
+    nk_pipe *pipes = calloc((size_t)c->n_dev, sizeof *pipes);
+    pthread_t th[64];
+    for (int dd = 0; dd < c->n_dev; dd++)
+    {
+        pipes[dd].c = c;
+        pipes[dd].dv = &c->dev[dd];
+        c->dev[dd].index_s = c->dev[dd].device_s = c->dev[dd].write_s = 0;
+    }
+    for (int dd = 1; dd < c->n_dev; dd++)
+        pthread_create(&th[dd], NULL, nk_device_pipeline, &pipes[dd]);
+    nk_device_pipeline(&pipes[0]);
+    for (int dd = 1; dd < c->n_dev; dd++)
+        pthread_join(th[dd], NULL);
+    free(pipes);
+    int rc = NK_OK;
+    double mi = 0, md = 0, mw = 0;
+    for (int dd = 0; dd < c->n_dev; dd++)
+    {
+        nk_dev *dv = &c->dev[dd];
+        if (dv->rc && !rc)
+            rc = nk_fail(c, dv->rc, "%s", dv->err);
+        if (dv->index_s > mi)
+            mi = dv->index_s;
+        if (dv->device_s > md)
+            md = dv->device_s;
+        if (dv->write_s > mw)
+            mw = dv->write_s;
+    }
+    c->tot.index_seconds += mi;
+    c->tot.device_seconds += md;
+    c->tot.write_seconds += mw;
+    /* reporting totals are sums of the partitions' cumulative counters, C:1897-1909 */
+    uint64_t pr = 0, pt = 0, sk = 0, mu = 0;
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nk_part *p = &c->part[i];
+        pr += p->processed;
+        pt += p->printed;
+        sk += p->skipped;
+        nkd_part_stats st;
+        if (nkd_part_stats_get(c->dev[p->dev].eng, p->lidx, &st) == NK_OK && st.used > mu)
+            mu = st.used;
+    }
+    c->tot.processed = pr;
+    c->tot.printed = pt;
+    c->tot.skipped = sk;
+    c->file_max_used = mu;
+    if (mu > c->tot.max_used)
+        c->tot.max_used = mu;
+    c->tot.process_seconds += nk_now() - t0;
+    return rc;
+}
+
+int nk_process_paired(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size)
+{
+    return nk_process(c, fwd, fwd_size, rev, rev_size, 1);
+}
+int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size) { return nk_process(c, fwd, fwd_size, NULL, 0, 0); }
+
+int nk_totals_get(nk_ctx *c, nk_totals *out)
+{
+    *out = c->tot;
+    return NK_OK;
+}
+
+int nk_partition_stats(nk_ctx *c, int partition, nkd_part_stats *out)
+{
+    int i = partition - c->part_first;
+    if (i < 0 || i >= c->n_local)
+        return nk_fail(c, NK_EINVAL, "partition %d is not owned by this context", partition);
+    nk_part *p = &c->part[i];
+    int rc = nkd_part_stats_get(c->dev[p->dev].eng, p->lidx, out);
+    if (rc)
+        return nk_fail(c, rc, "%s", nkd_last_error(c->dev[p->dev].eng));
+    out->processed = p->processed;
+    out->printed = p->printed;
+    out->skipped = p->skipped;
+    return NK_OK;
+}
+
+int nk_finish(nk_ctx *c)
+{ /* C:2398-2413 */
+    if (c->finished)
+        return NK_OK;
+    c->finished = 1;
+    int rc = NK_OK;
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nk_part *p = &c->part[i];
+        if (p->out_f && fclose(p->out_f) != 0 && !rc)
+            rc = nk_fail(c, NK_EIO, "error closing output: %s", strerror(errno));
+        p->out_f = NULL;
+        if (p->out_r && fclose(p->out_r) != 0 && !rc)
+            rc = nk_fail(c, NK_EIO, "error closing output: %s", strerror(errno));
+        p->out_r = NULL;
+        if (c->cfg.dump_tables && c->seeded && !rc)
+        {
+            nkd_part_stats st;
+            nkd_engine *e = c->dev[p->dev].eng;
+            nkd_part_stats_get(e, p->lidx, &st);
+            uint64_t *keys = malloc(st.capacity * sizeof *keys);
+            int32_t *counts = malloc(st.capacity * sizeof *counts);
+            if (!keys || !counts)
+                rc = nk_fail(c, NK_ENOMEM, "Memory allocation failed (table dump)");
+            else if ((rc = nkd_export(e, p->lidx, keys, counts, st.capacity)) != 0)
+                nk_fail(c, rc, "%s", nkd_last_error(e));
+            else
+                rc = nk_write_dump(c, keys, counts, st.capacity, "", p->gid);
+            free(keys);
+            free(counts);
+        }
+    }
+    return rc;
+}
+
+/* ------------------------------------------------------------------ CLI (C:492-832, C:2223-2455) */
+
+typedef struct
+{
+    char **fwd;
+    int nfwd;
+    char **rev;
+    int nrev;
+    int single, memory, debug;
+    nk_config cfg;
+} nk_cli;
+
+static void nk_usage(void)
+{
+    fprintf(stderr,
+            "Usage:\n\n\t\tMandatory:\n"
+            "\t\t* --forward|-f file1 [file2+]\tList of forward (read1) sequence files\n"
+            "\t\t* --reverse|-r file1 [file2+]\tList of reverse (read2) sequence files\n\n"
+            "\t\tOptional:\n"
+            "\t\t[--single|-s]\t\t\t\tdata are single ended; --forward files without a --reverse partner are single-end\n"
+            "\t\t[--ksize|-k (integer 5-31; def. 15)]\tk-mer size\n"
+            "\t\t[--depth|-d (integer; def. 100)]\tcount at which a k-mer is high coverage; at least 2 x partitions\n"
+            "\t\t[--coverage|-g (float 0-1; def. 0.9)]\tproportion of a read's k-mers that must be high coverage to drop it\n"
+            "\t\t[--canonical|-c]\t\t\tmerge k-mers with their reverse complement\n"
+            "\t\t[--filetype|-t (fq|fa; def. fq)]\tinput format\n"
+            "\t\t[--outformat|-o (fq|fa; def. fq)]\toutput format\n"
+            "\t\t[--memory_start|-m (integer Gb)]\tinitial table memory across all partitions\n"
+            "\t\t[--cpu|-p (int; def 1)]\t\t\tnumber of partitions (the reference's threads); fixed by the user, spread over the GPUs\n"
+            "\t\t[--verbose|-e] [--debug|-b level] [--print|-P] [--version|-v] [--help|-h]\n"
+            "\t\tB200 placement: --gpus N (or NKB200_GPUS) uses N GPUs of this node; results do not depend on N\n\n");
+}
+
+static int nk_is_fa(const char *s) { return !strcasecmp(s, "fa") || !strcasecmp(s, "fasta") || !strcasecmp(s, "fsa") || !strcasecmp(s, "fas"); }
+static int nk_is_fq(const char *s) { return !strcasecmp(s, "fq") || !strcasecmp(s, "fastq") || !strcasecmp(s, "fsq"); }
+
+/* -f/-r take every following argument up to the next one starting with '-', C:747-832 */
+static void nk_add_files(char ***list, int *n, char *first, char **argv, int *idx)
+{
+    char *cur = first;
+    for (;;)
+    {
+        if (access(cur, R_OK) == 0)
+        {
+            *list = realloc(*list, (size_t)(*n + 1) * sizeof(char *));
+            (*list)[(*n)++] = strdup(cur);
+        }
+        else
+            fprintf(stderr, "Warning: File '%s' does not exist or is not readable. Skipping.\n", cur);
+        if (argv[*idx] == NULL || argv[*idx][0] == '-')
+            break;
+        cur = argv[(*idx)++];
+    }
+}
+
+static int nk_parse(nk_cli *a, int argc, char **argv, int *gpus)
+{
+    memset(a, 0, sizeof *a);
+    nk_config *c = &a->cfg;
+    c->coverage = 0.9;
+    c->partitions = 1;
+    c->k = 15;
+    c->depth = 100;
+    c->in_fastq = c->out_fastq = 1;
+    static struct option lo[] = {{"forward", 1, 0, 'f'}, {"reverse", 1, 0, 'r'}, {"ksize", 1, 0, 'k'}, {"depth", 1, 0, 'd'},
+                                 {"coverage", 1, 0, 'g'}, {"filetype", 1, 0, 't'}, {"outformat", 1, 0, 'o'}, {"cpu", 1, 0, 'p'},
+                                 {"memory_start", 1, 0, 'm'}, {"debug", 1, 0, 'b'}, {"verbose", 0, 0, 'e'}, {"help", 0, 0, 'h'},
+                                 {"canonical", 0, 0, 'c'}, {"version", 0, 0, 'v'}, {"single", 0, 0, 's'}, {"print", 0, 0, 'P'},
+                                 {"gpus", 1, 0, 1000}, {0, 0, 0, 0}};
+    int o;
+    optind = 1;
+    while ((o = getopt_long(argc, argv, "f:r:k:d:g:t:o:p:m:b:ehcvsP", lo, NULL)) != -1)
+    {
+        switch (o)
+        {
+        case 1000:
+            *gpus = atoi(optarg);
+            break;
+        case 'P':
+            c->dump_tables = 1;
+            break;
+        case 's':
+            a->single = 1;
+            break;
+        case 'c':
+            c->canonical = 1;
+            break;
+        case 'm':
+            a->memory = atoi(optarg);
+            if (a->memory < 1)
+            {
+                printf("Memory cannot be less than 1 Gb %'d\n", a->memory);
+                return 0;
+            }
+            break;
+        case 'b':
+            a->debug = atoi(optarg);
+            break;
+        case 'h':
+            nk_usage();
+            exit(EXIT_SUCCESS);
+        case 'p':
+            c->partitions = atoi(optarg);
+            break;
+        case 'f':
+            nk_add_files(&a->fwd, &a->nfwd, optarg, argv, &optind);
+            break;
+        case 'r':
+            nk_add_files(&a->rev, &a->nrev, optarg, argv, &optind);
+            break;
+        case 'k':
+            c->k = atoi(optarg);
+            break;
+        case 'd':
+            c->depth = atoi(optarg);
+            break;
+        case 'g':
+            c->coverage = atof(optarg);
+            break;
+        case 'v':
+            printf("%d\n", NK_VERSION);
+            exit(EXIT_SUCCESS);
+        case 'e':
+            c->verbose = 1;
+            break;
+        case 't':
+            if (nk_is_fa(optarg))
+                c->in_fastq = 0;
+            else if (nk_is_fq(optarg))
+                c->in_fastq = 1;
+            else
+            {
+                printf("Input file format must be either fa or fq, not %s\n", optarg);
+                return 0;
+            }
+            break;
+        case 'o':
+            if (nk_is_fa(optarg))
+                c->out_fastq = 0;
+            else if (nk_is_fq(optarg))
+                c->out_fastq = 1;
+            else
+            {
+                printf("Output file format must be either fa or fq, not %s\n", optarg);
+                return 0;
+            }
+            break;
+        default:
+            fprintf(stderr, "Unexpected error in option processing\n");
+            return 0;
+        }
+    }
+    if (c->verbose)
+    {
+        printf("\nVERSION: %d, CMD: ", NK_VERSION);
+        for (int i = 0; i < argc; i++)
+            printf("%s ", argv[i]);
+        printf("\n\n");
+    }
+    if (c->partitions <= 0)
+    { /* the reference divides by the CPU count before checking it (C:674): report the check's message */
+        fprintf(stderr, "Error: CPU count (%d) must be a positive integer and up to %d\n", c->partitions, NK_MAX_PARTITIONS);
+        return 0;
+    }
+    c->memory_gb = a->memory;
+    int depth_part = c->depth / c->partitions;
+    uint64_t cap = nk_capacity_unclamped(a->memory, c->partitions);
+    float mem_part = (float)cap * 16 / 1073741824;
+    uint64_t lim = nk_pow4_wrapping(c->k);
+    int mem_total = a->memory;
+    if (lim < cap)
+    {
+        cap = lim;
+        mem_part = (float)cap * 16 / 1073741824;
+        mem_total = (int)(mem_part * c->partitions);
+    }
+    printf("Initial hash table size set to %'zu (maximum for k=%d is %'zu); memory ~ %'0.2f Gb for each of %d threads (~ %'d Gb total))\n\n",
+           (size_t)cap, c->k, (size_t)lim, mem_part, c->partitions, mem_total);
+    if (a->nfwd == 0 || (a->nrev == 0 && !a->single))
+    {
+        fprintf(stderr, "Error: no fwd (%d) or reverse (%d) files provided\n", a->nfwd, a->nrev);
+        return 0;
+    }
+    if (!c->in_fastq && c->out_fastq)
+    {
+        fprintf(stderr, "Error: cannot request an output format of FASTQ when input is FASTA\n");
+        return 0;
+    }
+    if (!a->single && a->nfwd != a->nrev)
+    {
+        fprintf(stderr, "Error: Number of forward (%d) and reverse files (%d) must match\n", a->nfwd, a->nrev);
+        return 0;
+    }
+    if (c->partitions > NK_MAX_PARTITIONS)
+    {
+        fprintf(stderr, "Error: CPU count (%d) must be a positive integer and up to %d\n", c->partitions, NK_MAX_PARTITIONS);
+        return 0;
+    }
+    int kmax = getenv("NKB200_ALLOW_K32") ? 32 : 31;
+    if (c->k < 5 || c->k > kmax)
+    {
+        fprintf(stderr, "Error: Only kmer sizes (%d) of 5 to 31 are supported\n", c->k);
+        return 0;
+    }
+    if (c->coverage > 1 || c->coverage < 0.001)
+    {
+        fprintf(stderr, "Error: Coverage (%3.f) is the proportion of the sequence covered by high kmers and must be between 0 and 1\n", c->coverage);
+        return 0;
+    }
+    if (c->depth < 2)
+    {
+        fprintf(stderr, "Error: Depth (%d) is the number of times a kmer needs to be found before being flagged as high coverage, it must be above 1\n", c->depth);
+        return 0;
+    }
+    if (depth_part < 2)
+    {
+        fprintf(stderr, "Error: Depth (%d) must be at least 2 x number of CPUs (for performance reasons; but this version of the program is written to normalise to 50+\n", c->depth);
+        return 0;
+    }
+    return 1;
+}
+
+typedef struct
+{
+    void *map;
+    size_t size;
+} nk_map;
+
+static int nk_map_file(const char *path, nk_map *m)
+{ /* mmap_file, C:424-461 */
+    m->map = NULL;
+    m->size = 0;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0)
+    {
+        perror("Error opening file");
+        return -1;
+    }
+    struct stat sb;
+    if (fstat(fd, &sb) < 0)
+    {
+        perror("Error getting file size");
+        close(fd);
+        return -1;
+    }
+    m->size = (size_t)sb.st_size;
+    if (m->size == 0)
+    {
+        fprintf(stderr, "Error mapping file: Invalid argument\n");
+        close(fd);
+        return -1;
+    }
+    m->map = mmap(NULL, m->size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m->map == MAP_FAILED)
+    {
+        perror("Error mapping file");
+        m->map = NULL;
+        m->size = 0;
+        return -1;
+    }
+    madvise(m->map, m->size, MADV_SEQUENTIAL);
+    return 0;
+}
+
+static void nk_unmap(nk_map *m)
+{
+    if (m->map)
+        munmap(m->map, m->size);
+    m->map = NULL;
+    m->size = 0;
+}
+
+int nk_main(int argc, char **argv)
+{
+    setlocale(LC_ALL, "");
+    nk_cli a;
+    int gpus = getenv("NKB200_GPUS") ? atoi(getenv("NKB200_GPUS")) : 1;
+    if (!nk_parse(&a, argc, argv, &gpus))
+    {
+        nk_usage();
+        return 1;
+    }
+    nk_config *cfg = &a.cfg;
+    cfg->n_forward_files = a.nfwd;
+    cfg->have_reverse = a.nrev != 0;
+    int avail = nkd_device_count();
+    if (gpus < 1)
+        gpus = 1;
+    if (avail > 0 && gpus > avail)
+        gpus = avail;
+    cfg->n_devices = gpus;
+    nk_ctx *c = NULL;
+    int rc = nk_create(cfg, &c);
+    if (rc)
+    {
+        fprintf(stderr, "%s\n", nk_create_error());
+        return 1;
+    }
+    double t_seed = nk_now();
+    int want = 1 + (int)(3e6 / a.nfwd); /* C:2242 */
+    for (int i = 0; i < a.nfwd && !rc; i++)
+    {
+        for (int m = 0; m < 2 && !rc; m++)
+        {
+            if (m == 1 && i >= a.nrev)
+                break;
+            const char *path = m ? a.rev[i] : a.fwd[i];
+            if (cfg->verbose)
+                printf("Seeding hash table with up to %'d records from file %s\n", want, path);
+            nk_map mp;
+            if (nk_map_file(path, &mp) < 0)
+                continue; /* the reference walks a zero-length mapping here */
+            rc = nk_seed_buffer(c, mp.map, mp.size, want);
+            nk_unmap(&mp);
+        }
+    }
+    if (!rc)
+        rc = nk_seed_finish(c);
+    if (rc)
+    {
+        fprintf(stderr, "%s\n", nk_last_error(c));
+        nk_destroy(c);
+        return 1;
+    }
+    if (cfg->verbose)
+        printf("Seeding took %.2f seconds on %d GPU(s)\n", nk_now() - t_seed, gpus);
+
+    time_t start_time = time(NULL); /* the reference's clock starts after seeding, C:2308 */
+    double t_proc = nk_now();
+    int mapped_ok = 1;
+    for (int i = 0; i < a.nfwd; i++)
+    {
+        int paired = i < a.nrev;
+        nk_map mf = {0}, mr = {0};
+        int okf = nk_map_file(a.fwd[i], &mf) == 0, okr = 1;
+        if (paired)
+        {
+            printf("Processing file pair %d of %d: %s and %s\n", i + 1, a.nfwd, a.fwd[i], a.rev[i]);
+            okr = nk_map_file(a.rev[i], &mr) == 0;
+        }
+        else
+            printf("Processing single-ended file %d of %d: %s\n", i + 1, a.nfwd, a.fwd[i]);
+        if (!okf || !okr)
+        { /* the reference jumps to cleanup and still returns 0, C:2318-2321 */
+            fprintf(stderr, "Error memory mapping input files\n");
+            mapped_ok = 0;
+            nk_unmap(&mf);
+            nk_unmap(&mr);
+            break;
+        }
+        char lead = cfg->in_fastq ? '@' : '>';
+        const char *kind = cfg->in_fastq ? "FASTQ" : "FASTA";
+        if (((const char *)mf.map)[0] != lead)
+        {
+            fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a.fwd[i], ((const char *)mf.map)[0]);
+            return 1;
+        }
+        if (paired && ((const char *)mr.map)[0] != lead)
+        {
+            fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a.rev[i], ((const char *)mr.map)[0]);
+            return 1;
+        }
+        uint64_t before[NK_MAX_PARTITIONS];
+        for (int t = 0; t < c->n_local; t++)
+            before[t] = c->part[t].processed;
+        double tf = nk_now();
+        rc = paired ? nk_process_paired(c, mf.map, mf.size, mr.map, mr.size) : nk_process_single(c, mf.map, mf.size);
+        double dt = nk_now() - tf;
+        nk_unmap(&mf);
+        nk_unmap(&mr);
+        if (rc == NK_EDATA)
+        { /* FATAL / partition errors: message + exit(EXIT_FAILURE) */
+            const char *m = nk_last_error(c);
+            if (!strncmp(m, "ERROR", 5))
+                printf("%s\n", m);
+            else
+                fprintf(stderr, "%s\n", m);
+            nk_finish(c);
+            nk_destroy(c);
+            return 1;
+        }
+        if (rc)
+        {
+            fprintf(stderr, "%s\n", nk_last_error(c));
+            fprintf(stderr, "Error processing files\n");
+            nk_destroy(c);
+            return 1;
+        }
+        for (int t = 0; t < c->n_local; t++)
+        { /* the per-thread line of C:1752 (rates are ours) */
+            nk_part *p = &c->part[t];
+            nkd_part_stats st;
+            nk_partition_stats(c, p->gid, &st);
+            printf("Thread %d - Processing rate: %'.0f (%+.2f%%) sequences/s, processed %'zu pairs, printed: %'zu (%+.2f%%), skipped: %'zu (%+.2f%%), Unique kmers (all sequences; this thread): %'zu (%+.2f%%)\n",
+                   p->gid, dt > 0 ? (double)(p->processed - before[t]) / dt : 0.0, 0.0, (size_t)p->processed, (size_t)p->printed, 0.0,
+                   (size_t)p->skipped, 0.0, (size_t)st.used, 0.0);
+        }
+        printf("Cumulative file statistics: Processed %'zu, Printed %'zu, Skipped %'zu, Cumulative Max Unique Kmers in a thread: %'zu\n",
+               (size_t)c->tot.processed, (size_t)c->tot.printed, (size_t)c->tot.skipped, (size_t)c->file_max_used);
+    }
+    rc = nk_finish(c);
+    if (rc)
+    {
+        fprintf(stderr, "%s\n", nk_last_error(c));
+        nk_destroy(c);
+        return 1;
+    }
+    if (mapped_ok)
+    {
+        printf("\n--- Final Report ---\n");
+        printf("Processed Records: %'zu\n", (size_t)c->tot.processed);
+        printf("Printed Records: %'zu\n", (size_t)c->tot.printed);
+        printf("Skipped Records: %'zu\n", (size_t)c->tot.skipped);
+        printf("Cumulative Max unique kmers in any thread: %'zu\n", (size_t)c->tot.max_used);
+    }
+    double total_runtime = difftime(time(NULL), start_time);
+    printf("Total runtime: %.2f seconds\n", total_runtime);
+    if (c->tot.processed > 0)
+    {
+        double fine = nk_now() - t_proc;
+        double rate = (double)c->tot.processed / (total_runtime > 0 ? total_runtime : fine);
+        printf("Overall processing rate: %'.0f %s per second\n", rate, a.nrev ? "sequence pairs" : "sequences");
+    }
+    else
+        printf("No data processed\n");
+    if (cfg->verbose)
+        printf("B200: seed %.3f s, process %.3f s (index %.3f, device %.3f, write %.3f) on %d GPU(s), %d host threads\n",
+               c->tot.seed_seconds, c->tot.process_seconds, c->tot.index_seconds, c->tot.device_seconds, c->tot.write_seconds, gpus, c->threads);
+    nk_destroy(c);
+    return 0;
+}
