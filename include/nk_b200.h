@@ -128,6 +128,17 @@ int nkd_run(nkd_engine *e);
 int nkd_fetch(nkd_engine *e, uint8_t *accept, size_t n_records, int64_t *first_invalid);
 /* time of the last nkd_run on the device, from CUDA events on the engine's stream */
 int nkd_last_run_ms(nkd_engine *e, float *total_ms, float *probe_ms);
+/* cumulative since nkd_create: what bench.py's roofline and gpu_launches are computed from */
+typedef struct
+{
+    uint64_t launches;       /* kernels launched (all kinds, incl. the slow path's radix sort as 1) */
+    uint64_t probe_launches; /* k_probe launches in scoring steps */
+    double run_ms;           /* sum of nkd_run device times (CUDA events) */
+    double probe_ms;         /* sum of k_probe device times (CUDA events) */
+    uint64_t probe_touches;  /* slots visited inside k_probe (the rest are visited by k_open) */
+    uint64_t h2d_bytes, d2h_bytes;
+} nkd_run_stats;
+int nkd_run_stats_get(nkd_engine *e, nkd_run_stats *out);
 
 int nkd_part_stats_get(nkd_engine *e, int part, nkd_part_stats *out);
 /* print_kmer_table's data source (C:354-385): slot-ordered copy of partition's table */
@@ -192,6 +203,10 @@ typedef struct
     uint64_t max_used;                    /* reporting.max_total_kmers */
     double seed_seconds, process_seconds, index_seconds, device_seconds, write_seconds;
     uint64_t h2d_bytes, d2h_bytes;
+    /* device-side figures summed over the GPUs of this context (scoring steps only) */
+    double run_ms, probe_ms;
+    uint64_t launches, probe_launches;
+    uint64_t ops, touches, probe_touches, slow_events, expansions;
 } nk_totals;
 
 int nk_totals_get(nk_ctx *c, nk_totals *out);

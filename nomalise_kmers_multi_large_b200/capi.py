@@ -47,6 +47,16 @@ class PartStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class RunStats(C.Structure):
+    """nkd_run_stats"""
+    _fields_ = [("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("run_ms", C.c_double),
+                ("probe_ms", C.c_double), ("probe_touches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class EngineConfig(C.Structure):
     """nkd_config"""
     _fields_ = [("device", C.c_int), ("k", C.c_int), ("canonical", C.c_int), ("depth_per_part", C.c_int),
@@ -69,7 +79,10 @@ class Totals(C.Structure):
     _fields_ = [("processed", C.c_uint64), ("printed", C.c_uint64), ("skipped", C.c_uint64), ("max_used", C.c_uint64),
                 ("seed_seconds", C.c_double), ("process_seconds", C.c_double), ("index_seconds", C.c_double),
                 ("device_seconds", C.c_double), ("write_seconds", C.c_double), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("run_ms", C.c_double), ("probe_ms", C.c_double),
+                ("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("ops", C.c_uint64),
+                ("touches", C.c_uint64), ("probe_touches", C.c_uint64), ("slow_events", C.c_uint64),
+                ("expansions", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -78,7 +91,7 @@ class Totals(C.Structure):
 ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step", "nkd_seed_finish", "nkd_seed_stats",
                   "nkd_seed_export", "nkd_stage", "nkd_run", "nkd_fetch", "nkd_last_run_ms", "nkd_part_stats_get",
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
-                  "nkd_device_count"]
+                  "nkd_device_count", "nkd_run_stats_get"]
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
                     "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main"]
@@ -102,6 +115,8 @@ def _declare_engine(lib):
     lib.nkd_part_stats_get.argtypes = [vp, C.c_int, C.POINTER(PartStats)]
     lib.nkd_export.argtypes = [vp, C.c_int, vp, vp, C.c_uint64]
     lib.nkd_extract_keys.argtypes = [vp, u8p, sz, vp, sz, vp, sz, u8p]
+    lib.nkd_run_stats_get.argtypes = [vp, C.POINTER(RunStats)]
+    lib.nkd_device_count.restype = C.c_int
     return lib
 
 
@@ -245,6 +260,11 @@ class Engine:
         a, b = C.c_float(), C.c_float()
         self.lib.nkd_last_run_ms(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def run_stats(self):
+        rs = RunStats()
+        self._check(self.lib.nkd_run_stats_get(self.h, C.byref(rs)))
+        return rs.as_dict()
 
     def part_stats(self, part):
         st = PartStats()

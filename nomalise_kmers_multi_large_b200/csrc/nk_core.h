@@ -106,6 +106,7 @@ struct NkCounters
     unsigned overflow;
     unsigned inv_max; /* max over invalid records of NK_TMAX - record index; 0 = none */
     unsigned pad[2];
+    unsigned long long probe_touches; /* slots visited by k_probe (all partitions) */
     unsigned long long touches[256]; /* per partition, slots visited */
     unsigned long long real_ops[256];
     unsigned claims[256];

@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
             if (P.mode != NK_MODE_COUNT)
             {
                 if (touches)
+                {
                     atomicAdd(&P.ctr->touches[part], (unsigned long long)touches);
+                    atomicAdd(&P.ctr->probe_touches, (unsigned long long)touches);
+                }
                 if (n_real)
                     atomicAdd(&P.total[r], (unsigned)(P.delta * (int)n_real));
                 if (high)
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(256) k_decide(const NkRun P, unsigned n_record
 struct CudaBackend
 {
     int dev = -1, sms = 148;
+    unsigned long long launches = 0;
     cudaStream_t stream = nullptr;
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
@@ -357,11 +361,11 @@ struct CudaBackend
     void probe(const NkRun &P)
     {
         if (P.n_reads)
-            k_probe<<<grid_for(P.n_reads, NK_WARPS), NK_THREADS, 0, stream>>>(P);
+            k_probe<<<grid_for(P.n_reads, NK_WARPS), NK_THREADS, 0, stream>>>(P), launches++;
     }
-    void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P); }
-    void apply(const NkRun &P, unsigned n) { k_apply<<<grid_for(n, 256), 256, 0, stream>>>(P, n); }
-    void classify(const NkRun &P, unsigned n) { k_classify<<<grid_for(n, 256), 256, 0, stream>>>(P, n); }
+    void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P), launches++; }
+    void apply(const NkRun &P, unsigned n) { k_apply<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }
+    void classify(const NkRun &P, unsigned n) { k_classify<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }
     void sort_pairs(unsigned long long *kin, unsigned long long *kout, unsigned long long *vin, unsigned long long *vout,
                     unsigned n)
     {
@@ -369,26 +373,27 @@ struct CudaBackend
         ok(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long *)kin, kout,
                                            (const unsigned long long *)vin, vout, (int)n, 0, 64, stream),
            "radix sort");
+        launches++;
     }
     void rank(const NkRun &P, const unsigned long long *keys, const unsigned long long *vals, unsigned n)
     {
-        k_rank<<<grid_for(n, 256), 256, 0, stream>>>(P, keys, vals, n);
+        k_rank<<<grid_for(n, 256), 256, 0, stream>>>(P, keys, vals, n), launches++;
     }
-    void commit(const NkRun &P, unsigned n) { k_commit<<<grid_for(n, 256), 256, 0, stream>>>(P, n); }
+    void commit(const NkRun &P, unsigned n) { k_commit<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }
     void untag(const NkRun &P, unsigned n)
     {
         if (n)
-            k_untag<<<grid_for(n, 256), 256, 0, stream>>>(P, n);
+            k_untag<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++;
     }
     void rehash(const NkSlot *old_tab, unsigned long long cap, NkSlot *nt, unsigned long long ncap, unsigned long long nmagic)
     {
-        k_rehash_place<<<grid_for(cap, 256), 256, 0, stream>>>(old_tab, cap, nt, ncap, nmagic);
-        k_rehash_fill<<<grid_for(ncap, 256), 256, 0, stream>>>(old_tab, nt, ncap);
+        k_rehash_place<<<grid_for(cap, 256), 256, 0, stream>>>(old_tab, cap, nt, ncap, nmagic), launches++;
+        k_rehash_fill<<<grid_for(ncap, 256), 256, 0, stream>>>(old_tab, nt, ncap), launches++;
     }
     void decide(const NkRun &P, unsigned n_records, int paired, float coverage, unsigned char *accept)
     {
         if (n_records)
-            k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept);
+            k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept), launches++;
     }
 };
 

@@ -95,6 +95,14 @@ int nkd_last_run_ms(nkd_engine *h, float *total_ms, float *probe_ms)
         *probe_ms = h->e.last_probe_ms;
     return NK_OK;
 }
+int nkd_run_stats_get(nkd_engine *h, nkd_run_stats *out)
+{
+    *out = h->e.rs;
+    out->launches = h->e.be.launches;
+    out->h2d_bytes = h->e.h2d_bytes;
+    out->d2h_bytes = h->e.d2h_bytes;
+    return NK_OK;
+}
 int nkd_part_stats_get(nkd_engine *h, int part, nkd_part_stats *out)
 {
     if (part < 0 || part >= (int)h->e.parts.size())

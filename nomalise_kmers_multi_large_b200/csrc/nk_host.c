@@ -1377,6 +1377,33 @@ int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size) { return nk_p
 int nk_totals_get(nk_ctx *c, nk_totals *out)
 {
     *out = c->tot;
+    out->run_ms = out->probe_ms = 0;
+    out->launches = out->probe_launches = out->probe_touches = out->h2d_bytes = out->d2h_bytes = 0;
+    out->ops = out->touches = out->slow_events = out->expansions = 0;
+    for (int d = 0; d < c->n_dev; d++)
+    {
+        nkd_run_stats rs;
+        nkd_run_stats_get(c->dev[d].eng, &rs);
+        out->run_ms += rs.run_ms;
+        out->probe_ms += rs.probe_ms;
+        out->launches += rs.launches;
+        out->probe_launches += rs.probe_launches;
+        out->probe_touches += rs.probe_touches;
+        out->h2d_bytes += rs.h2d_bytes;
+        out->d2h_bytes += rs.d2h_bytes;
+    }
+    if (c->seeded)
+        for (int i = 0; i < c->n_local; i++)
+        {
+            nkd_part_stats st;
+            if (nkd_part_stats_get(c->dev[c->part[i].dev].eng, c->part[i].lidx, &st) == NK_OK)
+            {
+                out->ops += st.ops;
+                out->touches += st.touches;
+                out->slow_events += st.slow_events;
+                out->expansions += st.expansions;
+            }
+        }
     return NK_OK;
 }
 

@@ -84,6 +84,7 @@ class NkEngine
     int paired = 0;
     std::vector<unsigned> T;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    nkd_run_stats rs{};
     bool staged = false, ran = false;
     float last_total_ms = 0, last_probe_ms = 0;
 
@@ -407,7 +408,11 @@ class NkEngine
                 hi[p] = T[p];
             }
             if (mode == NK_MODE_SCORE && np > 0)
+            {
                 tabs[0]->st.slow_events += h_ctr.n_slow; /* device-wide figure, kept on partition 0 */
+                rs.probe_touches += h_ctr.probe_touches;
+                rs.probe_launches++;
+            }
         }
         return NK_OK;
     }
@@ -572,6 +577,8 @@ class NkEngine
         be.sync();
         last_total_ms = be.timer_ms(0);
         last_probe_ms = be.timer_ms(1);
+        rs.run_ms += last_total_ms;
+        rs.probe_ms += last_probe_ms;
         int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         if (first_invalid)
             *first_invalid = (inv >= 0 && (size_t)inv < nrec) ? inv : -1;

@@ -20,6 +20,7 @@
 struct EmuBackend
 {
     std::mt19937_64 rng;
+    unsigned long long launches = 0;
     int init(int, std::string &)
     {
         const char *s = getenv("NK_EMU_SEED");
@@ -91,7 +92,9 @@ struct EmuBackend
                 continue;
             P.total[op.read] += (unsigned)P.delta;
             int high = 0;
-            P.ctr->touches[part] += nk_probe_op(P, pd, part, key, t, op.read, high);
+            unsigned tch = nk_probe_op(P, pd, part, key, t, op.read, high);
+            P.ctr->touches[part] += tch;
+            P.ctr->probe_touches += tch;
             P.high[op.read] += (unsigned)high;
         }
     }
