@@ -112,6 +112,25 @@ struct NkCounters
     unsigned claims[256];
 };
 
+/* Lists (pending, open, claim, slow) are appended to through per-warp chunks: a warp reserves `chunk`
+ * entries with ONE global atomic and hands them out through a shared-memory cursor, because a single
+ * append counter hit by every warp serialises the whole kernel at the L2 atomic unit.  Unused entries
+ * of a chunk are written as holes and skipped by every consumer. */
+enum
+{
+    NK_LIST_PEND = 0,
+    NK_LIST_OPEN = 1,
+    NK_LIST_CLAIM = 2,
+    NK_LIST_SLOW = 3,
+    NK_NLISTS = 4
+};
+#define NK_HOLE 0xFFFFFFFFu
+
+struct NkWarpCur
+{
+    unsigned base[NK_NLISTS], used[NK_NLISTS], cap[NK_NLISTS];
+};
+
 enum
 {
     NK_MODE_SCORE = 0,
@@ -141,6 +160,8 @@ struct NkRun
     unsigned slow_cap;
     NkCounters *ctr;
     unsigned long long *keys_out; /* NK_MODE_KEYS */
+    unsigned chunk[NK_NLISTS];    /* entries a warp reserves at a time (device only) */
+    NkWarpCur *wcur;              /* this warp's cursors in shared memory (device only) */
 };
 
 /* ---------------------------------------------------------------- primitives */
@@ -197,22 +218,69 @@ NK_HD void nk_red_or32(unsigned *p, unsigned v)
     *p |= v;
 #endif
 }
-/* reserve one list entry; on the device the lanes of a warp that call together share one atomic */
-NK_HD unsigned nk_append(unsigned *ctr)
+/* reserve one entry of list `list` (global counter gctr) */
+NK_HD unsigned nk_list_append(const NkRun &P, int list, unsigned *gctr)
 {
 #if NK_DEVICE_CODE
+    NkWarpCur *wc = P.wcur;
     unsigned mask = __activemask();
     int leader = __ffs(mask) - 1;
     unsigned lane = threadIdx.x & 31;
-    unsigned base = 0;
+    unsigned old = 0;
     if ((int)lane == leader)
-        base = atomicAdd(ctr, __popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1));
+        old = atomicAdd(&wc->used[list], (unsigned)__popc(mask)); /* shared-memory atomic */
+    old = __shfl_sync(mask, old, leader);
+    unsigned my = old + __popc(mask & ((1u << lane) - 1));
+    if (my < wc->cap[list])
+        return wc->base[list] + my;
+    return atomicAdd(gctr, 1u); /* chunk exhausted in the middle of a read: rare */
 #else
-    return (*ctr)++;
+    (void)P;
+    (void)list;
+    return (*gctr)++;
 #endif
 }
+
+#if defined(__CUDACC__)
+/* Converged-warp call: make sure the warp's chunk of `list` has `need` free entries, else close it
+ * (holes) and reserve a fresh one.  hole(idx) writes one hole record. */
+template <class HoleFn>
+__device__ __forceinline__ void nk_chunk_ensure(const NkRun &P, int list, unsigned *gctr, unsigned need, unsigned gcap,
+                                                HoleFn hole)
+{
+    NkWarpCur *wc = P.wcur;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned used = wc->used[list], cap = wc->cap[list];
+    if (used + need <= cap || (cap > 0 && used == 0))
+        return;
+    for (unsigned i = used + lane; i < cap; i += 32)
+        hole(wc->base[list] + i);
+    __syncwarp();
+    if (lane == 0)
+    {
+        unsigned ch = P.chunk[list];
+        unsigned b = atomicAdd(gctr, ch);
+        unsigned c = b >= gcap ? 0u : (gcap - b < ch ? gcap - b : ch);
+        if (c < ch)
+            atomicOr(&P.ctr->overflow, list == NK_LIST_PEND ? NK_OVF_PEND : list == NK_LIST_OPEN ? NK_OVF_OPEN : NK_OVF_CLAIM);
+        wc->base[list] = b;
+        wc->used[list] = 0;
+        wc->cap[list] = c;
+    }
+    __syncwarp();
+}
+template <class HoleFn>
+__device__ __forceinline__ void nk_chunk_close(const NkRun &P, int list, HoleFn hole)
+{
+    NkWarpCur *wc = P.wcur;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned used = wc->used[list], cap = wc->cap[list];
+    for (unsigned i = used + lane; i < cap; i += 32)
+        hole(wc->base[list] + i);
+    __syncwarp();
+}
+#endif
+
 NK_HD NkSlot nk_load_slot(const NkSlot *p)
 {
 #if NK_DEVICE_CODE
@@ -308,7 +376,7 @@ NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int which, 
     }
     else if (P.record)
     {
-        unsigned idx = nk_append(&P.ctr->n_pend);
+        unsigned idx = nk_list_append(P, NK_LIST_PEND, &P.ctr->n_pend);
         if (idx < P.pend_cap)
         {
             NkPend r;
@@ -328,7 +396,7 @@ NK_HD void nk_defer(const NkRun &P, unsigned long long key, unsigned t, unsigned
 {
     if (!P.record)
         return;
-    unsigned idx = nk_append(&P.ctr->n_open);
+    unsigned idx = nk_list_append(P, NK_LIST_OPEN, &P.ctr->n_open);
     if (idx >= P.open_cap)
     {
         nk_red_or32(&P.ctr->overflow, NK_OVF_OPEN);
@@ -397,9 +465,12 @@ NK_HD unsigned nk_probe_op(const NkRun &P, const NkPart &pd, unsigned part, unsi
 }
 
 /* phase 2: finish a deferred operation now that every claim time is known */
-NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc)
+NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc, int &claimed)
 {
     NkOpen o = P.open[idx];
+    claimed = 0;
+    if (o.flags == NK_HOLE)
+        return 0;
     const NkPart &pd = P.parts[o.part];
     unsigned long long i = o.slot;
     unsigned c = o.c;
@@ -413,7 +484,7 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc)
         { /* this operation stores the key: count becomes 1 (0 when seeding), test is false (depth >= 2) */
             if (P.record)
             {
-                unsigned ci = nk_append(&P.ctr->n_claim);
+                unsigned ci = nk_list_append(P, NK_LIST_CLAIM, &P.ctr->n_claim);
                 if (ci < P.claim_cap)
                 {
                     NkClaim cl;
@@ -426,7 +497,7 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc)
                 }
                 else
                     nk_red_or32(&P.ctr->overflow, NK_OVF_CLAIM);
-                nk_red_add32(reinterpret_cast<int *>(&P.ctr->claims[o.part]), 1);
+                claimed = 1; /* the caller adds it to ctr->claims[o.part] */
             }
             return 0;
         }
@@ -480,6 +551,8 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc)
 NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
 {
     NkPend r = P.pend[idx];
+    if (r.slot == NK_HOLE)
+        return;
     const NkPart &pd = P.parts[P.reads[r.read].part];
     int *ctr = (r.tw & 2u) ? reinterpret_cast<int *>(&pd.tab[r.slot].aux) : &pd.tab[r.slot].count;
     nk_red_add32(ctr, 1);
@@ -489,13 +562,15 @@ NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
 NK_HD void nk_classify_op(const NkRun &P, unsigned idx)
 {
     NkPend r = P.pend[idx];
+    if (r.slot == NK_HOLE)
+        return;
     const NkPart &pd = P.parts[P.reads[r.read].part];
     NkSlot e = nk_load_slot(&pd.tab[r.slot]);
     int which = (r.tw >> 1) & 1;
     long long v = which ? 1ll + (long long)e.aux : (long long)e.count;
     if (v < P.depth)
         return;
-    unsigned si = nk_append(&P.ctr->n_slow);
+    unsigned si = nk_list_append(P, NK_LIST_SLOW, &P.ctr->n_slow);
     if (si >= P.slow_cap)
         return; /* cannot happen: slow_cap == pend_cap */
     unsigned t = r.tw >> 2;
@@ -509,8 +584,8 @@ NK_HD void nk_rank_op(const NkRun &P, const unsigned long long *keys, const unsi
                       unsigned i)
 {
     unsigned long long key = keys[i];
-    if (!(key & 1))
-        return; /* only the terminal landing is tested (C:1494) */
+    if (!(key & 1) || key == ~0ull)
+        return; /* only the terminal landing is tested (C:1494); all-ones = hole */
     unsigned long long seg = key >> (NK_T_BITS + 1);
     unsigned lo = 0, hi = i; /* first index whose segment is >= seg */
     while (lo < hi)
@@ -536,6 +611,8 @@ NK_HD void nk_rank_op(const NkRun &P, const unsigned long long *keys, const unsi
 NK_HD void nk_commit_op(const NkRun &P, unsigned idx)
 {
     NkClaim cl = P.claim[idx];
+    if (cl.slot == NK_HOLE)
+        return;
     NkSlot *s = &P.parts[cl.part].tab[cl.slot];
     NkSlot n;
     n.key = cl.key;
@@ -548,7 +625,7 @@ NK_HD void nk_commit_op(const NkRun &P, unsigned idx)
 NK_HD void nk_untag_op(const NkRun &P, unsigned idx)
 {
     NkOpen o = P.open[idx];
-    if (!(o.flags & 1u))
+    if (o.flags == NK_HOLE || !(o.flags & 1u))
         return;
     NkSlot *s = &P.parts[o.part].tab[o.slot];
     if (s->key & NK_TAG)

@@ -66,13 +66,47 @@ __device__ __forceinline__ unsigned long long nk_window_key_packed(const unsigne
     return x;
 }
 
-__global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
+__device__ __forceinline__ void nk_cur_init(NkWarpCur *wc, unsigned lane)
 {
+    if (lane < NK_NLISTS)
+    {
+        wc->base[lane] = 0;
+        wc->used[lane] = 0;
+        wc->cap[lane] = 0;
+    }
+    __syncwarp();
+}
+
+template <int MODE>
+__device__ __forceinline__ void nk_probe_body(NkRun P)
+{
+    P.mode = MODE; /* compile-time mode: the per-operation code specialises */
     __shared__ unsigned s_words[NK_WARPS][NK_WORDS];
+    __shared__ NkWarpCur s_cur[NK_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned *words = s_words[warp];
+    P.wcur = &s_cur[warp];
+    nk_cur_init(P.wcur, lane);
+    auto pend_hole = [&](unsigned i) { P.pend[i].slot = NK_HOLE; };
+    auto open_hole = [&](unsigned i) { P.open[i].flags = NK_HOLE; };
     const unsigned nwarps = gridDim.x * NK_WARPS;
-    const bool one_part = (P.mode == NK_MODE_SEED || P.mode == NK_MODE_KEYS);
+    const bool one_part = (MODE == NK_MODE_SEED || MODE == NK_MODE_KEYS);
+    /* per-partition counters are accumulated in registers and flushed when the partition changes:
+     * reads are partition-major, so a warp flushes a handful of times per launch */
+    unsigned acc_part = 0xFFFFFFFFu, acc_real = 0, acc_touch = 0;
+    auto flush = [&]() {
+        if (lane == 0 && acc_part != 0xFFFFFFFFu)
+        {
+            if (acc_real)
+                atomicAdd(&P.ctr->real_ops[acc_part], (unsigned long long)acc_real);
+            if (acc_touch)
+            {
+                atomicAdd(&P.ctr->touches[acc_part], (unsigned long long)acc_touch);
+                atomicAdd(&P.ctr->probe_touches, (unsigned long long)acc_touch);
+            }
+        }
+        acc_real = acc_touch = 0;
+    };
     for (unsigned r = blockIdx.x * NK_WARPS + warp; r < P.n_reads; r += nwarps)
     {
         const uint4 rraw = __ldg(reinterpret_cast<const uint4 *>(P.reads + r));
@@ -82,6 +116,17 @@ __global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
         const int nwin = (int)len - P.k + 1;
         if (op_base + (unsigned)nwin <= pd.lo || op_base >= pd.hi)
             continue;
+        if (part != acc_part)
+        {
+            flush();
+            acc_part = part;
+        }
+        if (P.record && (MODE == NK_MODE_SCORE || MODE == NK_MODE_SEED))
+        {
+            if (MODE == NK_MODE_SCORE)
+                nk_chunk_ensure(P, NK_LIST_PEND, &P.ctr->n_pend, 2u * (unsigned)nwin + 32u, P.pend_cap, pend_hole);
+            nk_chunk_ensure(P, NK_LIST_OPEN, &P.ctr->n_open, (unsigned)nwin + 32u, P.open_cap, open_hole);
+        }
         const unsigned nchunks = (len + 15u) >> 4;
         unsigned bad = 0;
         for (unsigned c = lane; c < nchunks + 2u; c += 32u)
@@ -95,7 +140,7 @@ __global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
             words[c] = w;
         }
         __syncwarp();
-        if (P.mode != NK_MODE_COUNT && __any_sync(0xFFFFFFFFu, bad != 0) && lane == 0)
+        if (MODE != NK_MODE_COUNT && __any_sync(0xFFFFFFFFu, bad != 0) && lane == 0)
             P.invalid[r] = 1;
         unsigned n_real = 0, touches = 0;
         int high = 0;
@@ -107,7 +152,7 @@ __global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
             if (!live)
                 continue;
             const unsigned long long key = nk_window_key_packed(words, w, P.k, P.canonical);
-            if (P.mode == NK_MODE_KEYS)
+            if (MODE == NK_MODE_KEYS)
             {
                 P.keys_out[t] = key;
                 continue;
@@ -115,45 +160,94 @@ __global__ void __launch_bounds__(NK_THREADS) k_probe(const NkRun P)
             if (key == 0) /* all-A window (or all-T under --canonical): ignored entirely, C:1483 */
                 continue;
             n_real++;
-            if (P.mode != NK_MODE_COUNT)
+            if (MODE != NK_MODE_COUNT)
                 touches += nk_probe_op(P, pd, part, key, t, r, high);
         }
         __syncwarp();
-        n_real = __reduce_add_sync(0xFFFFFFFFu, n_real);
-        touches = __reduce_add_sync(0xFFFFFFFFu, touches);
-        high = __reduce_add_sync(0xFFFFFFFFu, high);
-        if (lane == 0 && P.mode != NK_MODE_KEYS)
+        if (MODE != NK_MODE_KEYS)
         {
-            if (n_real)
-                atomicAdd(&P.ctr->real_ops[part], (unsigned long long)n_real);
-            if (P.mode != NK_MODE_COUNT)
+            n_real = __reduce_add_sync(0xFFFFFFFFu, n_real);
+            acc_real += n_real;
+            if (MODE != NK_MODE_COUNT)
             {
-                if (touches)
+                acc_touch += __reduce_add_sync(0xFFFFFFFFu, touches);
+                high = __reduce_add_sync(0xFFFFFFFFu, high);
+                if (lane == 0)
                 {
-                    atomicAdd(&P.ctr->touches[part], (unsigned long long)touches);
-                    atomicAdd(&P.ctr->probe_touches, (unsigned long long)touches);
+                    if (n_real)
+                        atomicAdd(&P.total[r], (unsigned)(P.delta * (int)n_real));
+                    if (high)
+                        atomicAdd(&P.high[r], (unsigned)high);
                 }
-                if (n_real)
-                    atomicAdd(&P.total[r], (unsigned)(P.delta * (int)n_real));
-                if (high)
-                    atomicAdd(&P.high[r], (unsigned)high);
             }
         }
         __syncwarp();
     }
+    flush();
+    if (P.record && (MODE == NK_MODE_SCORE || MODE == NK_MODE_SEED))
+    {
+        nk_chunk_close(P, NK_LIST_PEND, pend_hole);
+        nk_chunk_close(P, NK_LIST_OPEN, open_hole);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_open(const NkRun P)
+/* distinct symbols per mode so that profiles separate scoring from seeding */
+__global__ void __launch_bounds__(NK_THREADS) k_probe_score(const NkRun P) { nk_probe_body<NK_MODE_SCORE>(P); }
+__global__ void __launch_bounds__(NK_THREADS) k_probe_seed(const NkRun P) { nk_probe_body<NK_MODE_SEED>(P); }
+__global__ void __launch_bounds__(NK_THREADS) k_probe_count(const NkRun P) { nk_probe_body<NK_MODE_COUNT>(P); }
+__global__ void __launch_bounds__(NK_THREADS) k_probe_keys(const NkRun P) { nk_probe_body<NK_MODE_KEYS>(P); }
+
+__global__ void __launch_bounds__(256) k_open(NkRun P)
 {
+    __shared__ NkWarpCur s_cur[8];
+    __shared__ unsigned s_touch[NK_MAX_PARTITIONS], s_claims[NK_MAX_PARTITIONS];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    P.wcur = &s_cur[warp];
+    nk_cur_init(P.wcur, lane);
+    for (unsigned i = threadIdx.x; i < NK_MAX_PARTITIONS; i += blockDim.x)
+        s_touch[i] = s_claims[i] = 0;
+    __syncthreads();
+    auto pend_hole = [&](unsigned i) { P.pend[i].slot = NK_HOLE; };
+    auto claim_hole = [&](unsigned i) { P.claim[i].slot = NK_HOLE; };
     const unsigned n = min(P.ctr->n_open, P.open_cap);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (unsigned base = (blockIdx.x * 8u + warp) * 32u; base < n; base += gridDim.x * 256u)
     {
-        int high = 0;
-        unsigned touches = nk_open_op(P, i, high);
-        if (touches)
-            atomicAdd(&P.ctr->touches[P.open[i].part], (unsigned long long)touches);
-        if (high)
-            atomicAdd(&P.high[P.open[i].read], (unsigned)high);
+        if (P.record)
+        {
+            if (P.mode == NK_MODE_SCORE)
+                nk_chunk_ensure(P, NK_LIST_PEND, &P.ctr->n_pend, 32u * 6u, P.pend_cap, pend_hole);
+            nk_chunk_ensure(P, NK_LIST_CLAIM, &P.ctr->n_claim, 32u, P.claim_cap, claim_hole);
+        }
+        const unsigned i = base + lane;
+        if (i < n)
+        {
+            int high = 0, claimed = 0;
+            unsigned touches = nk_open_op(P, i, high, claimed);
+            if (touches | (unsigned)claimed | (unsigned)high)
+            {
+                const unsigned part = P.open[i].part;
+                if (touches)
+                    atomicAdd(&s_touch[part], touches);
+                if (claimed)
+                    atomicAdd(&s_claims[part], 1u);
+                if (high)
+                    atomicAdd(&P.high[P.open[i].read], (unsigned)high);
+            }
+        }
+        __syncwarp();
+    }
+    if (P.record)
+    {
+        nk_chunk_close(P, NK_LIST_PEND, pend_hole);
+        nk_chunk_close(P, NK_LIST_CLAIM, claim_hole);
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < NK_MAX_PARTITIONS; i += blockDim.x)
+    {
+        if (s_touch[i])
+            atomicAdd(&P.ctr->touches[i], (unsigned long long)s_touch[i]);
+        if (s_claims[i])
+            atomicAdd(&P.ctr->claims[i], s_claims[i]);
     }
 }
 
@@ -162,10 +256,22 @@ __global__ void __launch_bounds__(256) k_apply(const NkRun P, unsigned n)
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         nk_apply_op(P, i);
 }
-__global__ void __launch_bounds__(256) k_classify(const NkRun P, unsigned n)
+__global__ void __launch_bounds__(256) k_classify(NkRun P, unsigned n)
 {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        nk_classify_op(P, i);
+    __shared__ NkWarpCur s_cur[8];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    P.wcur = &s_cur[warp];
+    nk_cur_init(P.wcur, lane);
+    auto slow_hole = [&](unsigned i) { P.slow_key[i] = ~0ull; };
+    for (unsigned base = (blockIdx.x * 8u + warp) * 32u; base < n; base += gridDim.x * 256u)
+    {
+        nk_chunk_ensure(P, NK_LIST_SLOW, &P.ctr->n_slow, 32u, P.slow_cap, slow_hole);
+        const unsigned i = base + lane;
+        if (i < n)
+            nk_classify_op(P, i);
+        __syncwarp();
+    }
+    nk_chunk_close(P, NK_LIST_SLOW, slow_hole);
 }
 __global__ void __launch_bounds__(256) k_rank(const NkRun P, const unsigned long long *keys, const unsigned long long *vals,
                                              unsigned n)
@@ -256,6 +362,9 @@ struct CudaBackend
             return NK_ENODEVICE;
         }
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        /* the table is probed with random 16-byte gathers: fetch single 32-byte sectors from HBM */
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+        cudaGetLastError();
         return NK_OK;
     }
     void shutdown()
@@ -296,6 +405,21 @@ struct CudaBackend
     void d2h(void *h, const void *d, size_t n) { ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream), "D2H copy"); }
     void d2d(void *d, const void *s, size_t n) { ok(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream), "D2D copy"); }
     void sync() { ok(cudaStreamSynchronize(stream), "stream synchronize"); }
+
+    /* entries a warp reserves per global atomic: large enough to make the atomics negligible, small enough
+     * that the holes of (SMs x 8 x 8) warps stay a small fraction of the list */
+    void chunk_sizes(unsigned *c, unsigned pend_cap, unsigned open_cap, unsigned claim_cap, unsigned slow_cap)
+    {
+        unsigned warps = (unsigned)sms * 8u * 8u;
+        auto pick = [&](unsigned cap, unsigned mx) {
+            unsigned v = cap / (4u * warps);
+            return v < 32u ? 32u : (v > mx ? mx : v);
+        };
+        c[NK_LIST_PEND] = pick(pend_cap, 2048);
+        c[NK_LIST_OPEN] = pick(open_cap, 1024);
+        c[NK_LIST_CLAIM] = pick(claim_cap, 512);
+        c[NK_LIST_SLOW] = pick(slow_cap, 1024);
+    }
 
     bool prepare_sort(size_t n, std::string &err)
     {
@@ -360,8 +484,24 @@ struct CudaBackend
 
     void probe(const NkRun &P)
     {
-        if (P.n_reads)
-            k_probe<<<grid_for(P.n_reads, NK_WARPS), NK_THREADS, 0, stream>>>(P), launches++;
+        if (!P.n_reads)
+            return;
+        unsigned g = grid_for(P.n_reads, NK_WARPS);
+        launches++;
+        switch (P.mode)
+        {
+        case NK_MODE_SCORE:
+            k_probe_score<<<g, NK_THREADS, 0, stream>>>(P);
+            break;
+        case NK_MODE_SEED:
+            k_probe_seed<<<g, NK_THREADS, 0, stream>>>(P);
+            break;
+        case NK_MODE_COUNT:
+            k_probe_count<<<g, NK_THREADS, 0, stream>>>(P);
+            break;
+        default:
+            k_probe_keys<<<g, NK_THREADS, 0, stream>>>(P);
+        }
     }
     void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P), launches++; }
     void apply(const NkRun &P, unsigned n) { k_apply<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }

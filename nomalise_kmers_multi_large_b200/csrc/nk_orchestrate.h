@@ -240,6 +240,7 @@ class NkEngine
         P.slow_cap = pend_cap;
         P.ctr = d_ctr;
         P.keys_out = d_keys_out;
+        be.chunk_sizes(P.chunk, pend_cap, open_cap, claim_cap, pend_cap);
         return P;
     }
 
@@ -349,15 +350,16 @@ class NkEngine
                     /* the claim that brings `used` to the threshold; the next non-ignored window grows the table */
                     if (!fetched)
                     {
-                        h_claims.resize(h_ctr.n_claim);
-                        if (h_ctr.n_claim)
-                            be.d2h(h_claims.data(), d_claim, (size_t)h_ctr.n_claim * sizeof(NkClaim));
+                        unsigned nc = std::min(h_ctr.n_claim, claim_cap);
+                        h_claims.resize(nc);
+                        if (nc)
+                            be.d2h(h_claims.data(), d_claim, (size_t)nc * sizeof(NkClaim));
                         be.sync();
                         fetched = true;
                     }
                     std::vector<unsigned> times;
                     for (auto &c : h_claims)
-                        if (c.part == p)
+                        if (c.slot != NK_HOLE && c.part == p)
                             times.push_back(c.t);
                     uint64_t m = t.thr - t.used;
                     std::nth_element(times.begin(), times.begin() + (m - 1), times.end());
@@ -381,13 +383,14 @@ class NkEngine
             /* commit */
             if (mode == NK_MODE_SCORE)
             {
-                unsigned np_ = h_ctr.n_pend;
+                unsigned np_ = std::min(h_ctr.n_pend, pend_cap);
                 if (np_)
                 {
                     be.apply(F, np_);
                     be.classify(F, np_);
                     be.d2h(&h_ctr.n_slow, &d_ctr->n_slow, sizeof(unsigned));
                     be.sync();
+                    h_ctr.n_slow = std::min(h_ctr.n_slow, pend_cap);
                     if (h_ctr.n_slow)
                     {
                         be.sort_pairs(d_skey[0], d_skey[1], d_sval[0], d_sval[1], h_ctr.n_slow);
@@ -396,7 +399,7 @@ class NkEngine
                 }
             }
             if (h_ctr.n_claim)
-                be.commit(F, h_ctr.n_claim);
+                be.commit(F, std::min(h_ctr.n_claim, claim_cap));
             for (size_t p = 0; p < np; p++)
             {
                 NkTable &t = *tabs[p];

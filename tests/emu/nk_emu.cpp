@@ -37,6 +37,7 @@ struct EmuBackend
     void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void sync() {}
     bool prepare_sort(size_t, std::string &) { return true; }
+    void chunk_sizes(unsigned *c, unsigned, unsigned, unsigned, unsigned) { c[0] = c[1] = c[2] = c[3] = 0; }
     void begin_timer(int) {}
     void end_timer(int) {}
     void reset_timer(int) {}
@@ -103,9 +104,10 @@ struct EmuBackend
         unsigned n = std::min(P.ctr->n_open, P.open_cap);
         for (unsigned idx : order(n))
         {
-            int high = 0;
-            unsigned touches = nk_open_op(P, idx, high);
+            int high = 0, claimed = 0;
+            unsigned touches = nk_open_op(P, idx, high, claimed);
             P.ctr->touches[P.open[idx].part] += touches;
+            P.ctr->claims[P.open[idx].part] += (unsigned)claimed;
             P.high[P.open[idx].read] += (unsigned)high;
         }
     }
