@@ -126,9 +126,9 @@ enum
 };
 #define NK_HOLE 0xFFFFFFFFu
 
-struct NkWarpCur
+struct NkWarpCur /* two chunks per list: the second one is reserved ahead so a read never runs dry */
 {
-    unsigned base[NK_NLISTS], used[NK_NLISTS], cap[NK_NLISTS];
+    unsigned base[NK_NLISTS], cap[NK_NLISTS], base2[NK_NLISTS], cap2[NK_NLISTS], used[NK_NLISTS];
 };
 
 enum
@@ -233,7 +233,10 @@ NK_HD unsigned nk_list_append(const NkRun &P, int list, unsigned *gctr)
     unsigned my = old + __popc(mask & ((1u << lane) - 1));
     if (my < wc->cap[list])
         return wc->base[list] + my;
-    return atomicAdd(gctr, 1u); /* chunk exhausted in the middle of a read: rare */
+    my -= wc->cap[list];
+    if (my < wc->cap2[list])
+        return wc->base2[list] + my;
+    return atomicAdd(gctr, 1u); /* both chunks exhausted inside one read: rare */
 #else
     (void)P;
     (void)list;
@@ -242,41 +245,47 @@ NK_HD unsigned nk_list_append(const NkRun &P, int list, unsigned *gctr)
 }
 
 #if defined(__CUDACC__)
-/* Converged-warp call: make sure the warp's chunk of `list` has `need` free entries, else close it
- * (holes) and reserve a fresh one.  hole(idx) writes one hole record. */
-template <class HoleFn>
-__device__ __forceinline__ void nk_chunk_ensure(const NkRun &P, int list, unsigned *gctr, unsigned need, unsigned gcap,
-                                                HoleFn hole)
+/* Converged-warp call before a unit of work: when the first chunk is used up, the second becomes the first
+ * and a fresh one is reserved with ONE global atomic.  No holes are produced here. */
+__device__ __forceinline__ void nk_chunk_rotate(const NkRun &P, int list, unsigned *gctr, unsigned gcap)
 {
     NkWarpCur *wc = P.wcur;
     const unsigned lane = threadIdx.x & 31;
-    unsigned used = wc->used[list], cap = wc->cap[list];
-    if (used + need <= cap || (cap > 0 && used == 0))
-        return;
-    for (unsigned i = used + lane; i < cap; i += 32)
-        hole(wc->base[list] + i);
-    __syncwarp();
-    if (lane == 0)
+    for (int round = 0; round < 2; round++)
     {
-        unsigned ch = P.chunk[list];
-        unsigned b = atomicAdd(gctr, ch);
-        unsigned c = b >= gcap ? 0u : (gcap - b < ch ? gcap - b : ch);
-        if (c < ch)
-            atomicOr(&P.ctr->overflow, list == NK_LIST_PEND ? NK_OVF_PEND : list == NK_LIST_OPEN ? NK_OVF_OPEN : NK_OVF_CLAIM);
-        wc->base[list] = b;
-        wc->used[list] = 0;
-        wc->cap[list] = c;
+        if (wc->used[list] < wc->cap[list])
+            break;
+        __syncwarp();
+        if (lane == 0)
+        {
+            unsigned over = wc->used[list] - wc->cap[list];
+            unsigned ch = P.chunk[list];
+            unsigned b = atomicAdd(gctr, ch);
+            unsigned c = b >= gcap ? 0u : (gcap - b < ch ? gcap - b : ch);
+            if (c < ch)
+                atomicOr(&P.ctr->overflow, list == NK_LIST_PEND ? NK_OVF_PEND : list == NK_LIST_OPEN ? NK_OVF_OPEN : NK_OVF_CLAIM);
+            wc->base[list] = wc->base2[list];
+            wc->cap[list] = wc->cap2[list];
+            wc->used[list] = over < wc->cap2[list] ? over : wc->cap2[list];
+            wc->base2[list] = b;
+            wc->cap2[list] = c;
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
+/* end of kernel: the unused entries of both chunks become holes; hole(idx) writes one hole record */
 template <class HoleFn>
 __device__ __forceinline__ void nk_chunk_close(const NkRun &P, int list, HoleFn hole)
 {
     NkWarpCur *wc = P.wcur;
     const unsigned lane = threadIdx.x & 31;
-    unsigned used = wc->used[list], cap = wc->cap[list];
-    for (unsigned i = used + lane; i < cap; i += 32)
+    __syncwarp();
+    unsigned used = wc->used[list], cap = wc->cap[list], cap2 = wc->cap2[list];
+    unsigned u1 = used < cap ? used : cap, u2 = used > cap ? (used - cap < cap2 ? used - cap : cap2) : 0u;
+    for (unsigned i = u1 + lane; i < cap; i += 32)
         hole(wc->base[list] + i);
+    for (unsigned i = u2 + lane; i < cap2; i += 32)
+        hole(wc->base2[list] + i);
     __syncwarp();
 }
 #endif
@@ -284,8 +293,12 @@ __device__ __forceinline__ void nk_chunk_close(const NkRun &P, int list, HoleFn 
 NK_HD NkSlot nk_load_slot(const NkSlot *p)
 {
 #if NK_DEVICE_CODE
-    /* L2-only (no L1 allocation): random 16-byte gathers never hit L1 */
-    uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    /* Plain ld.global: measured on B200 (profiles/microbench) L1-bypassing loads (.cg/.cv/no_allocate) gather
+     * at half the rate (18.9 vs 35.4 G/s).  A stale L1 line is harmless here: counts that matter are either
+     * untouched during the launch or only need ">= depth-1", and an unseen claim TAG reads as "empty at step
+     * start", which is what a TAG means.  asm volatile keeps the compiler from merging re-reads in the walk loop. */
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     NkSlot s;
     s.key = ((unsigned long long)v.y << 32) | v.x;
     s.count = (int)v.z;

@@ -70,9 +70,9 @@ __device__ __forceinline__ void nk_cur_init(NkWarpCur *wc, unsigned lane)
 {
     if (lane < NK_NLISTS)
     {
-        wc->base[lane] = 0;
+        wc->base[lane] = wc->base2[lane] = 0;
+        wc->cap[lane] = wc->cap2[lane] = 0;
         wc->used[lane] = 0;
-        wc->cap[lane] = 0;
     }
     __syncwarp();
 }
@@ -124,8 +124,8 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
         if (P.record && (MODE == NK_MODE_SCORE || MODE == NK_MODE_SEED))
         {
             if (MODE == NK_MODE_SCORE)
-                nk_chunk_ensure(P, NK_LIST_PEND, &P.ctr->n_pend, 2u * (unsigned)nwin + 32u, P.pend_cap, pend_hole);
-            nk_chunk_ensure(P, NK_LIST_OPEN, &P.ctr->n_open, (unsigned)nwin + 32u, P.open_cap, open_hole);
+                nk_chunk_rotate(P, NK_LIST_PEND, &P.ctr->n_pend, P.pend_cap);
+            nk_chunk_rotate(P, NK_LIST_OPEN, &P.ctr->n_open, P.open_cap);
         }
         const unsigned nchunks = (len + 15u) >> 4;
         unsigned bad = 0;
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(256) k_open(NkRun P)
         if (P.record)
         {
             if (P.mode == NK_MODE_SCORE)
-                nk_chunk_ensure(P, NK_LIST_PEND, &P.ctr->n_pend, 32u * 6u, P.pend_cap, pend_hole);
-            nk_chunk_ensure(P, NK_LIST_CLAIM, &P.ctr->n_claim, 32u, P.claim_cap, claim_hole);
+                nk_chunk_rotate(P, NK_LIST_PEND, &P.ctr->n_pend, P.pend_cap);
+            nk_chunk_rotate(P, NK_LIST_CLAIM, &P.ctr->n_claim, P.claim_cap);
         }
         const unsigned i = base + lane;
         if (i < n)
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_classify(NkRun P, unsigned n)
     auto slow_hole = [&](unsigned i) { P.slow_key[i] = ~0ull; };
     for (unsigned base = (blockIdx.x * 8u + warp) * 32u; base < n; base += gridDim.x * 256u)
     {
-        nk_chunk_ensure(P, NK_LIST_SLOW, &P.ctr->n_slow, 32u, P.slow_cap, slow_hole);
+        nk_chunk_rotate(P, NK_LIST_SLOW, &P.ctr->n_slow, P.slow_cap);
         const unsigned i = base + lane;
         if (i < n)
             nk_classify_op(P, i);
@@ -415,10 +415,10 @@ struct CudaBackend
             unsigned v = cap / (4u * warps);
             return v < 32u ? 32u : (v > mx ? mx : v);
         };
-        c[NK_LIST_PEND] = pick(pend_cap, 2048);
-        c[NK_LIST_OPEN] = pick(open_cap, 1024);
-        c[NK_LIST_CLAIM] = pick(claim_cap, 512);
-        c[NK_LIST_SLOW] = pick(slow_cap, 1024);
+        c[NK_LIST_PEND] = pick(pend_cap, 512);
+        c[NK_LIST_OPEN] = pick(open_cap, 256);
+        c[NK_LIST_CLAIM] = pick(claim_cap, 64);
+        c[NK_LIST_SLOW] = pick(slow_cap, 64);
     }
 
     bool prepare_sort(size_t n, std::string &err)
