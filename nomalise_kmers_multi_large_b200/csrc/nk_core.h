@@ -218,25 +218,23 @@ NK_HD void nk_red_or32(unsigned *p, unsigned v)
     *p |= v;
 #endif
 }
-/* reserve one entry of list `list` (global counter gctr) */
+/* reserve one entry of list `list` (global counter gctr).  Device: every lane bumps its warp's cursor with its
+ * own shared-memory atomic.  No warp aggregation on purpose: appends happen in divergent code, and a
+ * __activemask()/__shfl_sync(mask) group can contain a lane that branches away and then waits at the
+ * warp barrier of the chunk rotation forever (seen on B200 in k_open). */
 NK_HD unsigned nk_list_append(const NkRun &P, int list, unsigned *gctr)
 {
 #if NK_DEVICE_CODE
     NkWarpCur *wc = P.wcur;
-    unsigned mask = __activemask();
-    int leader = __ffs(mask) - 1;
-    unsigned lane = threadIdx.x & 31;
-    unsigned old = 0;
-    if ((int)lane == leader)
-        old = atomicAdd(&wc->used[list], (unsigned)__popc(mask)); /* shared-memory atomic */
-    old = __shfl_sync(mask, old, leader);
-    unsigned my = old + __popc(mask & ((1u << lane) - 1));
+    if (wc == nullptr)
+        return atomicAdd(gctr, 1u);
+    unsigned my = atomicAdd(&wc->used[list], 1u);
     if (my < wc->cap[list])
         return wc->base[list] + my;
     my -= wc->cap[list];
     if (my < wc->cap2[list])
         return wc->base2[list] + my;
-    return atomicAdd(gctr, 1u); /* both chunks exhausted inside one read: rare */
+    return atomicAdd(gctr, 1u); /* both chunks exhausted inside one unit of work: rare */
 #else
     (void)P;
     (void)list;
@@ -253,9 +251,11 @@ __device__ __forceinline__ void nk_chunk_rotate(const NkRun &P, int list, unsign
     const unsigned lane = threadIdx.x & 31;
     for (int round = 0; round < 2; round++)
     {
-        if (wc->used[list] < wc->cap[list])
+        /* The decision must be a warp vote: a lane that skipped the rotation may start appending (and bump
+         * `used`) while a slower lane is still looking at the cursor; a per-lane test then sends that lane
+         * into the barrier below alone, where it pairs with the others' next barrier and the warp deadlocks. */
+        if (!__any_sync(0xFFFFFFFFu, wc->used[list] >= wc->cap[list]))
             break;
-        __syncwarp();
         if (lane == 0)
         {
             unsigned over = wc->used[list] - wc->cap[list];
@@ -428,7 +428,7 @@ NK_HD void nk_defer(const NkRun &P, unsigned long long key, unsigned t, unsigned
         nk_atomic_max64(&home_slot->key, nk_make_tag(t, idx));
 }
 
-#define NK_MAX_WALK 40000 /* c*c is int arithmetic in the reference (C:1028): stay below overflow */
+#define NK_MAX_WALK 4096 /* watchdog: at load <= 0.8 a legitimate walk this long has probability ~0.8^4096 */
 
 /* phase 1: everything about operation (key,t) that does not depend on in-step claims.
  * Returns the number of slots visited (touches).  */

@@ -707,6 +707,8 @@ static int nk_seed_flush(nk_ctx *c, size_t n_reads, size_t bytes, const nk_buf *
 {
     if (!n_reads)
         return NK_OK;
+    if (getenv("NKB200_DEBUG"))
+        fprintf(stderr, "[nk] seed flush: %zu reads, %zu bytes\n", n_reads, bytes);
     nk_seed_job job;
     memset(&job, 0, sizeof job);
     job.c = c;

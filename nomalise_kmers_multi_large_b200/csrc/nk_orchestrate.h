@@ -88,6 +88,8 @@ class NkEngine
     bool staged = false, ran = false;
     float last_total_ms = 0, last_probe_ms = 0;
 
+    bool debug = getenv("NKB200_DEBUG") != nullptr;
+
     int fail(int code, const std::string &m)
     {
         err = m;
@@ -314,11 +316,38 @@ class NkEngine
             upload_parts(tabs, lo, hi);
             be.zero(d_ctr, sizeof(NkCounters));
             NkRun F = make_run(mode, +1, 1);
+            if (debug)
+            {
+                be.sync();
+                fprintf(stderr, "[nkd] mode %d launching probe: reads %u, p0 [%u,%u)\n", mode, F.n_reads, lo[0], hi[0]);
+            }
             be.begin_timer(1);
             be.probe(F);
             be.end_timer(1);
+            if (debug)
+            {
+                be.d2h(&h_ctr, d_ctr, 32);
+                be.sync();
+                fprintf(stderr, "[nkd] probe done: n_open %u n_pend %u ovf %x\n", h_ctr.n_open, h_ctr.n_pend, h_ctr.overflow);
+            }
             be.open_ops(F);
+            if (debug)
+            {
+                be.d2h(&h_ctr, d_ctr, 32);
+                be.sync();
+                fprintf(stderr, "[nkd] open done (n_open %u)\n", h_ctr.n_open);
+            }
             fetch_counters();
+            if (debug)
+            {
+                fprintf(stderr, "[nkd] mode %d fwd: open %u pend %u claim %u ovf %x |", mode, h_ctr.n_open, h_ctr.n_pend,
+                        h_ctr.n_claim, h_ctr.overflow);
+                for (size_t p = 0; p < np && p < 4; p++)
+                    fprintf(stderr, " p%zu [%u,%u) of %u used %llu/%llu cap %llu claims %u real %llu", p, lo[p], hi[p], T[p],
+                            (unsigned long long)tabs[p]->used, (unsigned long long)tabs[p]->thr,
+                            (unsigned long long)tabs[p]->cap, h_ctr.claims[p], (unsigned long long)h_ctr.real_ops[p]);
+                fprintf(stderr, "\n");
+            }
             if (h_ctr.overflow & NK_OVF_WALK)
                 return fail(NK_EINTERNAL, "probe walk exceeded the supported length (table degenerate)");
             bool ovf = (h_ctr.overflow & (NK_OVF_OPEN | NK_OVF_PEND | NK_OVF_CLAIM)) != 0;
@@ -371,6 +400,8 @@ class NkEngine
                     }
                 }
             }
+            if (debug && (cut || ovf))
+                fprintf(stderr, "[nkd] cut=%d ovf=%d -> undo and retry with shorter windows\n", (int)cut, (int)ovf);
             if (cut)
             { /* abandon this run: replay it with -1 (the decisions are stable), forget the claim attempts */
                 NkRun U = make_run(mode, -1, 0);
