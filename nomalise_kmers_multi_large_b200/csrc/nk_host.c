@@ -211,54 +211,240 @@ static int nk_ranges_by_size(const nk_buf *f, int p, int fastq, uint64_t *st, ui
     return 0;
 }
 
+/* ---- byte scanning: 64 bytes at a time, AVX2 when the CPU has it, SSE2 otherwise ---- */
+#include <immintrin.h>
+
+/* bit i of *nl / *nul is set when p[i] is '\n' / NUL, for i < 64 */
+typedef void (*nk_mask64_fn)(const char *p, uint64_t *nl, uint64_t *nul);
+
+__attribute__((target("avx2"))) static void nk_mask64_avx2(const char *p, uint64_t *nl, uint64_t *nul)
+{
+    const __m256i a = _mm256_loadu_si256((const __m256i *)p), b = _mm256_loadu_si256((const __m256i *)(p + 32));
+    const __m256i n = _mm256_set1_epi8('\n'), z = _mm256_setzero_si256();
+    *nl = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(a, n)) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(b, n)) << 32);
+    *nul = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(a, z)) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(b, z)) << 32);
+}
+
+static void nk_mask64_sse2(const char *p, uint64_t *nl, uint64_t *nul)
+{
+    const __m128i n = _mm_set1_epi8('\n'), z = _mm_setzero_si128();
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < 4; i++)
+    {
+        __m128i v = _mm_loadu_si128((const __m128i *)(p + 16 * i));
+        a |= (uint64_t)(uint16_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, n)) << (16 * i);
+        b |= (uint64_t)(uint16_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, z)) << (16 * i);
+    }
+    *nl = a;
+    *nul = b;
+}
+
+static nk_mask64_fn nk_mask64_pick(void)
+{
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("avx2") ? nk_mask64_avx2 : nk_mask64_sse2;
+}
+static nk_mask64_fn nk_mask64 = NULL;
+
+static inline void nk_mask64_tail(const char *p, size_t n, uint64_t *nl, uint64_t *nul)
+{ /* fewer than 64 bytes left: never touch memory past the mapping */
+    char tmp[64];
+    memset(tmp, 1, sizeof tmp);
+    memcpy(tmp, p, n);
+    nk_mask64(tmp, nl, nul);
+    if (n < 64)
+    {
+        *nl &= ((uint64_t)1 << n) - 1;
+        *nul &= ((uint64_t)1 << n) - 1;
+    }
+}
+
+/* number of '\n' in [p, p+n) */
+static uint64_t nk_count_newlines(const char *p, size_t n)
+{
+    uint64_t c = 0, nl, nul;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64)
+    {
+        nk_mask64(p + i, &nl, &nul);
+        c += (uint64_t)__builtin_popcountll(nl);
+    }
+    if (i < n)
+    {
+        nk_mask64_tail(p + i, n - i, &nl, &nul);
+        c += (uint64_t)__builtin_popcountll(nl);
+    }
+    return c;
+}
+
+/* offset of the k-th (1-based) '\n' in [p, p+n), or n when there are fewer */
+static size_t nk_kth_newline(const char *p, size_t n, uint64_t k)
+{
+    uint64_t nl, nul;
+    size_t i = 0;
+    for (; i < n; i += 64)
+    {
+        if (i + 64 <= n)
+            nk_mask64(p + i, &nl, &nul);
+        else
+            nk_mask64_tail(p + i, n - i, &nl, &nul);
+        uint64_t c = (uint64_t)__builtin_popcountll(nl);
+        if (c < k)
+        {
+            k -= c;
+            continue;
+        }
+        while (--k)
+            nl &= nl - 1;
+        return i + (size_t)__builtin_ctzll(nl);
+    }
+    return n;
+}
+
+/* streaming newline iterator over [pos, end) of a buffer */
+typedef struct
+{
+    const char *data;
+    size_t end;     /* scan limit (file size) */
+    size_t blk;     /* offset of the 64-byte block the masks describe */
+    uint64_t nl;    /* unread newline bits of that block */
+    int nul_seen;   /* a NUL byte was seen in a block touched since the last reset */
+} nk_nliter;
+
+static inline void nk_nliter_seek(nk_nliter *it, const char *data, size_t pos, size_t end)
+{
+    it->data = data;
+    it->end = end;
+    it->blk = pos & ~(size_t)63;
+    it->nul_seen = 0;
+    it->nl = 0;
+    if (it->blk < end)
+    {
+        uint64_t nul;
+        if (it->blk + 64 <= end)
+            nk_mask64(data + it->blk, &it->nl, &nul);
+        else
+            nk_mask64_tail(data + it->blk, end - it->blk, &it->nl, &nul);
+        uint64_t keep = ~(uint64_t)0 << (pos & 63);
+        it->nl &= keep;
+        it->nul_seen = (nul & keep) != 0;
+    }
+}
+
+/* offset of the next '\n', or SIZE_MAX at the end of the buffer */
+static inline size_t nk_nliter_next(nk_nliter *it)
+{
+    for (;;)
+    {
+        if (it->nl)
+        {
+            size_t r = it->blk + (size_t)__builtin_ctzll(it->nl);
+            it->nl &= it->nl - 1;
+            return r;
+        }
+        it->blk += 64;
+        if (it->blk >= it->end)
+            return SIZE_MAX;
+        uint64_t nul;
+        if (it->blk + 64 <= it->end)
+            nk_mask64(it->data + it->blk, &it->nl, &nul);
+        else
+            nk_mask64_tail(it->data + it->blk, it->end - it->blk, &it->nl, &nul);
+        it->nul_seen |= nul != 0;
+    }
+}
+
+/* per-file line index: newline counts of fixed chunks, built on all host cores */
+#define NK_LI_CHUNK ((size_t)4 << 20)
 typedef struct
 {
     const nk_buf *f;
-    size_t chunk;
-    uint64_t *counts;
-} nk_count_job;
+    int nchunks;
+    uint64_t *cum; /* cum[i] = newlines in chunks [0, i) */
+} nk_lineidx;
 
-static void nk_count_task(int i, void *a)
+static void nk_lineidx_task(int i, void *a)
 {
-    nk_count_job *j = a;
-    size_t lo = (size_t)i * j->chunk, hi = lo + j->chunk;
-    if (hi > j->f->size)
-        hi = j->f->size;
-    uint64_t n = 0;
-    const char *p = j->f->data + lo, *end = j->f->data + hi;
-    while (p < end && (p = memchr(p, '\n', (size_t)(end - p))) != NULL)
-    {
-        n++;
-        p++;
-    }
-    j->counts[i] = n;
+    nk_lineidx *li = a;
+    size_t lo = (size_t)i * NK_LI_CHUNK, hi = lo + NK_LI_CHUNK;
+    if (hi > li->f->size)
+        hi = li->f->size;
+    li->cum[i + 1] = nk_count_newlines(li->f->data + lo, hi - lo);
 }
 
-/* count_records_seqfile, C:1302-1320 (the newline count is spread over the host cores) */
-uint64_t nk_count_records(const char *data, size_t size, int fastq)
+static void nk_lineidx_build(nk_lineidx *li, const nk_buf *f)
 {
-    nk_buf f = {data, size};
-    int nt = nk_host_threads();
-    size_t chunk = (size_t)8 << 20;
-    int nchunks = (int)((size + chunk - 1) / chunk);
-    uint64_t lines = 0;
-    if (nchunks > 0)
+    if (!nk_mask64)
+        nk_mask64 = nk_mask64_pick();
+    li->f = f;
+    li->nchunks = (int)((f->size + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
+    li->cum = calloc((size_t)li->nchunks + 1, sizeof(uint64_t));
+    nk_parallel_for(li->nchunks, nk_host_threads(), nk_lineidx_task, li);
+    for (int i = 0; i < li->nchunks; i++)
+        li->cum[i + 1] += li->cum[i];
+}
+
+static void nk_lineidx_free(nk_lineidx *li)
+{
+    free(li->cum);
+    li->cum = NULL;
+}
+
+/* offset of the newline with global 0-based index g, or SIZE_MAX */
+static size_t nk_lineidx_find(const nk_lineidx *li, uint64_t g)
+{
+    if (li->nchunks == 0 || g >= li->cum[li->nchunks])
+        return SIZE_MAX;
+    int lo = 0, hi = li->nchunks - 1; /* last chunk whose cum <= g */
+    while (lo < hi)
     {
-        uint64_t *counts = calloc((size_t)nchunks, sizeof *counts);
-        nk_count_job job = {&f, chunk, counts};
-        nk_parallel_for(nchunks, nt, nk_count_task, &job);
-        for (int i = 0; i < nchunks; i++)
-            lines += counts[i];
-        free(counts);
+        int mid = (lo + hi + 1) / 2;
+        if (li->cum[mid] <= g)
+            lo = mid;
+        else
+            hi = mid - 1;
     }
-    if (size > 0 && data[size - 1] != '\n')
+    size_t base = (size_t)lo * NK_LI_CHUNK, n = NK_LI_CHUNK;
+    if (base + n > li->f->size)
+        n = li->f->size - base;
+    return base + nk_kth_newline(li->f->data + base, n, g - li->cum[lo] + 1);
+}
+
+/* newlines in [0, pos) */
+static uint64_t nk_lineidx_before(const nk_lineidx *li, size_t pos)
+{
+    if (pos == 0 || li->nchunks == 0)
+        return 0;
+    if (pos > li->f->size)
+        pos = li->f->size;
+    int c = (int)(pos / NK_LI_CHUNK);
+    if (c >= li->nchunks)
+        return li->cum[li->nchunks];
+    return li->cum[c] + nk_count_newlines(li->f->data + (size_t)c * NK_LI_CHUNK, pos - (size_t)c * NK_LI_CHUNK);
+}
+
+static uint64_t nk_records_from_lines(const nk_buf *f, uint64_t lines, int fastq)
+{ /* count_records_seqfile, C:1302-1320 */
+    if (f->size > 0 && f->data[f->size - 1] != '\n')
         lines++;
     return fastq ? lines / 4 : lines / 2;
 }
 
-/* calculate_thread_positions_from_records, C:1265-1300 */
-static void nk_ranges_by_records(const nk_buf *f, int p, int fastq, uint64_t records, uint64_t *st, uint64_t *en)
+uint64_t nk_count_records(const char *data, size_t size, int fastq)
 {
+    nk_buf f = {data, size};
+    nk_lineidx li;
+    nk_lineidx_build(&li, &f);
+    uint64_t r = nk_records_from_lines(&f, li.nchunks ? li.cum[li.nchunks] : 0, fastq);
+    nk_lineidx_free(&li);
+    return r;
+}
+
+/* calculate_thread_positions_from_records, C:1265-1300: partition t ends at the `want`-th newline counted
+ * from its own start; found through the line index instead of a sequential scan of the file */
+static void nk_ranges_by_records(const nk_lineidx *li, int p, int fastq, uint64_t records, uint64_t *st, uint64_t *en)
+{
+    const nk_buf *f = li->f;
     uint64_t per = records / (uint64_t)p;
     if (p < 2 || per < 1 || f->size < 1)
         return;
@@ -267,17 +453,12 @@ static void nk_ranges_by_records(const nk_buf *f, int p, int fastq, uint64_t rec
     en[p - 1] = f->size - 1;
     for (int t = 0; t < p - 1; t++)
     {
-        uint64_t seen = 0;
-        const char *q = f->data + st[t], *end = f->data + f->size;
-        while (q < end && (q = memchr(q, '\n', (size_t)(end - q))) != NULL)
+        uint64_t before = nk_lineidx_before(li, st[t]);
+        size_t pos = want > 0 ? nk_lineidx_find(li, before + (uint64_t)want - 1) : SIZE_MAX;
+        if (pos != SIZE_MAX)
         {
-            if (++seen == (uint64_t)want)
-            {
-                en[t] = (uint64_t)(q - f->data);
-                st[t + 1] = en[t] + 1;
-                break;
-            }
-            q++;
+            en[t] = pos;
+            st[t + 1] = pos + 1;
         }
     }
 }
@@ -296,7 +477,10 @@ int nk_partition_ranges(const char *data, size_t size, int partitions, int fastq
     }
     if (mode == 0)
         return nk_ranges_by_size(&f, partitions, fastq, starts, ends, &d) ? NK_EDATA : NK_OK;
-    nk_ranges_by_records(&f, partitions, fastq, records, starts, ends);
+    nk_lineidx li;
+    nk_lineidx_build(&li, &f);
+    nk_ranges_by_records(&li, partitions, fastq, records, starts, ends);
+    nk_lineidx_free(&li);
     return NK_OK;
 }
 
@@ -349,6 +533,7 @@ typedef struct
 {
     size_t fp, fe, rp, re;
     int done;
+    nk_nliter itf, itr; /* newline iterators positioned at fp / rp */
 } nk_cursor;
 
 typedef struct
@@ -382,13 +567,15 @@ typedef struct
     uint64_t last_processed;
 } nk_part;
 
+#define NK_NBUF 3 /* index step i+1, run step i on the GPU and write step i-1 at the same time */
+
 typedef struct
 {
     int ordinal;
     nkd_engine *eng;
     int n_parts;
     int *parts; /* indices into ctx->part */
-    nk_stepbuf sb[2];
+    nk_stepbuf sb[NK_NBUF];
     double index_s, device_s, write_s;
     uint64_t h2d, d2h;
     int rc;
@@ -470,7 +657,7 @@ void nk_destroy(nk_ctx *c)
     for (int d = 0; d < c->n_dev; d++)
     {
         nk_dev *dv = &c->dev[d];
-        for (int b = 0; b < 2; b++)
+        for (int b = 0; b < NK_NBUF; b++)
             nk_free_stepbuf(&dv->sb[b], dv->n_parts);
         if (dv->eng)
             nkd_destroy(dv->eng);
@@ -594,7 +781,7 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
             nk_destroy(c);
             return rc;
         }
-        for (int b = 0; b < 2; b++)
+        for (int b = 0; b < NK_NBUF; b++)
         {
             nk_stepbuf *sb = &dv->sb[b];
             sb->seq = nkd_alloc_pinned((size_t)ec.max_step_bytes + 64);
@@ -901,27 +1088,85 @@ static void nk_index_task(int li, void *a)
         nk_span sf = {cur->fp, 0, 0, 0, 1}, sr = {cur->rp, 0, 0, 0, 1};
         size_t fp = cur->fp, rp = cur->rp;
         int more = 1, complete = 1, plain_f = 1, plain_r = 1;
-        for (int i = 0; i < per; i++)
+        /* fast path: every line of the record ends in '\n' within 1023 chars and no NUL is near, so
+         * read_line (C:394-409) consumes exactly "text\n" each time; positions come from the SIMD iterator */
+        int fast = 1;
         {
-            uint32_t lf = 0, lr = 0;
-            int mf = 1, mr = 1;
-            size_t f0 = fp, r0 = rp;
-            fp = nk_take_line(ff, fp, &lf, &mf, &plain_f);
+            size_t q = fp;
+            for (int i = 0; i < per && fast; i++)
+            {
+                size_t nl = nk_nliter_next(&cur->itf);
+                if (nl == SIZE_MAX || nl - q >= (size_t)NK_MAX_LINE)
+                    fast = 0;
+                else
+                {
+                    if (i == 1)
+                    {
+                        sf.seq_rel = (uint16_t)(q - cur->fp);
+                        sf.seq_len = (uint16_t)(nl - q);
+                    }
+                    q = nl + 1;
+                }
+            }
+            if (fast && !cur->itf.nul_seen)
+                fp = q;
+            else
+                fast = 0;
+            if (paired && fast)
+            {
+                q = rp;
+                for (int i = 0; i < per && fast; i++)
+                {
+                    size_t nl = nk_nliter_next(&cur->itr);
+                    if (nl == SIZE_MAX || nl - q >= (size_t)NK_MAX_LINE)
+                        fast = 0;
+                    else
+                    {
+                        if (i == 1)
+                        {
+                            sr.seq_rel = (uint16_t)(q - cur->rp);
+                            sr.seq_len = (uint16_t)(nl - q);
+                        }
+                        q = nl + 1;
+                    }
+                }
+                if (fast && !cur->itr.nul_seen)
+                    rp = q;
+                else
+                    fast = 0;
+            }
+        }
+        if (fast)
+            more = nk_at(ff, fp) != '\0' && (!paired || nk_at(rf, rp) != '\0');
+        else
+        { /* anything unusual: the byte-exact line reader, then re-aim the iterators */
+            fp = cur->fp;
+            rp = cur->rp;
+            for (int i = 0; i < per; i++)
+            {
+                uint32_t lf = 0, lr = 0;
+                int mf = 1, mr = 1;
+                size_t f0 = fp, r0 = rp;
+                fp = nk_take_line(ff, fp, &lf, &mf, &plain_f);
+                if (paired)
+                    rp = nk_take_line(rf, rp, &lr, &mr, &plain_r);
+                if (i == 1)
+                {
+                    sf.seq_rel = (uint16_t)(f0 - cur->fp);
+                    sf.seq_len = (uint16_t)lf;
+                    sr.seq_rel = (uint16_t)(r0 - cur->rp);
+                    sr.seq_len = (uint16_t)lr;
+                }
+                if (!mf || !mr)
+                {
+                    more = 0;
+                    complete = (i == per - 1);
+                    break;
+                }
+            }
+            nk_nliter_seek(&cur->itf, ff->data, fp, ff->size);
             if (paired)
-                rp = nk_take_line(rf, rp, &lr, &mr, &plain_r);
-            if (i == 1)
-            {
-                sf.seq_rel = (uint16_t)(f0 - cur->fp);
-                sf.seq_len = (uint16_t)lf;
-                sr.seq_rel = (uint16_t)(r0 - cur->rp);
-                sr.seq_len = (uint16_t)lr;
-            }
-            if (!mf || !mr)
-            {
-                more = 0;
-                complete = (i == per - 1);
-                break;
-            }
+                nk_nliter_seek(&cur->itr, rf->data, rp, rf->size);
         }
         if (!complete)
         { /* a record whose lines cannot all be read is not scored (reference: undefined, C:1616-1629) */
@@ -1035,43 +1280,44 @@ typedef struct
     size_t *rec_base; /* first record of each partition inside the step's accept array */
 } nk_write_job;
 
-static void nk_write_task(int li, void *a)
+/* one task per (partition, mate): the forward and reverse outputs of a partition are independent files */
+static void nk_write_task(int idx, void *a)
 {
     nk_write_job *j = a;
     nk_ctx *c = j->c;
+    const int paired = c->paired, stride = paired ? 2 : 1;
+    const int li = idx / stride, mate = idx % stride;
     nk_part *p = &c->part[j->dv->parts[li]];
     nk_pstep *ps = &j->sb->ps[li];
     const uint8_t *acc = j->sb->accept + j->rec_base[li];
-    const int per = c->cfg.in_fastq ? 4 : 2, paired = c->paired, stride = paired ? 2 : 1;
+    const int per = c->cfg.in_fastq ? 4 : 2;
     const int to_fasta = c->cfg.in_fastq && !c->cfg.out_fastq;
+    FILE *out = mate ? p->out_r : p->out_f;
+    const nk_buf *src = mate ? &c->rf : &c->ff;
     char tmp[4 * NK_MAX_LINE + 16];
     size_t nrec = ps->n_records;
     if (ps->fatal_record >= 0 && (size_t)ps->fatal_record < nrec)
         nrec = (size_t)ps->fatal_record; /* the reference stops at the first non-DNA record */
+    uint64_t printed = 0;
     for (size_t r = 0; r < nrec; r++)
     {
-        p->processed++;
         if (!acc[r])
-        {
-            p->skipped++;
             continue;
-        }
-        p->printed++;
-        const nk_span *sf = &ps->spans[r * stride];
+        printed++;
+        const nk_span *sp = &ps->spans[r * (size_t)stride + (size_t)mate];
         if (to_fasta)
         {
             if (paired) /* single-end fq->fa prints nothing although it counts as printed, C:1995-1999 */
-            {
-                nk_emit_fasta(p->out_f, &c->ff, sf, 1, tmp);
-                nk_emit_fasta(p->out_r, &c->rf, sf + 1, 0, tmp);
-            }
+                nk_emit_fasta(out, src, sp, mate == 0, tmp);
         }
         else
-        {
-            nk_emit_lines(p->out_f, &c->ff, sf, per, tmp);
-            if (paired)
-                nk_emit_lines(p->out_r, &c->rf, sf + 1, per, tmp);
-        }
+            nk_emit_lines(out, src, sp, per, tmp);
+    }
+    if (mate == 0)
+    {
+        p->processed += nrec;
+        p->printed += printed;
+        p->skipped += nrec - printed;
     }
 }
 
@@ -1081,12 +1327,14 @@ typedef struct
 {
     nk_ctx *c;
     nk_dev *dv;
-    /* hand-off between the pipeline thread (index, write) and its GPU thread (stage, run, fetch) */
+    /* three stages over NK_NBUF staging buffers: indexer (this thread) -> GPU thread -> writer thread */
     pthread_mutex_t mu;
     pthread_cond_t cv;
-    int submitted, completed, quit; /* step counters */
-    int gpu_rc;
-    int64_t first_invalid[2];
+    int built, completed, written; /* steps finished by each stage */
+    int total;                     /* number of steps once the indexer ran dry, else -1 */
+    int abort_rc;                  /* first error of any stage */
+    int64_t first_invalid[NK_NBUF];
+    int t_index, t_write;
 } nk_pipe;
 
 static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_invalid)
@@ -1115,22 +1363,34 @@ static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_inv
     return rc;
 }
 
+static void nk_pipe_fail(nk_pipe *pp, int rc)
+{
+    pthread_mutex_lock(&pp->mu);
+    if (!pp->abort_rc)
+        pp->abort_rc = rc;
+    pthread_cond_broadcast(&pp->cv);
+    pthread_mutex_unlock(&pp->mu);
+}
+
 static void *nk_gpu_thread(void *a)
 {
     nk_pipe *pp = a;
     for (int step = 0;; step++)
     {
         pthread_mutex_lock(&pp->mu);
-        while (pp->submitted <= step && !pp->quit)
+        while (pp->built <= step && pp->total < 0 && !pp->abort_rc)
             pthread_cond_wait(&pp->cv, &pp->mu);
-        int quit = pp->quit && pp->submitted <= step;
+        int stop = pp->abort_rc || (pp->built <= step);
         pthread_mutex_unlock(&pp->mu);
-        if (quit)
+        if (stop)
             break;
-        int rc = nk_gpu_step(pp->c, pp->dv, &pp->dv->sb[step & 1], &pp->first_invalid[step & 1]);
+        int rc = nk_gpu_step(pp->c, pp->dv, &pp->dv->sb[step % NK_NBUF], &pp->first_invalid[step % NK_NBUF]);
+        if (rc)
+        {
+            nk_pipe_fail(pp, rc);
+            break;
+        }
         pthread_mutex_lock(&pp->mu);
-        if (rc && !pp->gpu_rc)
-            pp->gpu_rc = rc;
         pp->completed = step + 1;
         pthread_cond_broadcast(&pp->cv);
         pthread_mutex_unlock(&pp->mu);
@@ -1202,69 +1462,95 @@ static void nk_write_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
         b += sb->ps[i].n_records;
     }
     nk_write_job job = {c, dv, sb, rec_base};
-    nk_parallel_for(dv->n_parts, threads, nk_write_task, &job);
+    nk_parallel_for(dv->n_parts * (c->paired ? 2 : 1), threads, nk_write_task, &job);
     dv->write_s += nk_now() - t0;
 }
 
-/* Two staging buffers: while the GPU thread runs step i, this thread indexes step i+1 into the other
- * buffer, then (once i is back) submits i+1 and writes step i's accepted records. */
+static void *nk_writer_thread(void *a)
+{
+    nk_pipe *pp = a;
+    nk_ctx *c = pp->c;
+    nk_dev *dv = pp->dv;
+    for (int step = 0;; step++)
+    {
+        pthread_mutex_lock(&pp->mu);
+        while (pp->completed <= step && !(pp->total >= 0 && step >= pp->total) && !pp->abort_rc)
+            pthread_cond_wait(&pp->cv, &pp->mu);
+        int stop = pp->completed <= step; /* ran dry or aborted before this step finished on the GPU */
+        pthread_mutex_unlock(&pp->mu);
+        if (stop)
+            break;
+        nk_stepbuf *sb = &dv->sb[step % NK_NBUF];
+        int rc = NK_OK;
+        if (pp->first_invalid[step % NK_NBUF] >= 0)
+            rc = nk_report_invalid(c, dv, sb, pp->first_invalid[step % NK_NBUF]);
+        nk_write_step(c, dv, sb, pp->t_write);
+        if (rc)
+        {
+            nk_pipe_fail(pp, rc);
+            break;
+        }
+        pthread_mutex_lock(&pp->mu);
+        pp->written = step + 1;
+        pthread_cond_broadcast(&pp->cv);
+        pthread_mutex_unlock(&pp->mu);
+    }
+    return NULL;
+}
+
+/* per-GPU pipeline: this thread indexes records into the next free staging buffer */
 static void *nk_device_pipeline(void *a)
 {
     nk_pipe *pp = a;
     nk_ctx *c = pp->c;
     nk_dev *dv = pp->dv;
     int threads = c->threads / c->n_dev;
-    if (threads < 1)
-        threads = 1;
+    if (threads < 2)
+        threads = 2;
+    pp->t_write = threads / 3 > 0 ? threads / 3 : 1;
+    pp->t_index = threads - pp->t_write;
     dv->rc = NK_OK;
-    if (nk_build_step(c, dv, &dv->sb[0], threads) == 0)
-        return NULL;
-    pthread_t gth;
     pthread_mutex_init(&pp->mu, NULL);
     pthread_cond_init(&pp->cv, NULL);
-    pp->submitted = 1;
-    pp->completed = pp->quit = 0;
-    pp->gpu_rc = 0;
-    if (pthread_create(&gth, NULL, nk_gpu_thread, pp) != 0)
+    pp->built = pp->completed = pp->written = 0;
+    pp->total = -1;
+    pp->abort_rc = 0;
+    pthread_t gth, wth;
+    if (pthread_create(&gth, NULL, nk_gpu_thread, pp) != 0 || pthread_create(&wth, NULL, nk_writer_thread, pp) != 0)
     {
         dv->rc = NK_EINTERNAL;
-        snprintf(dv->err, sizeof dv->err, "cannot start the device thread");
+        snprintf(dv->err, sizeof dv->err, "cannot start the device threads");
         return NULL;
     }
     for (int step = 0;; step++)
     {
-        int have_next = nk_build_step(c, dv, &dv->sb[(step + 1) & 1], threads) > 0;
         pthread_mutex_lock(&pp->mu);
-        while (pp->completed <= step)
+        while (step - pp->written >= NK_NBUF && !pp->abort_rc)
             pthread_cond_wait(&pp->cv, &pp->mu);
-        int rc = pp->gpu_rc;
+        int stop = pp->abort_rc != 0;
         pthread_mutex_unlock(&pp->mu);
-        if (rc)
-        {
-            dv->rc = rc;
+        if (stop)
             break;
-        }
-        nk_stepbuf *sb = &dv->sb[step & 1];
-        if (pp->first_invalid[step & 1] >= 0)
-            dv->rc = nk_report_invalid(c, dv, sb, pp->first_invalid[step & 1]);
-        if (have_next && !dv->rc)
-        {
-            pthread_mutex_lock(&pp->mu);
-            pp->submitted = step + 2;
-            pthread_cond_broadcast(&pp->cv);
-            pthread_mutex_unlock(&pp->mu);
-        }
-        nk_write_step(c, dv, sb, threads);
-        if (!have_next || dv->rc)
+        size_t n = nk_build_step(c, dv, &dv->sb[step % NK_NBUF], pp->t_index);
+        pthread_mutex_lock(&pp->mu);
+        if (n == 0)
+            pp->total = step;
+        else
+            pp->built = step + 1;
+        pthread_cond_broadcast(&pp->cv);
+        pthread_mutex_unlock(&pp->mu);
+        if (n == 0)
             break;
     }
     pthread_mutex_lock(&pp->mu);
-    pp->quit = 1;
+    if (pp->total < 0)
+        pp->total = pp->built; /* aborted: let the other stages drain */
     pthread_cond_broadcast(&pp->cv);
     pthread_mutex_unlock(&pp->mu);
     pthread_join(gth, NULL);
-    if (!dv->rc && pp->gpu_rc)
-        dv->rc = pp->gpu_rc;
+    pthread_join(wth, NULL);
+    if (pp->abort_rc)
+        dv->rc = pp->abort_rc;
     pthread_mutex_destroy(&pp->mu);
     pthread_cond_destroy(&pp->cv);
     return NULL;
@@ -1301,9 +1587,14 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     }
     else
     { /* C:1815-1828: the forward file's record count is applied to both files */
-        uint64_t recs = nk_count_records(fwd, fsize, fastq);
-        nk_ranges_by_records(&c->ff, P, fastq, recs, c->fs, c->fe);
-        nk_ranges_by_records(&c->rf, P, fastq, recs, c->rs, c->re);
+        nk_lineidx lf, lr;
+        nk_lineidx_build(&lf, &c->ff);
+        nk_lineidx_build(&lr, &c->rf);
+        uint64_t recs = nk_records_from_lines(&c->ff, lf.nchunks ? lf.cum[lf.nchunks] : 0, fastq);
+        nk_ranges_by_records(&lf, P, fastq, recs, c->fs, c->fe);
+        nk_ranges_by_records(&lr, P, fastq, recs, c->rs, c->re);
+        nk_lineidx_free(&lf);
+        nk_lineidx_free(&lr);
     }
     for (int i = 0; i < c->n_local; i++)
     {
@@ -1313,6 +1604,11 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
         p->cur.rp = c->rs[p->gid];
         p->cur.re = c->re[p->gid];
         p->cur.done = 0;
+        if (!nk_mask64)
+            nk_mask64 = nk_mask64_pick();
+        nk_nliter_seek(&p->cur.itf, c->ff.data, p->cur.fp, c->ff.size);
+        if (paired)
+            nk_nliter_seek(&p->cur.itr, c->rf.data, p->cur.rp, c->rf.size);
         p->t_start = nk_now();
         p->last_processed = p->processed;
     }
