@@ -1,0 +1,49 @@
+"""Worker for tests/test_multirank_gloo.py: one rank of the N>1 path on CPU (gloo).  Each rank owns a contiguous
+slice of the fixed -p partitions (as bench.py --gpus N does), runs the host pipeline on it, and the three counters
+are summed with all_reduce -- the only cross-rank traffic the path has (C:1897-1909)."""
+import ctypes
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from nomalise_kmers_multi_large_b200 import capi  # noqa: E402
+from nomalise_kmers_multi_large_b200.pipeline import Pipeline  # noqa: E402
+
+
+def main():
+    fwd_path, rev_path, out_dir, parts, k, depth, libpath = sys.argv[1:8]
+    parts, k, depth = int(parts), int(k), int(depth)
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = ctypes.CDLL(libpath)
+    capi._declare_engine(lib)
+    capi._declare_pipeline(lib)
+    per = parts // world
+    fwd, rev = np.fromfile(fwd_path, dtype=np.uint8), np.fromfile(rev_path, dtype=np.uint8)
+    with Pipeline(k=k, depth=depth, canonical=True, partitions=parts, memory_gb=1, out_dir=out_dir, devices=(0,),
+                  part_first=rank * per, part_count=per, step_pairs=64, lib=lib) as p:
+        p.seed(fwd, 3000001)
+        p.seed(rev, 3000001)
+        p.seed_finish()
+        p.process_paired(fwd, rev)
+        p.finish()
+        t = p.totals()
+    sums = torch.tensor([t["processed"], t["printed"], t["skipped"]], dtype=torch.int64)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    mx = torch.tensor([t["max_used"]], dtype=torch.int64)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        Path(out_dir, "totals.json").write_text(json.dumps({"processed": int(sums[0]), "printed": int(sums[1]),
+                                                            "skipped": int(sums[2]), "max_used": int(mx[0])}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

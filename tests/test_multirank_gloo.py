@@ -1,0 +1,48 @@
+"""N>1 on CPU: two gloo ranks, each owning half of the fixed -p partitions (the placement bench.py --gpus 2 uses),
+must together produce exactly the files and counters of one process / of the oracle -- partitions share nothing."""
+import json
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+from tests import cli_cases as cc
+from tests import oracle_lib as ol
+
+ROOT = Path(__file__).resolve().parent.parent
+EMU_LIB = ROOT / "tests" / "emu" / "libnk_emu.so"
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_ranks_equal_one_process(tmp_path):
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "emu")], check=True, capture_output=True)
+    ol.build_oracle()
+    f, r = cc.synth(tmp_path, "s", 1500, seed=11)
+    parts, k, depth = 4, 21, 16
+    want = cc.run_cli(ol.ORACLE_CLI, ["-f", f, "-r", r, "-k", k, "-c", "-p", parts, "-d", depth, "-m", 1], tmp_path / "oracle")
+    out = tmp_path / "ranks"
+    out.mkdir()
+    port = free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "_rank_worker.py"), str(f), str(r), str(out),
+                                       str(parts), str(k), str(depth), str(EMU_LIB)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        o, e = p.communicate(timeout=600)
+        assert p.returncode == 0, e[-2000:]
+    import hashlib
+    got = {p.name: hashlib.md5(p.read_bytes()).hexdigest() for p in sorted(out.glob("output_*"))}
+    assert got == want["files"]
+    totals = json.loads((out / "totals.json").read_text())
+    assert (totals["processed"], totals["printed"], totals["skipped"], totals["max_used"]) == want["counters"][-1]
