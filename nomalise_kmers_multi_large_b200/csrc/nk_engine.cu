@@ -333,6 +333,12 @@ struct CudaBackend
             cuda_err = std::string(what) + ": " + cudaGetErrorString(e);
         return false;
     }
+    /* the current device is per host thread: every API entry selects this engine's GPU */
+    void enter()
+    {
+        if (dev >= 0)
+            cudaSetDevice(dev);
+    }
     bool failed(std::string &msg)
     {
         ok(cudaGetLastError(), "kernel launch");

@@ -47,6 +47,7 @@ void nkd_destroy(nkd_engine *h)
 {
     if (!h)
         return;
+    h->e.be.enter();
     h->e.destroy();
     delete h;
 }
@@ -56,15 +57,18 @@ const char *nkd_last_error(const nkd_engine *h) { return h ? h->e.err.c_str() : 
 int nkd_seed_step(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
                   int64_t *first_invalid)
 {
+    h->e.be.enter();
     return nkd_done(h, h->e.seed_step(seq, seq_bytes, reads, n_reads, first_invalid));
 }
 int nkd_stage_segments(nkd_engine *h, const uint8_t *seq_base, const nkd_segment *segs, int n_segs, int paired)
 {
+    h->e.be.enter();
     if (!h->e.seeded)
         return h->e.fail(NK_EINVAL, "nkd_stage_segments before nkd_seed_finish");
     return nkd_done(h, h->e.stage_segments(seq_base, segs, n_segs, paired, h->e.cfg.n_parts, false));
 }
-int nkd_seed_finish(nkd_engine *h) { return nkd_done(h, h->e.seed_finish()); }
+int nkd_seed_finish(nkd_engine *h) {
+    h->e.be.enter(); return nkd_done(h, h->e.seed_finish()); }
 int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)
 {
     *out = h->e.seed.st;
@@ -74,17 +78,21 @@ int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)
 }
 int nkd_seed_export(nkd_engine *h, uint64_t *keys, int32_t *counts, uint64_t capacity)
 {
+    h->e.be.enter();
     return nkd_done(h, h->e.export_table(h->e.seed, keys, counts, capacity));
 }
 int nkd_stage(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads, int paired)
 {
+    h->e.be.enter();
     if (!h->e.seeded)
         return h->e.fail(NK_EINVAL, "nkd_stage before nkd_seed_finish");
     return nkd_done(h, h->e.stage(seq, seq_bytes, reads, n_reads, paired, h->e.cfg.n_parts, false));
 }
-int nkd_run(nkd_engine *h) { return nkd_done(h, h->e.run_step()); }
+int nkd_run(nkd_engine *h) {
+    h->e.be.enter(); return nkd_done(h, h->e.run_step()); }
 int nkd_fetch(nkd_engine *h, uint8_t *accept, size_t n_records, int64_t *first_invalid)
 {
+    h->e.be.enter();
     return nkd_done(h, h->e.fetch(accept, n_records, first_invalid));
 }
 int nkd_last_run_ms(nkd_engine *h, float *total_ms, float *probe_ms)
@@ -114,6 +122,7 @@ int nkd_part_stats_get(nkd_engine *h, int part, nkd_part_stats *out)
 }
 int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_t capacity)
 {
+    h->e.be.enter();
     if (part < 0 || part >= (int)h->e.parts.size())
         return h->e.fail(NK_EINVAL, "no such partition");
     return nkd_done(h, h->e.export_table(h->e.parts[part], keys, counts, capacity));
@@ -121,6 +130,7 @@ int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_
 int nkd_extract_keys(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
                      uint64_t *keys_out, size_t n_ops, uint8_t *invalid_out)
 {
+    h->e.be.enter();
     return nkd_done(h, h->e.extract_keys(seq, seq_bytes, reads, n_reads, keys_out, n_ops, invalid_out));
 }
 

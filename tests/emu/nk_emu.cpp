@@ -28,6 +28,7 @@ struct EmuBackend
         return 0;
     }
     void shutdown() {}
+    void enter() {}
     bool failed(std::string &) { return false; }
     void *alloc(size_t n) { return malloc(n ? n : 1); }
     void release(void *p) { free(p); }
