@@ -39,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 
 K, DEPTH, COVERAGE, PARTS, READ_LEN, TRANSCRIPTS, SEED = 25, 100, 0.9, 8, 150, 20000, 1
 SEED_RECORDS = 1 + 3_000_000  # 1 + 3e6 / forward_file_count, C:2242
+CLASSES = ["probe", "open", "apply", "classify", "sort_rank", "commit", "decide", "growth_undo"]
 
 
 def shm_dir():
@@ -248,7 +249,9 @@ def run_ours(args):
             sampler.active = False
         barrier(dist, local)
         tot = [c.totals() for c in ctxs]
-        agg = {k: sum(t[k] for t in tot) for k in tot[0]}
+        agg = {k: sum(t[k] for t in tot) for k in tot[0] if k != "class_ms"}
+        for i, name in enumerate(CLASSES):
+            agg["ms_" + name] = sum(t["class_ms"][i] for t in tot)
         agg["wall_s"], agg["seed_s"] = wall, seed_s
         for c in ctxs:
             c.close()
@@ -257,13 +260,13 @@ def run_ours(args):
     if sampler:
         sampler.stop()
     shutil.rmtree(out_dir, ignore_errors=True)
-    n = len(steps)
+    n = n_ = len(steps)
     # per-step maxima over ranks (device time and wall), sums of the counted quantities
     dev_ms = sum(all_max(dist, local, s["run_ms"]) for s in steps)
     wall_s = sum(all_max(dist, local, s["wall_s"]) for s in steps)
     keys = ["processed", "printed", "skipped", "launches", "probe_launches", "ops", "touches", "probe_touches",
             "slow_events", "expansions", "h2d_bytes", "d2h_bytes", "probe_ms", "index_seconds", "device_seconds",
-            "write_seconds", "seed_s"]
+            "write_seconds", "seed_s", "pend_events", "open_ops"] + ["ms_" + n for n in CLASSES]
     sums = dict(zip(keys, all_sum(dist, local, [sum(s[k] for s in steps) for k in keys])))
     if rank != 0:
         return
@@ -301,9 +304,11 @@ def run_ours(args):
                      "avg_launch_ms": sums["probe_ms"] / max(sums["probe_launches"], 1),
                      "share_of_step": sums["probe_ms"] / max(world, 1) / dev_ms if dev_ms else None,
                      "touches_per_op": sums["touches"] / max(sums["ops"], 1)},
+        "kernel_ms_per_step": {n: sums["ms_" + n] / n_ / max(world, 1) for n in CLASSES},
         "clocks": sampler.summary() if sampler else None,
         "counters": {"printed": sums["printed"] / n, "skipped": sums["skipped"] / n, "ops": sums["ops"] / n,
                      "touches": sums["touches"] / n, "slow_events": sums["slow_events"] / n,
+                     "pending_list_entries": sums["pend_events"] / n, "open_list_entries": sums["open_ops"] / n,
                      "expansions_in_scoring": sums["expansions"] / n},
     }
     if world == 1 and not args.no_cpu_baseline:

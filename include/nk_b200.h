@@ -137,6 +137,10 @@ typedef struct
     double probe_ms;         /* sum of k_probe device times (CUDA events) */
     uint64_t probe_touches;  /* slots visited inside k_probe (the rest are visited by k_open) */
     uint64_t h2d_bytes, d2h_bytes;
+    /* CUDA-event time per kernel class in scoring steps: 0 probe, 1 open, 2 apply, 3 classify,
+     * 4 sort+rank, 5 commit, 6 decide, 7 growth/undo */
+    double class_ms[8];
+    uint64_t pend_events, open_ops, slow_events; /* list entries incl. chunk holes */
 } nkd_run_stats;
 int nkd_run_stats_get(nkd_engine *e, nkd_run_stats *out);
 
@@ -207,6 +211,8 @@ typedef struct
     double run_ms, probe_ms;
     uint64_t launches, probe_launches;
     uint64_t ops, touches, probe_touches, slow_events, expansions;
+    double class_ms[8]; /* see nkd_run_stats */
+    uint64_t pend_events, open_ops;
 } nk_totals;
 
 int nk_totals_get(nk_ctx *c, nk_totals *out);

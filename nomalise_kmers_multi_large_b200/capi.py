@@ -51,10 +51,11 @@ class RunStats(C.Structure):
     """nkd_run_stats"""
     _fields_ = [("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("run_ms", C.c_double),
                 ("probe_ms", C.c_double), ("probe_touches", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("class_ms", C.c_double * 8), ("pend_events", C.c_uint64),
+                ("open_ops", C.c_uint64), ("slow_events", C.c_uint64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "class_ms" else getattr(self, n)) for n, _ in self._fields_}
 
 
 class EngineConfig(C.Structure):
@@ -82,10 +83,11 @@ class Totals(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("run_ms", C.c_double), ("probe_ms", C.c_double),
                 ("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("ops", C.c_uint64),
                 ("touches", C.c_uint64), ("probe_touches", C.c_uint64), ("slow_events", C.c_uint64),
-                ("expansions", C.c_uint64)]
+                ("expansions", C.c_uint64), ("class_ms", C.c_double * 8), ("pend_events", C.c_uint64),
+                ("open_ops", C.c_uint64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "class_ms" else getattr(self, n)) for n, _ in self._fields_}
 
 
 ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step", "nkd_seed_finish", "nkd_seed_stats",

@@ -85,7 +85,7 @@ struct NkPend /* an increment of a counter that was not saturated at step start 
 {
     unsigned slot;
     unsigned tw; /* t<<2 | which<<1 | terminal */
-    int base;    /* counter value at step start (1 for the post-claim counter) */
+    int base;    /* special list: counter value at step start (1 for the post-claim counter); else unused */
     unsigned read;
 };
 
@@ -105,7 +105,8 @@ struct NkCounters
     unsigned n_open, n_pend, n_claim, n_slow;
     unsigned overflow;
     unsigned inv_max; /* max over invalid records of NK_TMAX - record index; 0 = none */
-    unsigned pad[2];
+    unsigned n_spec;
+    unsigned pad;
     unsigned long long probe_touches; /* slots visited by k_probe (all partitions) */
     unsigned long long touches[256]; /* per partition, slots visited */
     unsigned long long real_ops[256];
@@ -122,7 +123,8 @@ enum
     NK_LIST_OPEN = 1,
     NK_LIST_CLAIM = 2,
     NK_LIST_SLOW = 3,
-    NK_NLISTS = 4
+    NK_LIST_SPEC = 4, /* events on slots claimed inside the step (their counters need the apply round) */
+    NK_NLISTS = 5
 };
 #define NK_HOLE 0xFFFFFFFFu
 
@@ -154,6 +156,8 @@ struct NkRun
     unsigned open_cap;
     NkPend *pend;
     unsigned pend_cap;
+    NkPend *spec;
+    unsigned spec_cap;
     NkClaim *claim;
     unsigned claim_cap;
     unsigned long long *slow_key, *slow_val;
@@ -202,6 +206,9 @@ NK_HD void nk_red_add32(int *p, int v)
     *p += v;
 #endif
 }
+/* count and aux live in one 8-byte word (count low, aux high): +1/+1 or -1/-1 in ONE atomic */
+#define NK_BOTH_PLUS 0x0000000100000001ull
+#define NK_BOTH_MINUS 0xFFFFFFFEFFFFFFFFull
 NK_HD void nk_red_add64(unsigned long long *p, unsigned long long v)
 {
 #if NK_DEVICE_CODE
@@ -375,13 +382,47 @@ NK_HD unsigned long long nk_window_key_ascii(const unsigned char *s, int k, int 
 
 /* ---------------------------------------------------------------- events */
 
-/* one increment of counter (slot, which) by the operation at time t.  which: 0 = count, 1 = aux
- * (count after an in-step claim, value = 1 + aux).  base = the counter's value at step start. */
-NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int which, int base, int terminal, unsigned t,
+/* Increment of the ordinary counter of a slot that is NOT claimed inside this step (stored before the step, or
+ * a ghost that stays empty).  cnt0 = count - aux is its value at step start for every reader at every moment,
+ * because unsaturated increments bump count and aux together in one 64-bit RED (aux is 0 between steps and is
+ * zeroed again by nk_classify_op).  Saturated: every test is true, only count moves.  The same holds for the
+ * -1 replay of an abandoned run. */
+NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int count, unsigned aux, int terminal, unsigned t,
                     unsigned read, int &high_acc)
 {
+    if (count - (int)aux >= P.depth - 1)
+    {
+        nk_red_add32(&pd.tab[slot].count, P.delta);
+        if (terminal)
+            high_acc += P.delta;
+        return;
+    }
+    nk_red_add64(reinterpret_cast<unsigned long long *>(&pd.tab[slot].count), P.delta > 0 ? NK_BOTH_PLUS : NK_BOTH_MINUS);
+    if (P.record)
+    {
+        unsigned idx = nk_list_append(P, NK_LIST_PEND, &P.ctr->n_pend);
+        if (idx < P.pend_cap)
+        {
+            NkPend r;
+            r.slot = slot;
+            r.tw = (t << 2) | (unsigned)terminal;
+            r.base = 0;
+            r.read = read;
+            P.pend[idx] = r;
+        }
+        else
+            nk_red_or32(&P.ctr->overflow, NK_OVF_PEND);
+    }
+}
+
+/* Increment of a counter of a slot that IS claimed inside this step: which 0 = the ghost count before the
+ * claim, which 1 = aux, the count after the claim (value 1 + aux, C:963).  base = value at step start. These
+ * counters are not touched until all probing is done (nk_apply_op), so base is what every reader sees. */
+NK_HD void nk_event_claimed(const NkRun &P, const NkPart &pd, unsigned slot, int which, int base, int terminal, unsigned t,
+                            unsigned read, int &high_acc)
+{
     if (base >= P.depth - 1)
-    { /* saturated: all tests on this counter are true this step; counts commute */
+    {
         int *ctr = which ? reinterpret_cast<int *>(&pd.tab[slot].aux) : &pd.tab[slot].count;
         nk_red_add32(ctr, P.delta);
         if (terminal)
@@ -389,15 +430,15 @@ NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int which, 
     }
     else if (P.record)
     {
-        unsigned idx = nk_list_append(P, NK_LIST_PEND, &P.ctr->n_pend);
-        if (idx < P.pend_cap)
+        unsigned idx = nk_list_append(P, NK_LIST_SPEC, &P.ctr->n_spec);
+        if (idx < P.spec_cap)
         {
             NkPend r;
             r.slot = slot;
             r.tw = (t << 2) | ((unsigned)which << 1) | (unsigned)terminal;
             r.base = base;
             r.read = read;
-            P.pend[idx] = r;
+            P.spec[idx] = r;
         }
         else
             nk_red_or32(&P.ctr->overflow, NK_OVF_PEND);
@@ -445,7 +486,7 @@ NK_HD unsigned nk_probe_op(const NkRun &P, const NkPart &pd, unsigned part, unsi
     }
     if (e.key == key)
     {
-        nk_event(P, pd, (unsigned)i, 0, e.count, 1, t, read, high_acc);
+        nk_event(P, pd, (unsigned)i, e.count, e.aux, 1, t, read, high_acc);
         return 1;
     }
     if (!nk_is_real(e.key))
@@ -470,7 +511,7 @@ NK_HD unsigned nk_probe_op(const NkRun &P, const NkPart &pd, unsigned part, unsi
         }
         touches++;
         int term = e.key == key;
-        nk_event(P, pd, (unsigned)i, 0, e.count, term, t, read, high_acc);
+        nk_event(P, pd, (unsigned)i, e.count, e.aux, term, t, read, high_acc);
         if (term)
             break;
     }
@@ -520,7 +561,7 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc, int &clai
         unsigned long long owner = P.open[nk_tag_open(f)].key;
         if (owner == o.key)
         {
-            nk_event(P, pd, (unsigned)i, 1, 1, 1, o.t, o.read, high_acc);
+            nk_event_claimed(P, pd, (unsigned)i, 1, 1, 1, o.t, o.read, high_acc);
             return 0;
         }
         landed = false; /* collision at home: walk */
@@ -543,27 +584,61 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc, int &clai
         if (nk_is_real(e.key))
         {
             int term = e.key == o.key;
-            nk_event(P, pd, (unsigned)i, 0, e.count, term, o.t, o.read, high_acc);
+            nk_event(P, pd, (unsigned)i, e.count, e.aux, term, o.t, o.read, high_acc);
             if (term)
                 break;
             continue;
         }
-        if (e.key == 0 || nk_tag_time(e.key) > o.t)
-        { /* empty at time t: the walk ends on a ghost counter (C:1015, C:1043-1044) */
-            nk_event(P, pd, (unsigned)i, 0, e.count, 1, o.t, o.read, high_acc);
+        if (e.key == 0)
+        { /* stays empty for the whole step: the walk ends on a ghost counter (C:1015, C:1043-1044) */
+            nk_event(P, pd, (unsigned)i, e.count, e.aux, 1, o.t, o.read, high_acc);
+            break;
+        }
+        if (nk_tag_time(e.key) > o.t)
+        { /* still empty at time t, claimed later in this step */
+            nk_event_claimed(P, pd, (unsigned)i, 0, e.count, 1, o.t, o.read, high_acc);
             break;
         }
         /* claimed earlier in this step by another key (a walker never meets its own key here:
          * keys are stored at their home slot only, and this walker's home holds a different key) */
-        nk_event(P, pd, (unsigned)i, 1, 1, 0, o.t, o.read, high_acc);
+        nk_event_claimed(P, pd, (unsigned)i, 1, 1, 0, o.t, o.read, high_acc);
     }
     return touches;
 }
 
-/* phase 3: apply a pending increment */
-NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
+/* slow-path records: key = (global slot, counter, t, terminal); value = (x, read, kind) where kind 1 means x is
+ * the counter's FINAL value (base = x - number of events of the segment) and kind 0 means x is its base */
+NK_HD void nk_slow_emit(const NkRun &P, const NkPart &pd, const NkPend &r, int x, int kind)
+{
+    unsigned si = nk_list_append(P, NK_LIST_SLOW, &P.ctr->n_slow);
+    if (si >= P.slow_cap)
+        return; /* cannot happen: slow_cap covers both lists */
+    unsigned t = r.tw >> 2;
+    P.slow_key[si] = ((pd.gbase + r.slot) << (NK_T_BITS + 2)) | ((unsigned long long)((r.tw >> 1) & 1u) << (NK_T_BITS + 1)) |
+                     ((unsigned long long)t << 1) | (r.tw & 1u);
+    P.slow_val[si] = ((unsigned long long)(unsigned)x << 32) | ((unsigned long long)r.read << 1) | (unsigned)kind;
+}
+
+/* ordinary counters: all increments are in.  A counter that ends below depth had only false tests; otherwise its
+ * events are ranked by time.  aux goes back to 0 (every touched unsaturated counter is visited here). */
+NK_HD void nk_classify_op(const NkRun &P, unsigned idx)
 {
     NkPend r = P.pend[idx];
+    if (r.slot == NK_HOLE)
+        return;
+    const NkPart &pd = P.parts[P.reads[r.read].part];
+    NkSlot *s = &pd.tab[r.slot];
+    NkSlot e = nk_load_slot(s);
+    if (e.aux != 0)
+        s->aux = 0;
+    if (e.count >= P.depth)
+        nk_slow_emit(P, pd, r, e.count, 1);
+}
+
+/* counters of slots claimed inside the step: apply the listed increments ... */
+NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
+{
+    NkPend r = P.spec[idx];
     if (r.slot == NK_HOLE)
         return;
     const NkPart &pd = P.parts[P.reads[r.read].part];
@@ -571,25 +646,17 @@ NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
     nk_red_add32(ctr, 1);
 }
 
-/* phase 4: a counter that ends below depth has only false tests; otherwise its events need ranking */
-NK_HD void nk_classify_op(const NkRun &P, unsigned idx)
+/* ... then classify them the same way */
+NK_HD void nk_classify_claimed_op(const NkRun &P, unsigned idx)
 {
-    NkPend r = P.pend[idx];
+    NkPend r = P.spec[idx];
     if (r.slot == NK_HOLE)
         return;
     const NkPart &pd = P.parts[P.reads[r.read].part];
     NkSlot e = nk_load_slot(&pd.tab[r.slot]);
-    int which = (r.tw >> 1) & 1;
-    long long v = which ? 1ll + (long long)e.aux : (long long)e.count;
-    if (v < P.depth)
-        return;
-    unsigned si = nk_list_append(P, NK_LIST_SLOW, &P.ctr->n_slow);
-    if (si >= P.slow_cap)
-        return; /* cannot happen: slow_cap == pend_cap */
-    unsigned t = r.tw >> 2;
-    P.slow_key[si] = ((pd.gbase + r.slot) << (NK_T_BITS + 2)) | ((unsigned long long)which << (NK_T_BITS + 1)) |
-                     ((unsigned long long)t << 1) | (r.tw & 1u);
-    P.slow_val[si] = ((unsigned long long)(unsigned)r.base << 32) | r.read;
+    long long v = (r.tw & 2u) ? 1ll + (long long)e.aux : (long long)e.count;
+    if (v >= P.depth)
+        nk_slow_emit(P, pd, r, r.base, 0);
 }
 
 /* phase 5: rank of event i inside its (slot,counter) segment of the time-sorted list */
@@ -609,13 +676,29 @@ NK_HD void nk_rank_op(const NkRun &P, const unsigned long long *keys, const unsi
         else
             hi = mid;
     }
-    long long after = (long long)(int)(vals[i] >> 32) + (long long)(i - lo + 1);
+    unsigned long long val = vals[i];
+    long long base = (long long)(int)(val >> 32);
+    if (val & 1)
+    { /* x is the final value: base = final - events of this counter in the step */
+        unsigned a = i, b = n; /* first index whose segment is > seg */
+        while (a < b)
+        {
+            unsigned mid = (a + b) >> 1;
+            if ((keys[mid] >> (NK_T_BITS + 1)) <= seg)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        base -= (long long)(a - lo);
+    }
+    long long after = base + (long long)(i - lo + 1);
     if (after >= P.depth)
     {
+        unsigned read = (unsigned)((val & 0xFFFFFFFFull) >> 1);
 #if NK_DEVICE_CODE
-        atomicAdd(&P.high[(unsigned)vals[i]], 1u);
+        atomicAdd(&P.high[read], 1u);
 #else
-        P.high[(unsigned)vals[i]] += 1u;
+        P.high[read] += 1u;
 #endif
     }
 }

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(256) k_open(NkRun P)
         s_touch[i] = s_claims[i] = 0;
     __syncthreads();
     auto pend_hole = [&](unsigned i) { P.pend[i].slot = NK_HOLE; };
+    auto spec_hole = [&](unsigned i) { P.spec[i].slot = NK_HOLE; };
     auto claim_hole = [&](unsigned i) { P.claim[i].slot = NK_HOLE; };
     const unsigned n = min(P.ctr->n_open, P.open_cap);
     for (unsigned base = (blockIdx.x * 8u + warp) * 32u; base < n; base += gridDim.x * 256u)
@@ -215,7 +216,10 @@ __global__ void __launch_bounds__(256) k_open(NkRun P)
         if (P.record)
         {
             if (P.mode == NK_MODE_SCORE)
+            {
                 nk_chunk_rotate(P, NK_LIST_PEND, &P.ctr->n_pend, P.pend_cap);
+                nk_chunk_rotate(P, NK_LIST_SPEC, &P.ctr->n_spec, P.spec_cap);
+            }
             nk_chunk_rotate(P, NK_LIST_CLAIM, &P.ctr->n_claim, P.claim_cap);
         }
         const unsigned i = base + lane;
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(256) k_open(NkRun P)
     if (P.record)
     {
         nk_chunk_close(P, NK_LIST_PEND, pend_hole);
+        nk_chunk_close(P, NK_LIST_SPEC, spec_hole);
         nk_chunk_close(P, NK_LIST_CLAIM, claim_hole);
     }
     __syncthreads();
@@ -256,7 +261,8 @@ __global__ void __launch_bounds__(256) k_apply(const NkRun P, unsigned n)
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         nk_apply_op(P, i);
 }
-__global__ void __launch_bounds__(256) k_classify(NkRun P, unsigned n)
+template <bool CLAIMED>
+__device__ __forceinline__ void nk_classify_body(NkRun &P, unsigned n)
 {
     __shared__ NkWarpCur s_cur[8];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -268,11 +274,18 @@ __global__ void __launch_bounds__(256) k_classify(NkRun P, unsigned n)
         nk_chunk_rotate(P, NK_LIST_SLOW, &P.ctr->n_slow, P.slow_cap);
         const unsigned i = base + lane;
         if (i < n)
-            nk_classify_op(P, i);
+        {
+            if (CLAIMED)
+                nk_classify_claimed_op(P, i);
+            else
+                nk_classify_op(P, i);
+        }
         __syncwarp();
     }
     nk_chunk_close(P, NK_LIST_SLOW, slow_hole);
 }
+__global__ void __launch_bounds__(256) k_classify(NkRun P, unsigned n) { nk_classify_body<false>(P, n); }
+__global__ void __launch_bounds__(256) k_classify_claimed(NkRun P, unsigned n) { nk_classify_body<true>(P, n); }
 __global__ void __launch_bounds__(256) k_rank(const NkRun P, const unsigned long long *keys, const unsigned long long *vals,
                                              unsigned n)
 {
@@ -323,7 +336,7 @@ struct CudaBackend
     {
         std::vector<cudaEvent_t> ev; /* start/stop pairs */
         size_t used = 0;
-    } timers[2];
+    } timers[9];
 
     bool ok(cudaError_t e, const char *what)
     {
@@ -406,6 +419,20 @@ struct CudaBackend
             cudaFree(p);
         }
     }
+    /* page-locked host memory is mapped into the device address space (UVA): the probe kernel can read the
+     * staged sequence bytes over PCIe with coalesced 16-byte loads instead of waiting for a bulk copy */
+    const void *device_view_of_host(const void *p)
+    {
+        if (getenv("NKB200_NO_ZEROCOPY"))
+            return nullptr;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    }
     void zero(void *p, size_t n) { ok(cudaMemsetAsync(p, 0, n, stream), "cudaMemsetAsync"); }
     void h2d(void *d, const void *h, size_t n) { ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream), "H2D copy"); }
     void d2h(void *h, const void *d, size_t n) { ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream), "D2H copy"); }
@@ -414,17 +441,19 @@ struct CudaBackend
 
     /* entries a warp reserves per global atomic: large enough to make the atomics negligible, small enough
      * that the holes of (SMs x 8 x 8) warps stay a small fraction of the list */
-    void chunk_sizes(unsigned *c, unsigned pend_cap, unsigned open_cap, unsigned claim_cap, unsigned slow_cap)
+    void chunk_sizes(unsigned *c, unsigned pend_cap, unsigned open_cap, unsigned claim_cap, unsigned slow_cap,
+                     unsigned spec_cap)
     {
         unsigned warps = (unsigned)sms * 8u * 8u;
         auto pick = [&](unsigned cap, unsigned mx) {
             unsigned v = cap / (4u * warps);
             return v < 32u ? 32u : (v > mx ? mx : v);
         };
-        c[NK_LIST_PEND] = pick(pend_cap, 512);
-        c[NK_LIST_OPEN] = pick(open_cap, 256);
-        c[NK_LIST_CLAIM] = pick(claim_cap, 64);
-        c[NK_LIST_SLOW] = pick(slow_cap, 64);
+        c[NK_LIST_PEND] = pick(pend_cap, 384);
+        c[NK_LIST_OPEN] = pick(open_cap, 192);
+        c[NK_LIST_CLAIM] = pick(claim_cap, 32);
+        c[NK_LIST_SLOW] = pick(slow_cap, 32);
+        c[NK_LIST_SPEC] = pick(spec_cap, 64);
     }
 
     bool prepare_sort(size_t n, std::string &err)
@@ -512,6 +541,10 @@ struct CudaBackend
     void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P), launches++; }
     void apply(const NkRun &P, unsigned n) { k_apply<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }
     void classify(const NkRun &P, unsigned n) { k_classify<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }
+    void classify_claimed(const NkRun &P, unsigned n)
+    {
+        k_classify_claimed<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++;
+    }
     void sort_pairs(unsigned long long *kin, unsigned long long *kout, unsigned long long *vin, unsigned long long *vout,
                     unsigned n)
     {

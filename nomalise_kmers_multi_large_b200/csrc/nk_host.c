@@ -1678,6 +1678,8 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
     out->run_ms = out->probe_ms = 0;
     out->launches = out->probe_launches = out->probe_touches = out->h2d_bytes = out->d2h_bytes = 0;
     out->ops = out->touches = out->slow_events = out->expansions = 0;
+    out->pend_events = out->open_ops = 0;
+    memset(out->class_ms, 0, sizeof out->class_ms);
     for (int d = 0; d < c->n_dev; d++)
     {
         nkd_run_stats rs;
@@ -1689,6 +1691,10 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
         out->probe_touches += rs.probe_touches;
         out->h2d_bytes += rs.h2d_bytes;
         out->d2h_bytes += rs.d2h_bytes;
+        out->pend_events += rs.pend_events;
+        out->open_ops += rs.open_ops;
+        for (int k = 0; k < 8; k++)
+            out->class_ms[k] += rs.class_ms[k];
     }
     if (c->seeded)
         for (int i = 0; i < c->n_local; i++)

@@ -62,18 +62,19 @@ class NkEngine
     bool seeded = false;
 
     /* step buffers */
+    const unsigned char *seq_view = nullptr; /* where the kernels read the step's sequence bytes from */
     unsigned char *d_seq = nullptr;
     NkRead *d_reads = nullptr;
     unsigned *d_high = nullptr, *d_total = nullptr;
     unsigned char *d_invalid = nullptr, *d_accept = nullptr;
     NkOpen *d_open = nullptr;
-    NkPend *d_pend = nullptr;
+    NkPend *d_pend = nullptr, *d_spec = nullptr;
     NkClaim *d_claim = nullptr;
     unsigned long long *d_skey[2] = {nullptr, nullptr}, *d_sval[2] = {nullptr, nullptr};
     unsigned long long *d_keys_out = nullptr;
     NkCounters *d_ctr = nullptr;
     NkPart *d_parts = nullptr;
-    unsigned open_cap = 0, pend_cap = 0, claim_cap = 0;
+    unsigned open_cap = 0, pend_cap = 0, claim_cap = 0, spec_cap = 0, slow_cap = 0;
 
     NkCounters h_ctr{};
     std::vector<NkPart> h_parts;
@@ -113,6 +114,8 @@ class NkEngine
         open_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_OPEN_FRAC", 1.0) + 1024);
         pend_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_PEND_FRAC", 2.0) + 1024);
         claim_cap = open_cap;
+        spec_cap = open_cap;
+        slow_cap = (unsigned)std::min<double>(4e9, (double)pend_cap + (double)spec_cap);
         bool ok = true;
         ok &= dalloc(d_seq, c.max_step_bytes + 64);
         ok &= dalloc(d_reads, c.max_step_reads + 1);
@@ -122,17 +125,18 @@ class NkEngine
         ok &= dalloc(d_accept, c.max_step_reads + 1);
         ok &= dalloc(d_open, open_cap);
         ok &= dalloc(d_pend, pend_cap);
+        ok &= dalloc(d_spec, spec_cap);
         ok &= dalloc(d_claim, claim_cap);
         for (int i = 0; i < 2; i++)
         {
-            ok &= dalloc(d_skey[i], pend_cap);
-            ok &= dalloc(d_sval[i], pend_cap);
+            ok &= dalloc(d_skey[i], slow_cap);
+            ok &= dalloc(d_sval[i], slow_cap);
         }
         ok &= dalloc(d_ctr, 1);
         ok &= dalloc(d_parts, NK_MAX_PARTITIONS);
         if (!ok)
             return fail(NK_ENOMEM, "nkd_create: cannot allocate step scratch");
-        if (!be.prepare_sort(pend_cap, err))
+        if (!be.prepare_sort(slow_cap, err))
             return NK_ENOMEM;
         h_parts.resize(NK_MAX_PARTITIONS);
         T.assign(NK_MAX_PARTITIONS, 0);
@@ -153,6 +157,7 @@ class NkEngine
         be.release(d_accept);
         be.release(d_open);
         be.release(d_pend);
+        be.release(d_spec);
         be.release(d_claim);
         for (int i = 0; i < 2; i++)
         {
@@ -218,7 +223,7 @@ class NkEngine
     NkRun make_run(int mode, int delta, int record)
     {
         NkRun P{};
-        P.seq = d_seq;
+        P.seq = seq_view ? seq_view : d_seq;
         P.reads = d_reads;
         P.n_reads = (unsigned)n_reads;
         P.parts = d_parts;
@@ -235,14 +240,16 @@ class NkEngine
         P.open_cap = open_cap;
         P.pend = d_pend;
         P.pend_cap = pend_cap;
+        P.spec = d_spec;
+        P.spec_cap = spec_cap;
         P.claim = d_claim;
         P.claim_cap = claim_cap;
         P.slow_key = d_skey[0];
         P.slow_val = d_sval[0];
-        P.slow_cap = pend_cap;
+        P.slow_cap = slow_cap;
         P.ctr = d_ctr;
         P.keys_out = d_keys_out;
-        be.chunk_sizes(P.chunk, pend_cap, open_cap, claim_cap, pend_cap);
+        be.chunk_sizes(P.chunk, pend_cap, open_cap, claim_cap, slow_cap, spec_cap);
         return P;
     }
 
@@ -330,7 +337,9 @@ class NkEngine
                 be.sync();
                 fprintf(stderr, "[nkd] probe done: n_open %u n_pend %u ovf %x\n", h_ctr.n_open, h_ctr.n_pend, h_ctr.overflow);
             }
+            be.begin_timer(2);
             be.open_ops(F);
+            be.end_timer(2);
             if (debug)
             {
                 be.d2h(&h_ctr, d_ctr, 32);
@@ -340,8 +349,8 @@ class NkEngine
             fetch_counters();
             if (debug)
             {
-                fprintf(stderr, "[nkd] mode %d fwd: open %u pend %u claim %u ovf %x |", mode, h_ctr.n_open, h_ctr.n_pend,
-                        h_ctr.n_claim, h_ctr.overflow);
+                fprintf(stderr, "[nkd] mode %d fwd: open %u pend %u spec %u claim %u ovf %x |", mode, h_ctr.n_open,
+                        h_ctr.n_pend, h_ctr.n_spec, h_ctr.n_claim, h_ctr.overflow);
                 for (size_t p = 0; p < np && p < 4; p++)
                     fprintf(stderr, " p%zu [%u,%u) of %u used %llu/%llu cap %llu claims %u real %llu", p, lo[p], hi[p], T[p],
                             (unsigned long long)tabs[p]->used, (unsigned long long)tabs[p]->thr,
@@ -405,32 +414,50 @@ class NkEngine
             if (cut)
             { /* abandon this run: replay it with -1 (the decisions are stable), forget the claim attempts */
                 NkRun U = make_run(mode, -1, 0);
+                be.begin_timer(8);
                 be.probe(U);
                 be.open_ops(U);
                 be.untag(U, std::min(h_ctr.n_open, open_cap));
+                be.end_timer(8);
                 hi = nhi;
                 continue;
             }
             /* commit */
             if (mode == NK_MODE_SCORE)
             {
-                unsigned np_ = std::min(h_ctr.n_pend, pend_cap);
-                if (np_)
+                unsigned np_ = std::min(h_ctr.n_pend, pend_cap), ns_ = std::min(h_ctr.n_spec, spec_cap);
+                if (ns_)
                 {
-                    be.apply(F, np_);
-                    be.classify(F, np_);
+                    be.begin_timer(3);
+                    be.apply(F, ns_);
+                    be.end_timer(3);
+                }
+                if (np_ || ns_)
+                {
+                    be.begin_timer(4);
+                    if (np_)
+                        be.classify(F, np_);
+                    if (ns_)
+                        be.classify_claimed(F, ns_);
+                    be.end_timer(4);
                     be.d2h(&h_ctr.n_slow, &d_ctr->n_slow, sizeof(unsigned));
                     be.sync();
-                    h_ctr.n_slow = std::min(h_ctr.n_slow, pend_cap);
+                    h_ctr.n_slow = std::min(h_ctr.n_slow, slow_cap);
                     if (h_ctr.n_slow)
                     {
+                        be.begin_timer(5);
                         be.sort_pairs(d_skey[0], d_skey[1], d_sval[0], d_sval[1], h_ctr.n_slow);
                         be.rank(F, d_skey[1], d_sval[1], h_ctr.n_slow);
+                        be.end_timer(5);
                     }
                 }
             }
             if (h_ctr.n_claim)
+            {
+                be.begin_timer(6);
                 be.commit(F, std::min(h_ctr.n_claim, claim_cap));
+                be.end_timer(6);
+            }
             for (size_t p = 0; p < np; p++)
             {
                 NkTable &t = *tabs[p];
@@ -446,6 +473,9 @@ class NkEngine
                 tabs[0]->st.slow_events += h_ctr.n_slow; /* device-wide figure, kept on partition 0 */
                 rs.probe_touches += h_ctr.probe_touches;
                 rs.probe_launches++;
+                rs.pend_events += h_ctr.n_pend;
+                rs.open_ops += h_ctr.n_open;
+                rs.slow_events += h_ctr.n_slow;
             }
         }
         return NK_OK;
@@ -472,6 +502,8 @@ class NkEngine
         int stride = is_paired ? 2 : 1;
         rec_part.resize(nr / stride + 1);
         size_t at = 0;
+        const unsigned char *view = (const unsigned char *)be.device_view_of_host(seq);
+        seq_view = view;
         for (int s = 0; s < n_segs; s++)
         {
             const nkd_segment &g = segs[s];
@@ -501,7 +533,8 @@ class NkEngine
             {
                 /* the last 16-byte chunk of a read may extend past seq_hi: the buffers are padded */
                 size_t hi = std::min<size_t>((g.seq_hi + 15) & ~(size_t)15, cfg.max_step_bytes);
-                be.h2d(d_seq + g.seq_lo, seq + g.seq_lo, hi - g.seq_lo);
+                if (!view)
+                    be.h2d(d_seq + g.seq_lo, seq + g.seq_lo, hi - g.seq_lo);
                 be.h2d(d_reads + at, g.reads, g.n_reads * sizeof(nkd_read));
                 h2d_bytes += (hi - g.seq_lo) + g.n_reads * sizeof(nkd_read);
             }
@@ -582,7 +615,8 @@ class NkEngine
         if (!staged)
             return fail(NK_EINVAL, "nkd_run without nkd_stage");
         be.begin_timer(0);
-        be.reset_timer(1);
+        for (int t = 1; t <= 8; t++)
+            be.reset_timer(t);
         be.zero(d_high, (n_reads + 1) * sizeof(unsigned));
         be.zero(d_total, (n_reads + 1) * sizeof(unsigned));
         be.zero(d_invalid, n_reads + 1);
@@ -593,7 +627,9 @@ class NkEngine
         if (rc)
             return rc;
         be.zero(d_ctr, sizeof(NkCounters));
+        be.begin_timer(7);
         be.decide(make_run(NK_MODE_SCORE, 0, 0), (unsigned)n_records, paired, cfg.coverage, d_accept);
+        be.end_timer(7);
         be.end_timer(0);
         ran = true;
         return NK_OK;
@@ -613,6 +649,9 @@ class NkEngine
         last_probe_ms = be.timer_ms(1);
         rs.run_ms += last_total_ms;
         rs.probe_ms += last_probe_ms;
+        rs.class_ms[0] += last_probe_ms;
+        for (int t = 2; t <= 8; t++)
+            rs.class_ms[t - 1] += be.timer_ms(t);
         int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         if (first_invalid)
             *first_invalid = (inv >= 0 && (size_t)inv < nrec) ? inv : -1;

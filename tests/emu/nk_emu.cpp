@@ -29,6 +29,7 @@ struct EmuBackend
     }
     void shutdown() {}
     void enter() {}
+    const void *device_view_of_host(const void *) { return nullptr; }
     bool failed(std::string &) { return false; }
     void *alloc(size_t n) { return malloc(n ? n : 1); }
     void release(void *p) { free(p); }
@@ -38,7 +39,7 @@ struct EmuBackend
     void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void sync() {}
     bool prepare_sort(size_t, std::string &) { return true; }
-    void chunk_sizes(unsigned *c, unsigned, unsigned, unsigned, unsigned) { c[0] = c[1] = c[2] = c[3] = 0; }
+    void chunk_sizes(unsigned *c, unsigned, unsigned, unsigned, unsigned, unsigned) { c[0] = c[1] = c[2] = c[3] = c[4] = 0; }
     void begin_timer(int) {}
     void end_timer(int) {}
     void reset_timer(int) {}
@@ -121,6 +122,11 @@ struct EmuBackend
     {
         for (unsigned i : order(n))
             nk_classify_op(P, i);
+    }
+    void classify_claimed(const NkRun &P, unsigned n)
+    {
+        for (unsigned i : order(n))
+            nk_classify_claimed_op(P, i);
     }
     void sort_pairs(unsigned long long *kin, unsigned long long *kout, unsigned long long *vin, unsigned long long *vout,
                     unsigned n)
