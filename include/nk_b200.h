@@ -148,6 +148,10 @@ int nkd_part_stats_get(nkd_engine *e, int part, nkd_part_stats *out);
 /* print_kmer_table's data source (C:354-385): slot-ordered copy of partition's table */
 int nkd_export(nkd_engine *e, int part, uint64_t *keys, int32_t *counts, uint64_t capacity);
 
+/* test hook: per-read (high, total) of the step just run (sequence_to_hash's two outputs, C:1459-1499);
+ * valid between nkd_run and the next nkd_stage */
+int nkd_read_scores(nkd_engine *e, uint32_t *high, uint32_t *total, size_t n_reads);
+
 /* test hooks: the codec alone (encode_kmer_plain / get_canonical_kmer, C:1118-1126, C:1175-1180).
  * keys_out receives one key per window of every read (0 = ignored window), in op order. */
 int nkd_extract_keys(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,

@@ -93,7 +93,7 @@ class Totals(C.Structure):
 ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step", "nkd_seed_finish", "nkd_seed_stats",
                   "nkd_seed_export", "nkd_stage", "nkd_run", "nkd_fetch", "nkd_last_run_ms", "nkd_part_stats_get",
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
-                  "nkd_device_count", "nkd_run_stats_get"]
+                  "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores"]
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
                     "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main"]
@@ -118,6 +118,7 @@ def _declare_engine(lib):
     lib.nkd_export.argtypes = [vp, C.c_int, vp, vp, C.c_uint64]
     lib.nkd_extract_keys.argtypes = [vp, u8p, sz, vp, sz, vp, sz, u8p]
     lib.nkd_run_stats_get.argtypes = [vp, C.POINTER(RunStats)]
+    lib.nkd_read_scores.argtypes = [vp, vp, vp, sz]
     lib.nkd_device_count.restype = C.c_int
     return lib
 
@@ -257,6 +258,11 @@ class Engine:
         self.stage(buf, descs, paired)
         self.run()
         return self.fetch()
+
+    def read_scores(self, n_reads):
+        hi, tot = np.empty(n_reads, np.uint32), np.empty(n_reads, np.uint32)
+        self._check(self.lib.nkd_read_scores(self.h, hi.ctypes.data, tot.ctypes.data, n_reads))
+        return hi, tot
 
     def last_run_ms(self):
         a, b = C.c_float(), C.c_float()

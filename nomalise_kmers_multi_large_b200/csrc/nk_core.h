@@ -99,6 +99,7 @@ struct NkClaim
 #define NK_OVF_PEND 2u
 #define NK_OVF_CLAIM 4u
 #define NK_OVF_WALK 8u
+#define NK_OVF_SLOW 16u
 
 struct NkCounters
 {
@@ -305,7 +306,11 @@ NK_HD NkSlot nk_load_slot(const NkSlot *p)
      * untouched during the launch or only need ">= depth-1", and an unseen claim TAG reads as "empty at step
      * start", which is what a TAG means.  asm volatile keeps the compiler from merging re-reads in the walk loop. */
     uint4 v;
+#ifdef NK_LOAD_CG
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
     NkSlot s;
     s.key = ((unsigned long long)v.y << 32) | v.x;
     s.count = (int)v.z;
@@ -608,31 +613,30 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc, int &clai
 
 /* slow-path records: key = (global slot, counter, t, terminal); value = (x, read, kind) where kind 1 means x is
  * the counter's FINAL value (base = x - number of events of the segment) and kind 0 means x is its base */
-NK_HD void nk_slow_emit(const NkRun &P, const NkPart &pd, const NkPend &r, int x, int kind)
+NK_HD void nk_slow_write(const NkRun &P, unsigned si, unsigned long long gslot, const NkPend &r, int x, int kind)
 {
-    unsigned si = nk_list_append(P, NK_LIST_SLOW, &P.ctr->n_slow);
-    if (si >= P.slow_cap)
-        return; /* cannot happen: slow_cap covers both lists */
     unsigned t = r.tw >> 2;
-    P.slow_key[si] = ((pd.gbase + r.slot) << (NK_T_BITS + 2)) | ((unsigned long long)((r.tw >> 1) & 1u) << (NK_T_BITS + 1)) |
+    P.slow_key[si] = (gslot << (NK_T_BITS + 2)) | ((unsigned long long)((r.tw >> 1) & 1u) << (NK_T_BITS + 1)) |
                      ((unsigned long long)t << 1) | (r.tw & 1u);
     P.slow_val[si] = ((unsigned long long)(unsigned)x << 32) | ((unsigned long long)r.read << 1) | (unsigned)kind;
 }
 
 /* ordinary counters: all increments are in.  A counter that ends below depth had only false tests; otherwise its
- * events are ranked by time.  aux goes back to 0 (every touched unsaturated counter is visited here). */
-NK_HD void nk_classify_op(const NkRun &P, unsigned idx)
+ * events are ranked by time (returns true: the caller appends a slow record).  aux goes back to 0 (every touched
+ * unsaturated counter is visited here). */
+NK_HD bool nk_classify_op(const NkRun &P, unsigned idx, NkPend &r, unsigned long long &gslot, int &x)
 {
-    NkPend r = P.pend[idx];
+    r = P.pend[idx];
     if (r.slot == NK_HOLE)
-        return;
+        return false;
     const NkPart &pd = P.parts[P.reads[r.read].part];
     NkSlot *s = &pd.tab[r.slot];
     NkSlot e = nk_load_slot(s);
     if (e.aux != 0)
         s->aux = 0;
-    if (e.count >= P.depth)
-        nk_slow_emit(P, pd, r, e.count, 1);
+    gslot = pd.gbase + r.slot;
+    x = e.count;
+    return e.count >= P.depth;
 }
 
 /* counters of slots claimed inside the step: apply the listed increments ... */
@@ -647,16 +651,17 @@ NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
 }
 
 /* ... then classify them the same way */
-NK_HD void nk_classify_claimed_op(const NkRun &P, unsigned idx)
+NK_HD bool nk_classify_claimed_op(const NkRun &P, unsigned idx, NkPend &r, unsigned long long &gslot, int &x)
 {
-    NkPend r = P.spec[idx];
+    r = P.spec[idx];
     if (r.slot == NK_HOLE)
-        return;
+        return false;
     const NkPart &pd = P.parts[P.reads[r.read].part];
     NkSlot e = nk_load_slot(&pd.tab[r.slot]);
     long long v = (r.tw & 2u) ? 1ll + (long long)e.aux : (long long)e.count;
-    if (v >= P.depth)
-        nk_slow_emit(P, pd, r, r.base, 0);
+    gslot = pd.gbase + r.slot;
+    x = r.base;
+    return v >= P.depth;
 }
 
 /* phase 5: rank of event i inside its (slot,counter) segment of the time-sorted list */

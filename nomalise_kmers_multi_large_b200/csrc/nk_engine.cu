@@ -261,28 +261,51 @@ __global__ void __launch_bounds__(256) k_apply(const NkRun P, unsigned n)
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         nk_apply_op(P, i);
 }
+/* Classification appends only at converged points, so the warp aggregates with a ballot: one global atomic
+ * per chunk of NK_SLOW_CHUNK entries, no shared cursor, and warps with nothing to emit reserve nothing. */
+#define NK_SLOW_CHUNK 256u
 template <bool CLAIMED>
 __device__ __forceinline__ void nk_classify_body(NkRun &P, unsigned n)
 {
-    __shared__ NkWarpCur s_cur[8];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    P.wcur = &s_cur[warp];
-    nk_cur_init(P.wcur, lane);
-    auto slow_hole = [&](unsigned i) { P.slow_key[i] = ~0ull; };
+    unsigned cbase = 0, cused = 0, ccap = 0; /* warp-uniform */
     for (unsigned base = (blockIdx.x * 8u + warp) * 32u; base < n; base += gridDim.x * 256u)
     {
-        nk_chunk_rotate(P, NK_LIST_SLOW, &P.ctr->n_slow, P.slow_cap);
         const unsigned i = base + lane;
+        NkPend r;
+        unsigned long long gslot = 0;
+        int x = 0;
+        bool emit = false;
         if (i < n)
+            emit = CLAIMED ? nk_classify_claimed_op(P, i, r, gslot, x) : nk_classify_op(P, i, r, gslot, x);
+        const unsigned votes = __ballot_sync(0xFFFFFFFFu, emit);
+        const unsigned cnt = __popc(votes);
+        if (cnt == 0)
+            continue;
+        if (cused + cnt > ccap)
         {
-            if (CLAIMED)
-                nk_classify_claimed_op(P, i);
-            else
-                nk_classify_op(P, i);
+            for (unsigned h = cused + lane; h < ccap; h += 32)
+                P.slow_key[cbase + h] = ~0ull; /* tail of the old chunk: holes */
+            unsigned b = 0;
+            if (lane == 0)
+                b = atomicAdd(&P.ctr->n_slow, NK_SLOW_CHUNK);
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            cbase = b;
+            cused = 0;
+            ccap = b >= P.slow_cap ? 0u : (P.slow_cap - b < NK_SLOW_CHUNK ? P.slow_cap - b : NK_SLOW_CHUNK);
+            if (ccap < cnt && lane == 0)
+                atomicOr(&P.ctr->overflow, NK_OVF_SLOW);
         }
-        __syncwarp();
+        if (emit)
+        {
+            unsigned my = cused + __popc(votes & ((1u << lane) - 1u));
+            if (my < ccap)
+                nk_slow_write(P, cbase + my, gslot, r, x, CLAIMED ? 0 : 1);
+        }
+        cused += cnt;
     }
-    nk_chunk_close(P, NK_LIST_SLOW, slow_hole);
+    for (unsigned h = (cused < ccap ? cused : ccap) + lane; h < ccap; h += 32)
+        P.slow_key[cbase + h] = ~0ull;
 }
 __global__ void __launch_bounds__(256) k_classify(NkRun P, unsigned n) { nk_classify_body<false>(P, n); }
 __global__ void __launch_bounds__(256) k_classify_claimed(NkRun P, unsigned n) { nk_classify_body<true>(P, n); }

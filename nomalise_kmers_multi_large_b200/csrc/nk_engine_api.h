@@ -127,6 +127,16 @@ int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_
         return h->e.fail(NK_EINVAL, "no such partition");
     return nkd_done(h, h->e.export_table(h->e.parts[part], keys, counts, capacity));
 }
+int nkd_read_scores(nkd_engine *h, uint32_t *high, uint32_t *total, size_t n_reads)
+{
+    h->e.be.enter();
+    if (n_reads != h->e.n_reads)
+        return h->e.fail(NK_EINVAL, "nkd_read_scores: read count differs from the staged step");
+    h->e.be.d2h(high, h->e.d_high, n_reads * sizeof(uint32_t));
+    h->e.be.d2h(total, h->e.d_total, n_reads * sizeof(uint32_t));
+    h->e.be.sync();
+    return nkd_done(h, NK_OK);
+}
 int nkd_extract_keys(nkd_engine *h, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
                      uint64_t *keys_out, size_t n_ops, uint8_t *invalid_out)
 {

@@ -115,7 +115,8 @@ class NkEngine
         pend_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_PEND_FRAC", 2.0) + 1024);
         claim_cap = open_cap;
         spec_cap = open_cap;
-        slow_cap = (unsigned)std::min<double>(4e9, (double)pend_cap + (double)spec_cap);
+        /* every listed event can turn into one slow record; chunked reservation wastes at most a chunk per warp */
+        slow_cap = (unsigned)std::min<double>(4e9, 1.25 * ((double)pend_cap + (double)spec_cap) + (1 << 20));
         bool ok = true;
         ok &= dalloc(d_seq, c.max_step_bytes + 64);
         ok &= dalloc(d_reads, c.max_step_reads + 1);
@@ -440,9 +441,10 @@ class NkEngine
                     if (ns_)
                         be.classify_claimed(F, ns_);
                     be.end_timer(4);
-                    be.d2h(&h_ctr.n_slow, &d_ctr->n_slow, sizeof(unsigned));
+                    be.d2h(&h_ctr, d_ctr, 32);
                     be.sync();
-                    h_ctr.n_slow = std::min(h_ctr.n_slow, slow_cap);
+                    if ((h_ctr.overflow & NK_OVF_SLOW) || h_ctr.n_slow > slow_cap)
+                        return fail(NK_EINTERNAL, "slow-path list overflow (scratch sizing bug)");
                     if (h_ctr.n_slow)
                     {
                         be.begin_timer(5);

@@ -121,12 +121,32 @@ struct EmuBackend
     void classify(const NkRun &P, unsigned n)
     {
         for (unsigned i : order(n))
-            nk_classify_op(P, i);
+        {
+            NkPend r;
+            unsigned long long g;
+            int x;
+            if (nk_classify_op(P, i, r, g, x))
+                emit(P, g, r, x, 1);
+        }
     }
     void classify_claimed(const NkRun &P, unsigned n)
     {
         for (unsigned i : order(n))
-            nk_classify_claimed_op(P, i);
+        {
+            NkPend r;
+            unsigned long long g;
+            int x;
+            if (nk_classify_claimed_op(P, i, r, g, x))
+                emit(P, g, r, x, 0);
+        }
+    }
+    void emit(const NkRun &P, unsigned long long g, const NkPend &r, int x, int kind)
+    {
+        unsigned si = P.ctr->n_slow++;
+        if (si < P.slow_cap)
+            nk_slow_write(P, si, g, r, x, kind);
+        else
+            P.ctr->overflow |= NK_OVF_SLOW;
     }
     void sort_pairs(unsigned long long *kin, unsigned long long *kout, unsigned long long *vin, unsigned long long *vout,
                     unsigned n)

@@ -30,6 +30,14 @@ def test_engine_matches_oracle(cuda_lib, case, seed):
     assert info["ops"] > 0
 
 
+def test_engine_is_deterministic_under_tight_scratch(cuda_lib):
+    """Scratch lists sized to the bare minimum, many repeats: any lost or duplicated list entry (a race in the
+    chunked appends) shows up as a differing score."""
+    for rep in range(12):
+        ec.run_case(cuda_lib, seed=1, k=15, canonical=False, depth=3, cap0=4099, paired=True, n_parts=2, steps=2,
+                    records_per_step=60)
+
+
 def test_engine_scratch_overflow_is_exact(cuda_lib, monkeypatch):
     monkeypatch.setenv("NKB200_OPEN_FRAC", "0.02")
     monkeypatch.setenv("NKB200_PEND_FRAC", "0.03")
