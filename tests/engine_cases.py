@@ -84,14 +84,14 @@ def run_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_par
             buf, descs, _ = capi.pack_reads(seqs, parts, k)
             acc, inv = eng.step(buf, descs, paired)
             assert inv == -1
-            hi, tot = eng.read_scores(len(seqs))
+            got_hi, got_tot = eng.read_scores(len(seqs))
             # sequence_to_hash's (high, total) of every read, in the reference's order (C:1459-1499, C:1559-1563)
             want_scores = []
             for p in range(n_parts):
                 for rec in per_part[p]:
                     for mate in (rec if paired else (rec,)):
                         want_scores.append(otabs[p].score(mate, k, canonical, depth))
-            got_scores = list(zip(hi.tolist(), tot.tolist()))
+            got_scores = list(zip(got_hi.tolist(), got_tot.tolist()))
             bad = [i for i in range(len(seqs)) if got_scores[i] != want_scores[i]]
             assert not bad, f"(high,total) differ at step {step}: reads {bad[:6]} got {[got_scores[i] for i in bad[:6]]} want {[want_scores[i] for i in bad[:6]]}"
             stride = 2 if paired else 1
