@@ -212,6 +212,8 @@ def run_ours(args):
     import torch
     from nomalise_kmers_multi_large_b200 import Pipeline, capi
     rank, world, local, dist = dist_setup(args.gpus)
+    if world > 1 and "NKB200_THREADS" not in os.environ:   # ranks share the box's host cores
+        os.environ["NKB200_THREADS"] = str(max(2, (os.cpu_count() or 2) // world))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
     capi.load_library()
     if rank == 0:

@@ -118,6 +118,11 @@ typedef struct
     const nkd_read *reads;
     size_t n_reads;
     size_t seq_lo, seq_hi;
+    /* optional fast path for callers that build the segment themselves (the host pipeline): when trusted is
+     * non-zero every read of the segment belongs to partition `part`, satisfies the nkd_read rules, and the
+     * partition's operation count in this step is `ops`; the per-read validation pass is skipped */
+    int trusted;
+    uint32_t part, ops;
 } nkd_segment;
 int nkd_stage_segments(nkd_engine *e, const uint8_t *seq_base, const nkd_segment *segs, int n_segs, int paired);
 /* page-locked host memory for the staging buffers (cudaMallocHost / cudaFreeHost) */

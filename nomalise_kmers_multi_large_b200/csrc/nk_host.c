@@ -1348,6 +1348,9 @@ static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_inv
         sb->segs[nseg].n_reads = ps->n_reads;
         sb->segs[nseg].seq_lo = ps->seq_lo;
         sb->segs[nseg].seq_hi = ps->seq_hi;
+        sb->segs[nseg].trusted = 1; /* built by nk_index_task under the nkd_read rules */
+        sb->segs[nseg].part = (uint32_t)i;
+        sb->segs[nseg].ops = ps->ops;
         nseg++;
         sb->n_records += ps->n_records;
     }

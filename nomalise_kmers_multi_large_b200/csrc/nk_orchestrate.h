@@ -488,7 +488,7 @@ class NkEngine
     int stage(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr, int is_paired, int n_tabs,
               bool ignore_part)
     {
-        nkd_segment s{reads, nr, 0, seq_bytes};
+        nkd_segment s{reads, nr, 0, seq_bytes, 0, 0, 0};
         return stage_segments(seq, &s, 1, is_paired, n_tabs, ignore_part);
     }
 
@@ -513,6 +513,16 @@ class NkEngine
                 return fail(NK_EINVAL, "step segment exceeds the byte limit given to nkd_create");
             if (is_paired && (g.n_reads & 1))
                 return fail(NK_EINVAL, "paired step with an odd number of reads");
+            if (g.trusted && !ignore_part)
+            {
+                if ((int)g.part >= n_tabs)
+                    return fail(NK_EINVAL, "segment names a partition that is not resident");
+                if (g.ops > T[g.part])
+                    T[g.part] = g.ops;
+                for (size_t i = (at + stride - 1) / stride; i < (at + g.n_reads + stride - 1) / stride; i++)
+                    rec_part[i] = (unsigned short)g.part;
+            }
+            else
             for (size_t i = 0; i < g.n_reads; i++)
             {
                 const nkd_read &rd = g.reads[i];
