@@ -78,7 +78,7 @@ typedef struct nkd_engine nkd_engine;
 typedef struct
 {
     int device;          /* CUDA ordinal */
-    int k;               /* 5..31 (C:724); 32 is accepted as an extension with no reference result */
+    int k;               /* 5..31 (C:724) */
     int canonical;       /* C:1472-1476 */
     int depth_per_part;  /* cfg.depth_per_cpu, C:674 */
     float coverage;      /* cfg.coverage as float32, C:216 */

@@ -130,7 +130,7 @@ static uint64_t nk_capacity_unclamped(int memory_gb, int partitions)
 uint64_t nk_initial_capacity(int memory_gb, int partitions, int k)
 {
     uint64_t cap = nk_capacity_unclamped(memory_gb, partitions > 0 ? partitions : 1);
-    uint64_t lim = k >= 32 ? (uint64_t)1 << 63 : nk_pow4_wrapping(k); /* k = 32 extension: no clamp */
+    uint64_t lim = nk_pow4_wrapping(k);
     return lim < cap ? lim : cap;
 }
 
@@ -686,10 +686,11 @@ void nk_destroy(nk_ctx *c)
 int nk_create(const nk_config *cfg, nk_ctx **out)
 {
     *out = NULL;
-    /* the limits parse_arguments enforces, C:704-743 (k = 32 is an extension the reference rejects) */
+    /* the limits parse_arguments enforces, C:704-743 (k = 32 is rejected as in the reference: a 64-bit key
+     * would also collide with the claim tag in bit 63 of the key field) */
     if (cfg->partitions <= 0 || cfg->partitions > NK_MAX_PARTITIONS)
         return nk_fail(NULL, NK_EINVAL, "Error: CPU count (%d) must be a positive integer and up to %d", cfg->partitions, NK_MAX_PARTITIONS);
-    if (cfg->k < 5 || cfg->k > 32)
+    if (cfg->k < 5 || cfg->k > 31)
         return nk_fail(NULL, NK_EINVAL, "Error: Only kmer sizes (%d) of 5 to 31 are supported", cfg->k);
     if (cfg->coverage > 1 || cfg->coverage < 0.001)
         return nk_fail(NULL, NK_EINVAL, "Error: Coverage (%3.f) is the proportion of the sequence covered by high kmers and must be between 0 and 1", cfg->coverage);
@@ -750,9 +751,14 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
     if (!sp)
     {
         const char *e = getenv("NKB200_STEP_PAIRS");
-        sp = e && atoi(e) > 0 ? (uint32_t)atoi(e) : 32768u;
-        while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > (96ull << 20))
-            sp /= 2;
+        if (e && atoi(e) > 0)
+            sp = (uint32_t)atoi(e);
+        else
+        {
+            sp = 32768u;
+            while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > (96ull << 20))
+                sp /= 2;
+        }
     }
     if (sp < 16)
         sp = 16;
@@ -1510,8 +1516,12 @@ static void *nk_device_pipeline(void *a)
     int threads = c->threads / c->n_dev;
     if (threads < 2)
         threads = 2;
-    pp->t_write = threads / 3 > 0 ? threads / 3 : 1;
-    pp->t_index = threads - pp->t_write;
+    /* one indexing task per partition, one writing task per partition and mate: give the indexer a thread
+     * per partition when there are enough cores and the writer the rest */
+    pp->t_index = dv->n_parts < threads - 1 ? dv->n_parts : (threads * 2 + 2) / 3;
+    if (pp->t_index >= threads)
+        pp->t_index = threads - 1;
+    pp->t_write = threads - pp->t_index;
     dv->rc = NK_OK;
     pthread_mutex_init(&pp->mu, NULL);
     pthread_cond_init(&pp->cv, NULL);
@@ -1961,8 +1971,7 @@ static int nk_parse(nk_cli *a, int argc, char **argv, int *gpus)
         fprintf(stderr, "Error: CPU count (%d) must be a positive integer and up to %d\n", c->partitions, NK_MAX_PARTITIONS);
         return 0;
     }
-    int kmax = getenv("NKB200_ALLOW_K32") ? 32 : 31;
-    if (c->k < 5 || c->k > kmax)
+    if (c->k < 5 || c->k > 31)
     {
         fprintf(stderr, "Error: Only kmer sizes (%d) of 5 to 31 are supported\n", c->k);
         return 0;

@@ -100,7 +100,7 @@ class NkEngine
     int create(const nkd_config &c)
     {
         cfg = c;
-        if (c.k < 5 || c.k > 32 || c.n_parts < 1 || c.n_parts > NK_MAX_PARTITIONS || c.depth_per_part < 2 ||
+        if (c.k < 5 || c.k > 31 || c.n_parts < 1 || c.n_parts > NK_MAX_PARTITIONS || c.depth_per_part < 2 ||
             c.capacity0 < 1 || c.capacity0 >= 0xFFFFFFFFull)
             return fail(NK_EINVAL, "nkd_create: bad configuration");
         if (c.max_step_ops >= (1ull << NK_T_BITS) || c.max_step_reads >= (1ull << 31))

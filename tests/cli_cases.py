@@ -103,4 +103,6 @@ def standard_cases(tmp: Path, n_pairs: int):
         ("ragged_lengths", ["-f", fv, "-r", rv, "-k", 25, "-p", 2, "-d", 8, "-m", 1, "-g", 1.0]),
         ("tiny_k5", ["-f", f2, "-r", r2, "-k", 5, "-p", 1, "-d", 400, "-m", 1]),
         ("one_partition_default_depth", ["-f", f2, "-r", r2, "-k", 20, "-m", 1]),
+        ("p64_canonical_config3_shape", ["-f", f, "-r", r, "-k", 25, "-c", "-p", 64, "-d", 256, "-m", 1]),   # configs[2] flags
+        ("depth_coverage_sweep_point", ["-f", f2, "-r", r2, "-k", 15, "-p", 4, "-d", 400, "-g", 0.96, "-m", 1, "-P"]),
     ]

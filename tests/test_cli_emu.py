@@ -22,7 +22,7 @@ def cases(tmp_path_factory):
 
 NAMES = ["canonical_p8", "stranded_k31_fa_growth", "dump_p4_k15", "equal_sizes_F6", "single_end",
          "single_end_fq2fa_empty", "fasta_in_out_mixed", "multi_file", "ragged_lengths", "tiny_k5",
-         "one_partition_default_depth"]
+         "one_partition_default_depth", "p64_canonical_config3_shape", "depth_coverage_sweep_point"]
 
 
 @pytest.mark.parametrize("name", NAMES)
