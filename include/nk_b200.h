@@ -189,7 +189,7 @@ typedef struct
 
 typedef struct nk_ctx nk_ctx;
 
-/* parse_arguments' derived values + init_hash_table + output files opened "w" (C:674-684, C:890, C:2286-2302) */
+/* parse_arguments' derived values + init_hash_table (C:674-684, C:890) */
 int nk_create(const nk_config *cfg, nk_ctx **out);
 void nk_destroy(nk_ctx *c);
 const char *nk_last_error(const nk_ctx *c);
@@ -201,7 +201,7 @@ uint64_t nk_initial_capacity(int memory_gb, int partitions, int k);
 
 /* seed_kmer_hash (C:1322-1373) on an in-memory file image */
 int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed);
-/* the per-thread copy_hash_table loop + "_seeds" dump (C:2251-2279) */
+/* the per-thread copy_hash_table loop + "_seeds" dump + output files opened "w" (C:2251-2302) */
 int nk_seed_finish(nk_ctx *c);
 
 /* multithreaded_process_files_paired (C:1772-1920) / _single (C:2113-2217) on in-memory file images:

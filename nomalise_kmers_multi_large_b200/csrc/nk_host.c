@@ -835,7 +835,15 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         return NK_ENOMEM;
     }
     memset(c->seed_seq, 0, c->seed_cap_bytes + 64);
-    /* every partition's outputs are opened "w" up front and appended to across input files, C:2286-2302 */
+    *out = c;
+    return NK_OK;
+}
+
+/* every partition's outputs are opened "w" once, after seeding (C:2286-2302 follows C:2244-2250), and appended to
+ * across input files */
+static int nk_open_outputs(nk_ctx *c)
+{
+    const nk_config *cfg = &c->cfg;
     for (int i = 0; i < c->n_local; i++)
     {
         nk_part *p = &c->part[i];
@@ -843,10 +851,9 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         p->out_f = fopen(n, "w");
         if (!p->out_f)
         {
-            nk_fail(NULL, NK_EIO, "Error opening file to write: %s", n);
+            int rc = nk_fail(c, NK_EIO, "Error opening file to write: %s", n);
             free(n);
-            nk_destroy(c);
-            return NK_EIO;
+            return rc;
         }
         free(n);
         p->wbuf_f = malloc(NK_WBUF);
@@ -857,17 +864,15 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
             p->out_r = fopen(n, "w");
             if (!p->out_r)
             {
-                nk_fail(NULL, NK_EIO, "Error opening file to write: %s", n);
+                int rc = nk_fail(c, NK_EIO, "Error opening file to write: %s", n);
                 free(n);
-                nk_destroy(c);
-                return NK_EIO;
+                return rc;
             }
             free(n);
             p->wbuf_r = malloc(NK_WBUF);
             setvbuf(p->out_r, p->wbuf_r, _IOFBF, NK_WBUF);
         }
     }
-    *out = c;
     return NK_OK;
 }
 
@@ -1057,6 +1062,9 @@ int nk_seed_finish(nk_ctx *c)
     for (int d = 0; d < c->n_dev; d++)
         if (c->dev[d].rc)
             return nk_fail(c, c->dev[d].rc, "%s", nkd_last_error(c->dev[d].eng));
+    int orc = nk_open_outputs(c);
+    if (orc)
+        return orc;
     c->seeded = 1;
     c->tot.seed_seconds += nk_now() - t0;
     return NK_OK;
