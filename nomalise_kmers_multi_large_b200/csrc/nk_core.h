@@ -166,6 +166,8 @@ struct NkRun
     NkCounters *ctr;
     unsigned long long *keys_out; /* NK_MODE_KEYS */
     unsigned chunk[NK_NLISTS];    /* entries a warp reserves at a time (device only) */
+    unsigned *bloom;              /* one bit per hashed global slot: "this counter reached depth in this run" */
+    unsigned bloom_words;         /* power of two */
     NkWarpCur *wcur;              /* this warp's cursors in shared memory (device only) */
 };
 
@@ -210,6 +212,16 @@ NK_HD void nk_red_add32(int *p, int v)
 /* count and aux live in one 8-byte word (count low, aux high): +1/+1 or -1/-1 in ONE atomic */
 #define NK_BOTH_PLUS 0x0000000100000001ull
 #define NK_BOTH_MINUS 0xFFFFFFFEFFFFFFFFull
+NK_HD unsigned long long nk_atomic_add64(unsigned long long *p, unsigned long long v)
+{
+#if NK_DEVICE_CODE
+    return atomicAdd(p, v);
+#else
+    unsigned long long o = *p;
+    *p += v;
+    return o;
+#endif
+}
 NK_HD void nk_red_add64(unsigned long long *p, unsigned long long v)
 {
 #if NK_DEVICE_CODE
@@ -225,6 +237,25 @@ NK_HD void nk_red_or32(unsigned *p, unsigned v)
 #else
     *p |= v;
 #endif
+}
+/* L2-resident filter of the counters that reached depth inside the current run (no false negatives) */
+NK_HD void nk_bloom_pos(const NkRun &P, unsigned long long gslot, unsigned &word, unsigned &bit)
+{
+    unsigned long long h = gslot * 0x9E3779B97F4A7C15ull;
+    word = (unsigned)(h >> 37) & (P.bloom_words - 1u);
+    bit = 1u << ((unsigned)(h >> 32) & 31u);
+}
+NK_HD void nk_bloom_set(const NkRun &P, unsigned long long gslot)
+{
+    unsigned w, b;
+    nk_bloom_pos(P, gslot, w, b);
+    nk_red_or32(&P.bloom[w], b);
+}
+NK_HD bool nk_bloom_test(const NkRun &P, unsigned long long gslot)
+{
+    unsigned w, b;
+    nk_bloom_pos(P, gslot, w, b);
+    return (P.bloom[w] & b) != 0;
 }
 /* reserve one entry of list `list` (global counter gctr).  Device: every lane bumps its warp's cursor with its
  * own shared-memory atomic.  No warp aggregation on purpose: appends happen in divergent code, and a
@@ -388,10 +419,14 @@ NK_HD unsigned long long nk_window_key_ascii(const unsigned char *s, int k, int 
 /* ---------------------------------------------------------------- events */
 
 /* Increment of the ordinary counter of a slot that is NOT claimed inside this step (stored before the step, or
- * a ghost that stays empty).  cnt0 = count - aux is its value at step start for every reader at every moment,
- * because unsaturated increments bump count and aux together in one 64-bit RED (aux is 0 between steps and is
- * zeroed again by nk_classify_op).  Saturated: every test is true, only count moves.  The same holds for the
- * -1 replay of an abandoned run. */
+ * a ghost that stays empty).  Unsaturated increments bump count and aux together in one 64-bit atomic, so
+ * count - aux never exceeds the counter's value at step start and equals it whenever aux was 0 then.  aux is
+ * zeroed when a counter is found to have reached depth (nk_classify_op) -- from then on it is saturated and aux
+ * stays 0 -- and when a slot is claimed (nk_prepare_claim_op).  A stale aux on a still-cold counter only makes it
+ * look less saturated, which costs a listing but never changes a result: the test outcome of a listed event comes
+ * from the counter's final value (below depth: false) or from time ranking with base = final - events listed.
+ * The atomic's return value tells the event that takes the counter to `depth`: it marks the run's filter, so that
+ * k_classify only revisits counters that reached depth.  The same holds for the -1 replay of an abandoned run. */
 NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int count, unsigned aux, int terminal, unsigned t,
                     unsigned read, int &high_acc)
 {
@@ -402,7 +437,15 @@ NK_HD void nk_event(const NkRun &P, const NkPart &pd, unsigned slot, int count, 
             high_acc += P.delta;
         return;
     }
-    nk_red_add64(reinterpret_cast<unsigned long long *>(&pd.tab[slot].count), P.delta > 0 ? NK_BOTH_PLUS : NK_BOTH_MINUS);
+    unsigned long long *word = reinterpret_cast<unsigned long long *>(&pd.tab[slot].count);
+    if (P.delta < 0)
+    {
+        nk_red_add64(word, NK_BOTH_MINUS);
+        return;
+    }
+    unsigned long long old = nk_atomic_add64(word, NK_BOTH_PLUS);
+    if ((int)(unsigned)old + 1 >= P.depth)
+        nk_bloom_set(P, pd.gbase + slot);
     if (P.record)
     {
         unsigned idx = nk_list_append(P, NK_LIST_PEND, &P.ctr->n_pend);
@@ -621,22 +664,38 @@ NK_HD void nk_slow_write(const NkRun &P, unsigned si, unsigned long long gslot, 
     P.slow_val[si] = ((unsigned long long)(unsigned)x << 32) | ((unsigned long long)r.read << 1) | (unsigned)kind;
 }
 
-/* ordinary counters: all increments are in.  A counter that ends below depth had only false tests; otherwise its
- * events are ranked by time (returns true: the caller appends a slow record).  aux goes back to 0 (every touched
- * unsaturated counter is visited here). */
+/* ordinary counters: all increments are in.  A counter that never reached depth (not in the filter, or a false
+ * positive whose final count is below depth) had only false tests.  Otherwise its events are ranked by time
+ * (returns true: the caller appends a slow record) and aux goes back to 0. */
 NK_HD bool nk_classify_op(const NkRun &P, unsigned idx, NkPend &r, unsigned long long &gslot, int &x)
 {
     r = P.pend[idx];
     if (r.slot == NK_HOLE)
         return false;
     const NkPart &pd = P.parts[P.reads[r.read].part];
+    gslot = pd.gbase + r.slot;
+    if (!nk_bloom_test(P, gslot))
+        return false;
     NkSlot *s = &pd.tab[r.slot];
     NkSlot e = nk_load_slot(s);
+    if (e.count < P.depth)
+        return false;
     if (e.aux != 0)
         s->aux = 0;
-    gslot = pd.gbase + r.slot;
     x = e.count;
-    return e.count >= P.depth;
+    return true;
+}
+
+/* between probe and the deferred operations: the operation that claims a slot zeroes its aux, which becomes
+ * the slot's post-claim counter (the ghost's stale aux, if any, has no meaning any more) */
+NK_HD void nk_prepare_claim_op(const NkRun &P, unsigned idx)
+{
+    NkOpen o = P.open[idx];
+    if (o.flags == NK_HOLE || !(o.flags & 1u))
+        return;
+    NkSlot *s = &P.parts[o.part].tab[o.slot];
+    if (nk_tag_time(s->key) == o.t && s->aux != 0)
+        s->aux = 0;
 }
 
 /* counters of slots claimed inside the step: apply the listed increments ... */

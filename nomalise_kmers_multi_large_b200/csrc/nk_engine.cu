@@ -256,6 +256,12 @@ __global__ void __launch_bounds__(256) k_open(NkRun P)
     }
 }
 
+__global__ void __launch_bounds__(256) k_prepare_claims(const NkRun P)
+{
+    const unsigned n = min(P.ctr->n_open, P.open_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        nk_prepare_claim_op(P, i);
+}
 __global__ void __launch_bounds__(256) k_apply(const NkRun P, unsigned n)
 {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -561,6 +567,7 @@ struct CudaBackend
             k_probe_keys<<<g, NK_THREADS, 0, stream>>>(P);
         }
     }
+    void prepare_claims(const NkRun &P) { k_prepare_claims<<<sms * 8, 256, 0, stream>>>(P), launches++; }
     void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P), launches++; }
     void apply(const NkRun &P, unsigned n) { k_apply<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }
     void classify(const NkRun &P, unsigned n) { k_classify<<<grid_for(n, 256), 256, 0, stream>>>(P, n), launches++; }

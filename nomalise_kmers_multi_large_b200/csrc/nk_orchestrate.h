@@ -74,6 +74,8 @@ class NkEngine
     unsigned long long *d_keys_out = nullptr;
     NkCounters *d_ctr = nullptr;
     NkPart *d_parts = nullptr;
+    unsigned *d_bloom = nullptr;
+    unsigned bloom_words = 0;
     unsigned open_cap = 0, pend_cap = 0, claim_cap = 0, spec_cap = 0, slow_cap = 0;
 
     NkCounters h_ctr{};
@@ -135,6 +137,11 @@ class NkEngine
         }
         ok &= dalloc(d_ctr, 1);
         ok &= dalloc(d_parts, NK_MAX_PARTITIONS);
+        /* filter: ~8 bits per operation of a step, 64 MB at most so that it stays in the 126 MB L2 */
+        bloom_words = 1u << 15;
+        while (bloom_words < (1u << 24) && (uint64_t)bloom_words * 32u < ops * 8u)
+            bloom_words <<= 1;
+        ok &= dalloc(d_bloom, bloom_words);
         if (!ok)
             return fail(NK_ENOMEM, "nkd_create: cannot allocate step scratch");
         if (!be.prepare_sort(slow_cap, err))
@@ -168,6 +175,7 @@ class NkEngine
         be.release(d_keys_out);
         be.release(d_ctr);
         be.release(d_parts);
+        be.release(d_bloom);
         be.shutdown();
     }
 
@@ -250,6 +258,8 @@ class NkEngine
         P.slow_cap = slow_cap;
         P.ctr = d_ctr;
         P.keys_out = d_keys_out;
+        P.bloom = d_bloom;
+        P.bloom_words = bloom_words;
         be.chunk_sizes(P.chunk, pend_cap, open_cap, claim_cap, slow_cap, spec_cap);
         return P;
     }
@@ -323,6 +333,8 @@ class NkEngine
             /* forward run: probe (claim-independent part), then the deferred operations */
             upload_parts(tabs, lo, hi);
             be.zero(d_ctr, sizeof(NkCounters));
+            if (mode == NK_MODE_SCORE)
+                be.zero(d_bloom, (size_t)bloom_words * sizeof(unsigned));
             NkRun F = make_run(mode, +1, 1);
             if (debug)
             {
@@ -339,6 +351,8 @@ class NkEngine
                 fprintf(stderr, "[nkd] probe done: n_open %u n_pend %u ovf %x\n", h_ctr.n_open, h_ctr.n_pend, h_ctr.overflow);
             }
             be.begin_timer(2);
+            if (mode == NK_MODE_SCORE)
+                be.prepare_claims(F);
             be.open_ops(F);
             be.end_timer(2);
             if (debug)

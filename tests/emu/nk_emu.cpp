@@ -101,6 +101,11 @@ struct EmuBackend
             P.high[op.read] += (unsigned)high;
         }
     }
+    void prepare_claims(const NkRun &P)
+    {
+        for (unsigned idx : order(std::min(P.ctr->n_open, P.open_cap)))
+            nk_prepare_claim_op(P, idx);
+    }
     void open_ops(const NkRun &P)
     {
         unsigned n = std::min(P.ctr->n_open, P.open_cap);
