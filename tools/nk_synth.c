@@ -1,7 +1,7 @@
 /*
  * nk_synth.c -- seeded synthetic paired-end RNA-Seq generator for the benchmarks and parity tests
  * (SURVEY.md 8(d)): T transcripts of length U[400,4000] over uniform ACGT; expression proportional to
- * lognormal(0, sigma=2) x length; fragment length N(300,50) clipped to [L, transcript]; read 1 =
+ * lognormal(0, sigma=2) x length (normal deviates by Irwin-Hall, libm-free); fragment length N(300,50) clipped to [L, transcript]; read 1 =
  * fragment[:L], read 2 = revcomp(fragment)[:L]; 0.5 % substitutions; one N in 1 % of read 1; quality 'I';
  * names of variable width so that the two files differ in size (the reference then takes its
  * record-count partitioner, C:1815-1828) unless --equal is given (C:1807-1813 path).
@@ -9,7 +9,6 @@
  * Library (ctypes) and CLI:  nk_synth -n pairs -o prefix [-s seed] [-t transcripts] [-L readlen] [--equal] [--fasta]
  */
 #define _GNU_SOURCE
-#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -30,12 +29,31 @@ static inline uint64_t rng_next(rng_t *r)
 }
 static inline double rng_unit(rng_t *r) { return (double)(rng_next(r) >> 11) * (1.0 / 9007199254740992.0); }
 static inline uint32_t rng_below(rng_t *r, uint32_t n) { return (uint32_t)(((rng_next(r) >> 32) * (uint64_t)n) >> 32); }
+/* No libm on purpose: the bytes this generator writes are part of committed golden vectors
+ * (tests/golden), so they must not depend on a host's exp/log/cos implementation.  Only + - * / and exact
+ * operations are used (IEEE double, no contraction). */
 static double rng_normal(rng_t *r)
-{
-    double u = rng_unit(r), v = rng_unit(r);
-    if (u < 1e-300)
-        u = 1e-300;
-    return sqrt(-2.0 * log(u)) * cos(6.283185307179586 * v);
+{ /* Irwin-Hall: sum of 12 uniforms - 6 has mean 0, variance 1 */
+    double s = 0.0;
+    for (int i = 0; i < 12; i++)
+        s += rng_unit(r);
+    return s - 6.0;
+}
+static double det_exp(double x)
+{ /* exp(x) = 2^k * exp(rem), rem in [-ln2/2, ln2/2], Taylor to degree 14 (error < 1e-16) */
+    const double ln2 = 0.6931471805599453;
+    double kf = x / ln2;
+    long k = (long)(kf >= 0 ? kf + 0.5 : kf - 0.5);
+    double rem = x - (double)k * ln2, term = 1.0, sum = 1.0;
+    for (int i = 1; i <= 14; i++)
+    {
+        term = term * rem / (double)i;
+        sum += term;
+    }
+    double scale = 1.0;
+    for (long i = 0; i < (k < 0 ? -k : k); i++)
+        scale *= 2.0;
+    return k >= 0 ? sum * scale : sum / scale;
 }
 static void rng_seed(rng_t *r, uint64_t seed)
 {
@@ -114,7 +132,7 @@ int nk_synth_generate(uint64_t n_pairs, uint64_t seed, uint32_t n_transcripts, u
     double acc = 0;
     for (uint32_t t = 0; t < n_transcripts; t++)
     {
-        acc += exp(2.0 * rng_normal(&r)) * (double)tlen[t];
+        acc += det_exp(2.0 * rng_normal(&r)) * (double)tlen[t];
         cum[t] = acc;
     }
     out_t of = {0}, orv = {0};
