@@ -369,6 +369,8 @@ NK_HD unsigned long long nk_mod(unsigned long long x, unsigned long long d, unsi
     return r;
 }
 
+/* is operation time t of this partition inside the window the current launch works on? */
+NK_HD bool nk_live(const NkPart &pd, unsigned t) { return t >= pd.lo && t < pd.hi; }
 NK_HD bool nk_is_real(unsigned long long f) { return f != 0 && !(f & NK_TAG); }
 NK_HD unsigned nk_tag_time(unsigned long long f) { return NK_TMAX - (unsigned)((f >> 32) & NK_TMAX); }
 NK_HD unsigned nk_tag_open(unsigned long long f) { return (unsigned)f; }
@@ -574,6 +576,8 @@ NK_HD unsigned nk_open_op(const NkRun &P, unsigned idx, int &high_acc, int &clai
     if (o.flags == NK_HOLE)
         return 0;
     const NkPart &pd = P.parts[o.part];
+    if (!nk_live(pd, o.t))
+        return 0;
     unsigned long long i = o.slot;
     unsigned c = o.c;
     unsigned touches = 0;
@@ -673,6 +677,8 @@ NK_HD bool nk_classify_op(const NkRun &P, unsigned idx, NkPend &r, unsigned long
     if (r.slot == NK_HOLE)
         return false;
     const NkPart &pd = P.parts[P.reads[r.read].part];
+    if (!nk_live(pd, r.tw >> 2))
+        return false;
     gslot = pd.gbase + r.slot;
     if (!nk_bloom_test(P, gslot))
         return false;
@@ -694,7 +700,7 @@ NK_HD void nk_prepare_claim_op(const NkRun &P, unsigned idx)
     if (o.flags == NK_HOLE || !(o.flags & 1u))
         return;
     NkSlot *s = &P.parts[o.part].tab[o.slot];
-    if (nk_tag_time(s->key) == o.t && s->aux != 0)
+    if ((s->key & NK_TAG) && nk_tag_time(s->key) == o.t && s->aux != 0)
         s->aux = 0;
 }
 
@@ -705,6 +711,8 @@ NK_HD void nk_apply_op(const NkRun &P, unsigned idx)
     if (r.slot == NK_HOLE)
         return;
     const NkPart &pd = P.parts[P.reads[r.read].part];
+    if (!nk_live(pd, r.tw >> 2))
+        return;
     int *ctr = (r.tw & 2u) ? reinterpret_cast<int *>(&pd.tab[r.slot].aux) : &pd.tab[r.slot].count;
     nk_red_add32(ctr, 1);
 }
@@ -716,6 +724,8 @@ NK_HD bool nk_classify_claimed_op(const NkRun &P, unsigned idx, NkPend &r, unsig
     if (r.slot == NK_HOLE)
         return false;
     const NkPart &pd = P.parts[P.reads[r.read].part];
+    if (!nk_live(pd, r.tw >> 2))
+        return false;
     NkSlot e = nk_load_slot(&pd.tab[r.slot]);
     long long v = (r.tw & 2u) ? 1ll + (long long)e.aux : (long long)e.count;
     gslot = pd.gbase + r.slot;
@@ -771,7 +781,7 @@ NK_HD void nk_rank_op(const NkRun &P, const unsigned long long *keys, const unsi
 NK_HD void nk_commit_op(const NkRun &P, unsigned idx)
 {
     NkClaim cl = P.claim[idx];
-    if (cl.slot == NK_HOLE)
+    if (cl.slot == NK_HOLE || !nk_live(P.parts[cl.part], cl.t))
         return;
     NkSlot *s = &P.parts[cl.part].tab[cl.slot];
     NkSlot n;
@@ -785,7 +795,7 @@ NK_HD void nk_commit_op(const NkRun &P, unsigned idx)
 NK_HD void nk_untag_op(const NkRun &P, unsigned idx)
 {
     NkOpen o = P.open[idx];
-    if (o.flags == NK_HOLE || !(o.flags & 1u))
+    if (o.flags == NK_HOLE || !(o.flags & 1u) || !nk_live(P.parts[o.part], o.t))
         return;
     NkSlot *s = &P.parts[o.part].tab[o.slot];
     if (s->key & NK_TAG)

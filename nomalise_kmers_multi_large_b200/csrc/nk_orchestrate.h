@@ -13,6 +13,7 @@
 #define NK_ORCHESTRATE_H
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -208,6 +209,10 @@ class NkEngine
             return NK_OK;
         if (ncap >= 0xFFFFFFFFull)
             return fail(NK_ENOMEM, "table growth beyond 2^32 slots is not supported on one partition");
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        if (debug)
+            be.sync();
+        double t0 = now();
         NkSlot *nt = (NkSlot *)be.alloc(ncap * sizeof(NkSlot));
         if (!nt)
         {
@@ -216,10 +221,15 @@ class NkEngine
                      (unsigned long long)t.cap, (unsigned long long)ncap);
             return fail(NK_ENOMEM, m);
         }
+        double t1 = now();
         be.zero(nt, ncap * sizeof(NkSlot));
         be.rehash(t.tab, t.cap, nt, ncap, nk_magic(ncap));
         be.sync();
+        double t2 = now();
         be.release(t.tab);
+        if (debug)
+            fprintf(stderr, "[nkd] expand %llu -> %llu slots: alloc %.2f ms, zero+rehash %.2f ms, free %.2f ms\n",
+                    (unsigned long long)t.cap, (unsigned long long)ncap, t1 - t0, t2 - t1, now() - t2);
         t.tab = nt;
         t.cap = ncap;
         t.thr = nk_expand_threshold(ncap);
@@ -426,16 +436,34 @@ class NkEngine
             }
             if (debug && (cut || ovf))
                 fprintf(stderr, "[nkd] cut=%d ovf=%d -> undo and retry with shorter windows\n", (int)cut, (int)ovf);
+            /* Partitions whose window must be shortened are abandoned for this round: their part of the run is
+             * replayed with -1 (the decisions are stable) and their claim tags are forgotten.  The others commit
+             * from this very run: every list consumer skips entries of partitions whose window is empty. */
+            std::vector<unsigned> clo(lo), chi(hi); /* windows the commit works on */
             if (cut)
-            { /* abandon this run: replay it with -1 (the decisions are stable), forget the claim attempts */
+            {
+                std::vector<unsigned> ulo(np), uhi(np);
+                for (size_t p = 0; p < np; p++)
+                {
+                    bool dead = ovf || nhi[p] != hi[p];
+                    ulo[p] = dead ? lo[p] : hi[p];
+                    uhi[p] = hi[p];
+                    if (dead)
+                        chi[p] = clo[p]; /* empty: nothing of it is committed */
+                }
+                upload_parts(tabs, ulo, uhi);
                 NkRun U = make_run(mode, -1, 0);
                 be.begin_timer(8);
                 be.probe(U);
                 be.open_ops(U);
                 be.untag(U, std::min(h_ctr.n_open, open_cap));
                 be.end_timer(8);
-                hi = nhi;
-                continue;
+                if (ovf)
+                { /* nothing can be trusted when a list overflowed: retry everything with halved windows */
+                    hi = nhi;
+                    continue;
+                }
+                upload_parts(tabs, clo, chi);
             }
             /* commit */
             if (mode == NK_MODE_SCORE)
@@ -477,6 +505,11 @@ class NkEngine
             for (size_t p = 0; p < np; p++)
             {
                 NkTable &t = *tabs[p];
+                if (chi[p] == clo[p] && hi[p] != lo[p])
+                { /* abandoned this round: run its shortened window next */
+                    hi[p] = nhi[p];
+                    continue;
+                }
                 t.used += h_ctr.claims[p];
                 t.st.used = t.used;
                 t.st.ops += h_ctr.real_ops[p];

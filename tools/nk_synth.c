@@ -1,7 +1,7 @@
 /*
  * nk_synth.c -- seeded synthetic paired-end RNA-Seq generator for the benchmarks and parity tests
  * (SURVEY.md 8(d)): T transcripts of length U[400,4000] over uniform ACGT; expression proportional to
- * lognormal(0, sigma=2) x length (normal deviates by Irwin-Hall, libm-free); fragment length N(300,50) clipped to [L, transcript]; read 1 =
+ * lognormal(0, sigma=2) x length (polar-method normals with libm-free log/exp); fragment length N(300,50) clipped to [L, transcript]; read 1 =
  * fragment[:L], read 2 = revcomp(fragment)[:L]; 0.5 % substitutions; one N in 1 % of read 1; quality 'I';
  * names of variable width so that the two files differ in size (the reference then takes its
  * record-count partitioner, C:1815-1828) unless --equal is given (C:1807-1813 path).
@@ -32,12 +32,36 @@ static inline uint32_t rng_below(rng_t *r, uint32_t n) { return (uint32_t)(((rng
 /* No libm on purpose: the bytes this generator writes are part of committed golden vectors
  * (tests/golden), so they must not depend on a host's exp/log/cos implementation.  Only + - * / and exact
  * operations are used (IEEE double, no contraction). */
+static double det_log(double x)
+{ /* x = m * 2^e with m in [sqrt(1/2), sqrt(2)); log m = 2 atanh((m-1)/(m+1)) by its series */
+    int e = 0;
+    while (x >= 1.4142135623730951)
+    {
+        x *= 0.5;
+        e++;
+    }
+    while (x < 0.7071067811865476)
+    {
+        x *= 2.0;
+        e--;
+    }
+    double z = (x - 1.0) / (x + 1.0), z2 = z * z, term = z, sum = 0.0;
+    for (int i = 1; i <= 41; i += 2)
+    {
+        sum += term / (double)i;
+        term *= z2;
+    }
+    return 2.0 * sum + (double)e * 0.6931471805599453;
+}
 static double rng_normal(rng_t *r)
-{ /* Irwin-Hall: sum of 12 uniforms - 6 has mean 0, variance 1 */
-    double s = 0.0;
-    for (int i = 0; i < 12; i++)
-        s += rng_unit(r);
-    return s - 6.0;
+{ /* Marsaglia polar method; sqrt is the correctly rounded hardware instruction */
+    for (;;)
+    {
+        double u = 2.0 * rng_unit(r) - 1.0, v = 2.0 * rng_unit(r) - 1.0, q = u * u + v * v;
+        if (q >= 1.0 || q < 1e-300)
+            continue;
+        return u * __builtin_sqrt(-2.0 * det_log(q) / q);
+    }
 }
 static double det_exp(double x)
 { /* exp(x) = 2^k * exp(rem), rem in [-ln2/2, ln2/2], Taylor to degree 14 (error < 1e-16) */
