@@ -210,7 +210,7 @@ def barrier(dist, local):
 
 def run_ours(args):
     import torch
-    from nomalise_kmers_multi_large_b200 import Pipeline, capi
+    from nomalise_kmers_multi_large_b200 import Pipeline, capi, plan_ranges
     rank, world, local, dist = dist_setup(args.gpus)
     if world > 1 and "NKB200_THREADS" not in os.environ:   # ranks share the box's host cores
         os.environ["NKB200_THREADS"] = str(max(2, (os.cpu_count() or 2) // world))
@@ -242,8 +242,19 @@ def run_ours(args):
         if sampler:
             sampler.active = it >= args.warmup
         t0 = time.perf_counter()
+        if world > 1:
+            # the byte ranges are computed once (rank 0, all host cores) and handed to the ranks: 256 bytes of control
+            # data, the counterpart of the reference's main thread computing them before it starts its workers
+            plan = torch.zeros((4, PARTS), dtype=torch.int64, device=f"cuda:{local}")
+            if rank == 0:
+                plan.copy_(torch.from_numpy(plan_ranges(fwd, rev, PARTS, True, os.cpu_count() or 0).view(np.int64)))
+            dist.broadcast(plan, src=0)
+            plan_np = plan.cpu().numpy().view(np.uint64)
         for c in ctxs:
-            c.process_paired(fwd, rev)
+            if world > 1:
+                c.process_planned(fwd, rev, plan_np)
+            else:
+                c.process_paired(fwd, rev)
             c.finish()
         torch.cuda.synchronize(local)
         wall = time.perf_counter() - t0

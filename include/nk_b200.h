@@ -210,6 +210,18 @@ int nk_seed_finish(nk_ctx *c);
 int nk_process_paired(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size);
 int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size);
 
+/* The byte ranges multithreaded_process_files_* computes before it starts its threads (C:1796-1838, C:2133-2143):
+ * whole file for one partition, calculate_thread_positions for equal sizes / single-end, the record-count
+ * partitioner otherwise.  Each array has `partitions` entries; rev may be NULL (single-end).  Split out so that a
+ * multi-process launch (one rank per GPU) computes the plan once instead of once per rank. */
+int nk_plan_ranges(const char *fwd, size_t fwd_size, const char *rev, size_t rev_size, int partitions, int fastq,
+                   int threads, uint64_t *fwd_starts, uint64_t *fwd_ends, uint64_t *rev_starts, uint64_t *rev_ends,
+                   char *errbuf, size_t errbuf_size);
+/* nk_process_paired / nk_process_single with a plan from nk_plan_ranges (rev arrays ignored for single-end) */
+int nk_process_planned(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size,
+                       const uint64_t *fwd_starts, const uint64_t *fwd_ends, const uint64_t *rev_starts,
+                       const uint64_t *rev_ends);
+
 typedef struct
 {
     uint64_t processed, printed, skipped; /* reporting.total_* (C:198-205) */

@@ -96,7 +96,8 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores"]
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
-                    "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main"]
+                    "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main",
+                    "nk_plan_ranges", "nk_process_planned"]
 
 
 def _declare_engine(lib):
@@ -144,6 +145,8 @@ def _declare_pipeline(lib):
     lib.nk_count_records.argtypes = [vp, sz, C.c_int]
     lib.nk_count_records.restype = C.c_uint64
     lib.nk_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.nk_plan_ranges.argtypes = [vp, sz, vp, sz, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_char_p, sz]
+    lib.nk_process_planned.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp]
     return lib
 
 

@@ -410,6 +410,12 @@ struct CudaBackend
             return NK_ENODEVICE;
         }
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+        {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         /* the table is probed with random 16-byte gathers: fetch single 32-byte sectors from HBM */
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
         cudaGetLastError();
@@ -424,16 +430,21 @@ struct CudaBackend
             for (auto e : t.ev)
                 cudaEventDestroy(e);
         if (sort_tmp)
-            cudaFree(sort_tmp);
+            cudaFreeAsync(sort_tmp, stream);
         if (stream)
+        {
+            cudaStreamSynchronize(stream);
             cudaStreamDestroy(stream);
+        }
         stream = nullptr;
     }
+    /* stream-ordered allocation from the device's pool, which keeps freed memory: table growth frees and
+     * allocates GBs, and cudaFree/cudaMalloc were seen to take 100-500 ms each there */
     void *alloc(size_t n)
     {
         cudaSetDevice(dev);
         void *p = nullptr;
-        if (cudaMalloc(&p, n ? n : 16) != cudaSuccess)
+        if (cudaMallocAsync(&p, n ? n : 16, stream) != cudaSuccess)
         {
             cudaGetLastError();
             return nullptr;
@@ -445,7 +456,7 @@ struct CudaBackend
         if (p)
         {
             cudaSetDevice(dev);
-            cudaFree(p);
+            cudaFreeAsync(p, stream);
         }
     }
     /* page-locked host memory is mapped into the device address space (UVA): the probe kernel can read the

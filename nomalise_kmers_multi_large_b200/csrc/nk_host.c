@@ -372,14 +372,16 @@ static void nk_lineidx_task(int i, void *a)
     li->cum[i + 1] = nk_count_newlines(li->f->data + lo, hi - lo);
 }
 
-static void nk_lineidx_build(nk_lineidx *li, const nk_buf *f)
+static void nk_lineidx_build_n(nk_lineidx *li, const nk_buf *f, int threads);
+static void nk_lineidx_build(nk_lineidx *li, const nk_buf *f) { nk_lineidx_build_n(li, f, nk_host_threads()); }
+static void nk_lineidx_build_n(nk_lineidx *li, const nk_buf *f, int threads)
 {
     if (!nk_mask64)
         nk_mask64 = nk_mask64_pick();
     li->f = f;
     li->nchunks = (int)((f->size + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
     li->cum = calloc((size_t)li->nchunks + 1, sizeof(uint64_t));
-    nk_parallel_for(li->nchunks, nk_host_threads(), nk_lineidx_task, li);
+    nk_parallel_for(li->nchunks, threads, nk_lineidx_task, li);
     for (int i = 0; i < li->nchunks; i++)
         li->cum[i + 1] += li->cum[i];
 }
@@ -1577,7 +1579,59 @@ static void *nk_device_pipeline(void *a)
     return NULL;
 }
 
-static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev, size_t rsize, int paired)
+static int nk_plan(const nk_buf *ff, const nk_buf *rf, int paired, int P, int fastq, int threads, uint64_t *fs,
+                   uint64_t *fe, uint64_t *rs, uint64_t *re, nk_diag *d)
+{
+    if (!nk_mask64)
+        nk_mask64 = nk_mask64_pick();
+    memset(fs, 0, sizeof(uint64_t) * (size_t)P);
+    memset(fe, 0, sizeof(uint64_t) * (size_t)P);
+    if (rs)
+        memset(rs, 0, sizeof(uint64_t) * (size_t)P);
+    if (re)
+        memset(re, 0, sizeof(uint64_t) * (size_t)P);
+    if (P == 1)
+    { /* C:1796-1803 */
+        fe[0] = ff->size - 1;
+        if (paired)
+            re[0] = rf->size - 1;
+    }
+    else if (!paired || ff->size == rf->size)
+    { /* C:1807-1813, C:2142 */
+        if (nk_ranges_by_size(ff, P, fastq, fs, fe, d) || (paired && nk_ranges_by_size(rf, P, fastq, rs, re, d)))
+            return NK_EDATA;
+    }
+    else
+    { /* C:1815-1828: the forward file's record count is applied to both files */
+        nk_lineidx lf, lr;
+        nk_lineidx_build_n(&lf, ff, threads);
+        nk_lineidx_build_n(&lr, rf, threads);
+        uint64_t recs = nk_records_from_lines(ff, lf.nchunks ? lf.cum[lf.nchunks] : 0, fastq);
+        nk_ranges_by_records(&lf, P, fastq, recs, fs, fe);
+        nk_ranges_by_records(&lr, P, fastq, recs, rs, re);
+        nk_lineidx_free(&lf);
+        nk_lineidx_free(&lr);
+    }
+    return NK_OK;
+}
+
+int nk_plan_ranges(const char *fwd, size_t fwd_size, const char *rev, size_t rev_size, int partitions, int fastq,
+                   int threads, uint64_t *fwd_starts, uint64_t *fwd_ends, uint64_t *rev_starts, uint64_t *rev_ends,
+                   char *errbuf, size_t errbuf_size)
+{
+    if (partitions < 1 || partitions > NK_MAX_PARTITIONS || !fwd || fwd_size == 0 || (rev && rev_size == 0))
+        return NK_EINVAL;
+    nk_buf ff = {fwd, fwd_size}, rf = {rev, rev_size};
+    nk_diag d = {{0}, 0};
+    int rc = nk_plan(&ff, &rf, rev != NULL, partitions, fastq, threads > 0 ? threads : nk_host_threads(), fwd_starts,
+                     fwd_ends, rev_starts, rev_ends, &d);
+    if (rc && errbuf && errbuf_size)
+        snprintf(errbuf, errbuf_size, "%s", d.msg);
+    return rc;
+}
+
+static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev, size_t rsize, int paired,
+                      const uint64_t *plan[4])
 {
     if (!c->seeded)
         return nk_fail(c, NK_EINVAL, "nk_process_* before nk_seed_finish");
@@ -1590,32 +1644,26 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     c->rf.data = rev;
     c->rf.size = rsize;
     c->paired = paired;
-    memset(c->fs, 0, sizeof(uint64_t) * (size_t)P);
-    memset(c->fe, 0, sizeof(uint64_t) * (size_t)P);
-    memset(c->rs, 0, sizeof(uint64_t) * (size_t)P);
-    memset(c->re, 0, sizeof(uint64_t) * (size_t)P);
-    nk_diag d = {{0}, 0};
-    if (P == 1)
-    { /* C:1796-1803 */
-        c->fe[0] = fsize - 1;
+    if (plan)
+    {
+        memcpy(c->fs, plan[0], sizeof(uint64_t) * (size_t)P);
+        memcpy(c->fe, plan[1], sizeof(uint64_t) * (size_t)P);
+        memset(c->rs, 0, sizeof(uint64_t) * (size_t)P);
+        memset(c->re, 0, sizeof(uint64_t) * (size_t)P);
         if (paired)
-            c->re[0] = rsize - 1;
-    }
-    else if (!paired || fsize == rsize)
-    { /* C:1807-1813, C:2142 */
-        if (nk_ranges_by_size(&c->ff, P, fastq, c->fs, c->fe, &d) || (paired && nk_ranges_by_size(&c->rf, P, fastq, c->rs, c->re, &d)))
-            return nk_fail(c, NK_EDATA, "%s", d.msg);
+        {
+            memcpy(c->rs, plan[2], sizeof(uint64_t) * (size_t)P);
+            memcpy(c->re, plan[3], sizeof(uint64_t) * (size_t)P);
+        }
+        for (int t = 0; t < P; t++)
+            if (c->fe[t] >= fsize || c->fs[t] > fsize || (paired && (c->re[t] >= rsize || c->rs[t] > rsize)))
+                return nk_fail(c, NK_EINVAL, "nk_process_planned: range outside the file");
     }
     else
-    { /* C:1815-1828: the forward file's record count is applied to both files */
-        nk_lineidx lf, lr;
-        nk_lineidx_build(&lf, &c->ff);
-        nk_lineidx_build(&lr, &c->rf);
-        uint64_t recs = nk_records_from_lines(&c->ff, lf.nchunks ? lf.cum[lf.nchunks] : 0, fastq);
-        nk_ranges_by_records(&lf, P, fastq, recs, c->fs, c->fe);
-        nk_ranges_by_records(&lr, P, fastq, recs, c->rs, c->re);
-        nk_lineidx_free(&lf);
-        nk_lineidx_free(&lr);
+    {
+        nk_diag d = {{0}, 0};
+        if (nk_plan(&c->ff, &c->rf, paired, P, fastq, c->threads, c->fs, c->fe, c->rs, c->re, &d))
+            return nk_fail(c, NK_EDATA, "%s", d.msg);
     }
     for (int i = 0; i < c->n_local; i++)
     {
@@ -1689,9 +1737,18 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
 
 int nk_process_paired(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size)
 {
-    return nk_process(c, fwd, fwd_size, rev, rev_size, 1);
+    return nk_process(c, fwd, fwd_size, rev, rev_size, 1, NULL);
 }
-int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size) { return nk_process(c, fwd, fwd_size, NULL, 0, 0); }
+int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size) { return nk_process(c, fwd, fwd_size, NULL, 0, 0, NULL); }
+int nk_process_planned(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size,
+                       const uint64_t *fwd_starts, const uint64_t *fwd_ends, const uint64_t *rev_starts,
+                       const uint64_t *rev_ends)
+{
+    const uint64_t *plan[4] = {fwd_starts, fwd_ends, rev_starts, rev_ends};
+    if (!fwd_starts || !fwd_ends || (rev && (!rev_starts || !rev_ends)))
+        return nk_fail(c, NK_EINVAL, "nk_process_planned: missing range arrays");
+    return nk_process(c, fwd, fwd_size, rev, rev ? rev_size : 0, rev != NULL, plan);
+}
 
 int nk_totals_get(nk_ctx *c, nk_totals *out)
 {

@@ -5,6 +5,8 @@ from __future__ import annotations
 import ctypes as C
 import subprocess
 
+import numpy as np
+
 from . import capi
 
 
@@ -52,6 +54,14 @@ class Pipeline:
         pr, nr = self._ptr(rev)
         self._check(self.lib.nk_process_paired(self.h, pf, nf, pr, nr))
 
+    def process_planned(self, fwd, rev, plan):
+        """nk_process_planned: plan = uint64 array of shape (4, partitions) from plan_ranges()"""
+        pf, nf = self._ptr(fwd)
+        pr, nr = self._ptr(rev) if rev is not None else (None, 0)
+        plan = np.ascontiguousarray(plan, dtype=np.uint64)
+        self._check(self.lib.nk_process_planned(self.h, pf, nf, pr, nr, plan[0].ctypes.data, plan[1].ctypes.data,
+                                                plan[2].ctypes.data, plan[3].ctypes.data))
+
     def process_single(self, fwd):
         pf, nf = self._ptr(fwd)
         self._check(self.lib.nk_process_single(self.h, pf, nf))
@@ -81,6 +91,20 @@ class Pipeline:
 
     def __exit__(self, *a):
         self.close()
+
+
+def plan_ranges(fwd, rev, partitions, fastq=True, threads=0, lib=None):
+    """nk_plan_ranges: the byte ranges of every partition (C:1796-1838); returns a (4, partitions) uint64 array."""
+    lib = lib if lib is not None else capi.load_library()
+    plan = np.zeros((4, partitions), dtype=np.uint64)
+    pf, nf = Pipeline._ptr(fwd)
+    pr, nr = Pipeline._ptr(rev) if rev is not None else (None, 0)
+    err = C.create_string_buffer(512)
+    rc = lib.nk_plan_ranges(pf, nf, pr, nr, partitions, int(fastq), threads, plan[0].ctypes.data, plan[1].ctypes.data,
+                            plan[2].ctypes.data, plan[3].ctypes.data, err, 512)
+    if rc != capi.NK_OK:
+        raise capi.NkError(rc, err.value.decode())
+    return plan
 
 
 def run_cli(args, cwd=None, env=None, **kw):

@@ -14,7 +14,7 @@ import torch.distributed as dist
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from nomalise_kmers_multi_large_b200 import capi  # noqa: E402
-from nomalise_kmers_multi_large_b200.pipeline import Pipeline  # noqa: E402
+from nomalise_kmers_multi_large_b200.pipeline import Pipeline, plan_ranges  # noqa: E402
 
 
 def main():
@@ -32,7 +32,12 @@ def main():
         p.seed(fwd, 3000001)
         p.seed(rev, 3000001)
         p.seed_finish()
-        p.process_paired(fwd, rev)
+        # the plan (byte ranges, C:1796-1838) is computed once on rank 0 and broadcast, as bench.py --gpus N does
+        plan = torch.zeros((4, parts), dtype=torch.int64)
+        if rank == 0:
+            plan.copy_(torch.from_numpy(plan_ranges(fwd, rev, parts, True, 2, lib=lib).view(np.int64)))
+        dist.broadcast(plan, src=0)
+        p.process_planned(fwd, rev, plan.numpy().view(np.uint64))
         p.finish()
         t = p.totals()
     sums = torch.tensor([t["processed"], t["printed"], t["skipped"]], dtype=torch.int64)
