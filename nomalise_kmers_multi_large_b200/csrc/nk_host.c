@@ -531,13 +531,6 @@ typedef struct
     uint32_t plain;    /* all lines are "text\n": the record can be copied verbatim */
 } nk_span;
 
-typedef struct nk_rscan /* one record of one mate as the fast scanner found it */
-{
-    uint64_t start;
-    uint32_t nbytes;
-    uint16_t seq_rel, seq_len;
-} nk_rscan;
-
 typedef struct
 {
     size_t fp, fe, rp, re;
@@ -553,12 +546,6 @@ typedef struct
     nk_span *spans;                 /* stride records (fwd, rev) */
     uint32_t ops;
     int64_t fatal_record; /* length-gate passed but the engine reported a non-DNA byte */
-    /* split indexing: the two mates' files are scanned independently, then paired */
-    struct nk_rscan *scan[2];
-    uint32_t n_scan[2];
-    uint8_t stop[2];        /* 0 limit or range end, 1 the data ends after the last scanned record, 2 next record is irregular */
-    size_t scan_end[2];     /* file position after the last scanned record */
-    size_t n_fast_reads;    /* reads whose sequence bytes the copy tasks still have to stage */
 } nk_pstep;
 
 typedef struct
@@ -657,8 +644,6 @@ static void nk_free_stepbuf(nk_stepbuf *sb, int n_parts)
         {
             nkd_free_pinned(sb->ps[i].reads);
             free(sb->ps[i].spans);
-            free(sb->ps[i].scan[0]);
-            free(sb->ps[i].scan[1]);
         }
     free(sb->ps);
     free(sb->segs);
@@ -822,11 +807,9 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
             {
                 sb->ps[i].reads = nkd_alloc_pinned((size_t)sp * 2u * sizeof(nkd_read));
                 sb->ps[i].spans = malloc((size_t)sp * 2u * sizeof(nk_span));
-                sb->ps[i].scan[0] = malloc((size_t)sp * sizeof(nk_rscan));
-                sb->ps[i].scan[1] = malloc((size_t)sp * sizeof(nk_rscan));
                 sb->ps[i].seq_lo = (size_t)i * c->step_bytes;
                 sb->ps[i].seq_end = sb->ps[i].seq_lo + c->step_bytes;
-                if (!sb->ps[i].reads || !sb->ps[i].spans || !sb->ps[i].scan[0] || !sb->ps[i].scan[1])
+                if (!sb->ps[i].reads || !sb->ps[i].spans)
                 {
                     nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (staging buffers)");
                     nk_destroy(c);
@@ -1100,8 +1083,9 @@ typedef struct
 
 /* Fill one partition's share of a step: the worker loop's record reader (C:1605-1631) up to the
  * step's record/byte/operation budget. */
-static void nk_index_seq(nk_step_job *j, int li, int append)
+static void nk_index_task(int li, void *a)
 {
+    nk_step_job *j = a;
     nk_ctx *c = j->c;
     nk_part *p = &c->part[j->dv->parts[li]];
     nk_pstep *ps = &j->sb->ps[li];
@@ -1109,14 +1093,10 @@ static void nk_index_seq(nk_step_job *j, int li, int append)
     const int per = c->cfg.in_fastq ? 4 : 2, k = c->cfg.k, paired = c->paired;
     const nk_buf *ff = &c->ff, *rf = &c->rf;
     nk_cursor *cur = &p->cur;
-    if (!append)
-    {
-        ps->n_reads = ps->n_records = 0;
-        ps->ops = 0;
-        ps->seq_hi = ps->seq_lo;
-        ps->n_fast_reads = 0;
-    }
-    size_t pos = ps->seq_hi;
+    ps->n_reads = ps->n_records = 0;
+    ps->ops = 0;
+    ps->seq_hi = ps->seq_lo;
+    size_t pos = ps->seq_lo;
     while (!cur->done && cur->fp < cur->fe && (!paired || cur->rp < cur->re))
     {
         if (ps->n_records >= c->step_pairs || pos + 2 * NK_MAX_LINE > ps->seq_end || ps->ops + 2 * NK_MAX_LINE > c->step_ops)
@@ -1240,150 +1220,6 @@ static void nk_index_seq(nk_step_job *j, int li, int append)
         ps->n_records++;
     }
     ps->seq_hi = pos;
-}
-
-/* ---- split indexing: scan each mate's file on its own thread, pair the records, stage the sequences ---- */
-
-static void nk_scan_task(int idx, void *a)
-{
-    nk_step_job *j = a;
-    nk_ctx *c = j->c;
-    const int stride = c->paired ? 2 : 1, li = idx / stride, mate = idx % stride;
-    nk_part *p = &c->part[j->dv->parts[li]];
-    nk_pstep *ps = &j->sb->ps[li];
-    nk_cursor *cur = &p->cur;
-    const int per = c->cfg.in_fastq ? 4 : 2;
-    const nk_buf *buf = mate ? &c->rf : &c->ff;
-    nk_nliter *it = mate ? &cur->itr : &cur->itf;
-    size_t pos = mate ? cur->rp : cur->fp;
-    const size_t end = mate ? cur->re : cur->fe;
-    nk_rscan *out = ps->scan[mate];
-    uint32_t n = 0;
-    uint8_t stop = 0;
-    while (!cur->done && n < c->step_pairs && pos < end)
-    {
-        size_t q = pos;
-        uint16_t seq_rel = 0, seq_len = 0;
-        int ok = 1;
-        for (int i = 0; i < per; i++)
-        {
-            size_t nl = nk_nliter_next(it);
-            if (nl == SIZE_MAX || nl - q >= (size_t)NK_MAX_LINE)
-            {
-                ok = 0;
-                break;
-            }
-            if (i == 1)
-            {
-                seq_rel = (uint16_t)(q - pos);
-                seq_len = (uint16_t)(nl - q);
-            }
-            q = nl + 1;
-        }
-        if (!ok || it->nul_seen)
-        { /* anything unusual is left to the byte-exact sequential reader */
-            stop = 2;
-            break;
-        }
-        out[n].start = pos;
-        out[n].nbytes = (uint32_t)(q - pos);
-        out[n].seq_rel = seq_rel;
-        out[n].seq_len = seq_len;
-        n++;
-        pos = q;
-        if (nk_at(buf, pos) == '\0')
-        { /* read_line returned NULL on the record's last line: it is scored, then the partition stops */
-            stop = 1;
-            break;
-        }
-    }
-    ps->n_scan[mate] = n;
-    ps->stop[mate] = stop;
-    ps->scan_end[mate] = pos;
-}
-
-static void nk_merge_task(int li, void *a)
-{
-    nk_step_job *j = a;
-    nk_ctx *c = j->c;
-    nk_part *p = &c->part[j->dv->parts[li]];
-    nk_pstep *ps = &j->sb->ps[li];
-    nk_cursor *cur = &p->cur;
-    const int k = c->cfg.k, paired = c->paired;
-    ps->n_reads = ps->n_records = 0;
-    ps->ops = 0;
-    ps->seq_hi = ps->seq_lo;
-    size_t pos = ps->seq_lo;
-    const uint32_t nf = ps->n_scan[0], nr = paired ? ps->n_scan[1] : nf;
-    const uint32_t n = nf < nr ? nf : nr;
-    uint32_t used = 0;
-    for (; used < n; used++)
-    {
-        if (ps->n_records >= c->step_pairs || pos + 2 * NK_MAX_LINE > ps->seq_end || ps->ops + 2 * NK_MAX_LINE > c->step_ops)
-            break;
-        const nk_rscan *f = &ps->scan[0][used], *r = paired ? &ps->scan[1][used] : NULL;
-        if ((int)f->seq_len < k || (paired && (int)r->seq_len < k))
-            continue; /* dropped silently, C:1430-1443 */
-        for (int m = 0; m < (paired ? 2 : 1); m++)
-        {
-            const nk_rscan *x = m ? r : f;
-            nkd_read *rd = &ps->reads[ps->n_reads];
-            rd->seq_off = (uint32_t)pos;
-            rd->op_base = ps->ops;
-            rd->len = x->seq_len;
-            rd->part = (uint16_t)p->lidx;
-            rd->reserved = 0;
-            nk_span *sp = &ps->spans[ps->n_reads];
-            sp->start = x->start;
-            sp->nbytes = x->nbytes;
-            sp->seq_rel = x->seq_rel;
-            sp->seq_len = x->seq_len;
-            sp->plain = 1;
-            ps->n_reads++;
-            ps->ops += (uint32_t)(x->seq_len - k + 1);
-            pos += ((size_t)x->seq_len + 15) & ~(size_t)15;
-        }
-        ps->n_records++;
-    }
-    ps->seq_hi = pos;
-    ps->n_fast_reads = ps->n_reads;
-    /* move the cursors to the first record not taken */
-    int cont_seq = 0;
-    for (int m = 0; m < (paired ? 2 : 1); m++)
-    {
-        size_t np_ = used < ps->n_scan[m] ? ps->scan[m][used].start : ps->scan_end[m];
-        const nk_buf *buf = m ? &c->rf : &c->ff;
-        if (m)
-            cur->rp = np_;
-        else
-            cur->fp = np_;
-        if (used < ps->n_scan[m] || ps->stop[m] == 2)
-            nk_nliter_seek(m ? &cur->itr : &cur->itf, buf->data, np_, buf->size); /* scanned past it: re-aim */
-        if (used == ps->n_scan[m] && ps->stop[m] == 1 && used > 0)
-            cur->done = 1; /* the data ended right after the last record taken */
-        if (used == ps->n_scan[m] && ps->stop[m] == 2)
-            cont_seq = 1;
-    }
-    if (cont_seq && !cur->done)
-        nk_index_seq(j, li, 1); /* the next record is unusual: finish this step with the exact reader */
-}
-
-static void nk_copy_task(int idx, void *a)
-{
-    nk_step_job *j = a;
-    nk_ctx *c = j->c;
-    const int stride = c->paired ? 2 : 1, li = idx / stride, mate = idx % stride;
-    nk_pstep *ps = &j->sb->ps[li];
-    uint8_t *seqbuf = j->sb->seq;
-    const nk_buf *src = mate ? &c->rf : &c->ff;
-    for (size_t r = (size_t)mate; r < ps->n_fast_reads; r += (size_t)stride)
-    {
-        const nkd_read *rd = &ps->reads[r];
-        const nk_span *sp = &ps->spans[r];
-        size_t need = ((size_t)rd->len + 15) & ~(size_t)15;
-        memcpy(seqbuf + rd->seq_off, src->data + sp->start + sp->seq_rel, rd->len);
-        memset(seqbuf + rd->seq_off + rd->len, 0, need - rd->len);
-    }
 }
 
 /* ------------------------------------------------------------------ writer (C:1649-1666, C:852-876) */
@@ -1528,7 +1364,7 @@ static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_inv
         sb->segs[nseg].n_reads = ps->n_reads;
         sb->segs[nseg].seq_lo = ps->seq_lo;
         sb->segs[nseg].seq_hi = ps->seq_hi;
-        sb->segs[nseg].trusted = 1; /* built by the indexer under the nkd_read rules */
+        sb->segs[nseg].trusted = 1; /* built by nk_index_task under the nkd_read rules */
         sb->segs[nseg].part = (uint32_t)i;
         sb->segs[nseg].ops = ps->ops;
         nseg++;
@@ -1585,10 +1421,7 @@ static size_t nk_build_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
 {
     double t0 = nk_now();
     nk_step_job job = {c, dv, sb};
-    const int stride = c->paired ? 2 : 1;
-    nk_parallel_for(dv->n_parts * stride, threads, nk_scan_task, &job);
-    nk_parallel_for(dv->n_parts, threads, nk_merge_task, &job);
-    nk_parallel_for(dv->n_parts * stride, threads, nk_copy_task, &job);
+    nk_parallel_for(dv->n_parts, threads, nk_index_task, &job);
     size_t n = 0;
     for (int i = 0; i < dv->n_parts; i++)
     {
@@ -1695,15 +1528,10 @@ static void *nk_device_pipeline(void *a)
         threads = 2;
     /* one indexing task per partition, one writing task per partition and mate: give the indexer a thread
      * per partition when there are enough cores and the writer the rest */
-    {
-        int tasks = dv->n_parts * (c->paired ? 2 : 1); /* scan/copy and write tasks per step */
-        pp->t_index = (threads * 5 + 7) / 8;
-        if (pp->t_index > tasks)
-            pp->t_index = tasks;
-        if (pp->t_index >= threads)
-            pp->t_index = threads - 1;
-        pp->t_write = threads - pp->t_index;
-    }
+    pp->t_index = dv->n_parts < threads - 1 ? dv->n_parts : (threads * 2 + 2) / 3;
+    if (pp->t_index >= threads)
+        pp->t_index = threads - 1;
+    pp->t_write = threads - pp->t_index;
     dv->rc = NK_OK;
     pthread_mutex_init(&pp->mu, NULL);
     pthread_cond_init(&pp->cv, NULL);
