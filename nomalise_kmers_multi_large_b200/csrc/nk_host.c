@@ -597,8 +597,9 @@ struct nk_ctx
     int threads;
     uint32_t step_pairs, step_ops, step_bytes;
     /* seeding */
-    uint8_t *seed_seq;
-    nkd_read *seed_reads;
+    uint8_t *seed_seq[2]; /* two staging buffers: one is parsed into while the GPUs seed from the other */
+    nkd_read *seed_reads[2];
+    uint64_t *seed_pos[2];
     size_t seed_cap_reads, seed_cap_bytes, seed_cap_ops;
     int seeded;
     /* totals */
@@ -674,8 +675,12 @@ void nk_destroy(nk_ctx *c)
         free(c->part[i].wbuf_f);
         free(c->part[i].wbuf_r);
     }
-    nkd_free_pinned(c->seed_seq);
-    nkd_free_pinned(c->seed_reads);
+    for (int b = 0; b < 2; b++)
+    {
+        nkd_free_pinned(c->seed_seq[b]);
+        nkd_free_pinned(c->seed_reads[b]);
+        free(c->seed_pos[b]);
+    }
     free(c->fs);
     free(c->fe);
     free(c->rs);
@@ -828,15 +833,19 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
     c->seed_cap_ops = (size_t)min_dev_parts * c->step_ops;
     if (c->seed_cap_ops > (1u << 27))
         c->seed_cap_ops = 1u << 27; /* one table: stay below 2^28 operations per step */
-    c->seed_seq = nkd_alloc_pinned(c->seed_cap_bytes + 64);
-    c->seed_reads = nkd_alloc_pinned(c->seed_cap_reads * sizeof(nkd_read));
-    if (!c->seed_seq || !c->seed_reads)
+    for (int b = 0; b < 2; b++)
     {
-        nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (seed staging)");
-        nk_destroy(c);
-        return NK_ENOMEM;
+        c->seed_seq[b] = nkd_alloc_pinned(c->seed_cap_bytes + 64);
+        c->seed_reads[b] = nkd_alloc_pinned(c->seed_cap_reads * sizeof(nkd_read));
+        c->seed_pos[b] = malloc(c->seed_cap_reads * sizeof(uint64_t));
+        if (!c->seed_seq[b] || !c->seed_reads[b] || !c->seed_pos[b])
+        {
+            nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (seed staging)");
+            nk_destroy(c);
+            return NK_ENOMEM;
+        }
+        memset(c->seed_seq[b], 0, c->seed_cap_bytes + 64);
     }
-    memset(c->seed_seq, 0, c->seed_cap_bytes + 64);
     *out = c;
     return NK_OK;
 }
@@ -883,9 +892,14 @@ static int nk_open_outputs(nk_ctx *c)
 typedef struct
 {
     nk_ctx *c;
+    int buf;
     size_t n_reads, bytes;
+    const nk_buf *f;
     int64_t inv[64];
     int rc[64];
+    int result;
+    pthread_t th;
+    int running;
 } nk_seed_job;
 
 static void nk_seed_task(int d, void *a)
@@ -893,7 +907,7 @@ static void nk_seed_task(int d, void *a)
     nk_seed_job *j = a;
     nk_dev *dv = &j->c->dev[d];
     j->inv[d] = -1;
-    j->rc[d] = nkd_seed_step(dv->eng, j->c->seed_seq, j->bytes, j->c->seed_reads, j->n_reads, &j->inv[d]);
+    j->rc[d] = nkd_seed_step(dv->eng, j->c->seed_seq[j->buf], j->bytes, j->c->seed_reads[j->buf], j->n_reads, &j->inv[d]);
 }
 
 static void nk_scrub_copy(char *dst, const char *src, size_t n)
@@ -903,31 +917,38 @@ static void nk_scrub_copy(char *dst, const char *src, size_t n)
     dst[n] = 0;
 }
 
-static int nk_seed_flush(nk_ctx *c, size_t n_reads, size_t bytes, const nk_buf *f, const uint64_t *seq_pos)
+/* one batch of seed reads on every GPU (each builds the same seed table) */
+static void *nk_seed_flush_thread(void *a)
 {
-    if (!n_reads)
-        return NK_OK;
+    nk_seed_job *j = a;
+    nk_ctx *c = j->c;
+    j->result = NK_OK;
     if (getenv("NKB200_DEBUG"))
-        fprintf(stderr, "[nk] seed flush: %zu reads, %zu bytes\n", n_reads, bytes);
-    nk_seed_job job;
-    memset(&job, 0, sizeof job);
-    job.c = c;
-    job.n_reads = n_reads;
-    job.bytes = bytes;
-    nk_parallel_for(c->n_dev, c->n_dev, nk_seed_task, &job); /* every GPU builds the same seed table */
+        fprintf(stderr, "[nk] seed flush: %zu reads, %zu bytes\n", j->n_reads, j->bytes);
+    nk_parallel_for(c->n_dev, c->n_dev, nk_seed_task, j);
     for (int d = 0; d < c->n_dev; d++)
-        if (job.rc[d])
-            return nk_fail(c, job.rc[d], "%s", nkd_last_error(c->dev[d].eng));
-    if (job.inv[0] >= 0)
+        if (j->rc[d] && !j->result)
+            j->result = nk_fail(c, j->rc[d], "%s", nkd_last_error(c->dev[d].eng));
+    if (!j->result && j->inv[0] >= 0)
     { /* is_valid_sequence_single's abort, C:1416-1420 */
-        size_t i = (size_t)job.inv[0];
-        char *s = malloc((size_t)c->seed_reads[i].len + 1);
-        nk_scrub_copy(s, f->data + seq_pos[i], c->seed_reads[i].len);
+        size_t i = (size_t)j->inv[0];
+        const nkd_read *rd = &c->seed_reads[j->buf][i];
+        char *s = malloc((size_t)rd->len + 1);
+        nk_scrub_copy(s, j->f->data + c->seed_pos[j->buf][i], rd->len);
         nk_fail(c, NK_EDATA, "FATAL: FWD sequence does not appear to be a DNA sequence\n%s\n", s);
         free(s);
-        return NK_EDATA;
+        j->result = NK_EDATA;
     }
-    return NK_OK;
+    return NULL;
+}
+
+static int nk_seed_join(nk_seed_job *j)
+{
+    if (!j->running)
+        return NK_OK;
+    pthread_join(j->th, NULL);
+    j->running = 0;
+    return j->result;
 }
 
 int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed)
@@ -935,30 +956,43 @@ int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed
     if (c->seeded)
         return nk_fail(c, NK_EINVAL, "nk_seed_buffer after nk_seed_finish");
     double t0 = nk_now();
+    if (!nk_mask64)
+        nk_mask64 = nk_mask64_pick();
     nk_buf f = {data, size};
     int per = c->cfg.in_fastq ? 4 : 2, k = c->cfg.k;
-    int line = 0, done = 0, rc = NK_OK;
-    size_t line_start = 0, seq_start = 0, seq_len = 0;
+    int done = 0, rc = NK_OK, cur = 0;
     size_t n_reads = 0, bytes = 0, ops = 0;
-    uint64_t *seq_pos = malloc(c->seed_cap_reads * sizeof *seq_pos);
-    const char *q = data, *end = data + size;
-    /* seed_kmer_hash splits on '\n' only and needs every line of a record terminated */
-    while (q < end && (q = memchr(q, '\n', (size_t)(end - q))) != NULL)
+    nk_seed_job jobs[2];
+    memset(jobs, 0, sizeof jobs);
+    /* seed_kmer_hash splits on '\n' only and needs every line of a record terminated (C:1334-1344); the GPUs
+     * seed from one staging buffer while the next batch is parsed into the other */
+    nk_nliter it;
+    nk_nliter_seek(&it, data, 0, size);
+    size_t rec_start = 0;
+    for (;;)
     {
-        size_t i = (size_t)(q - data);
-        q++;
-        if (line == 1)
+        size_t q = rec_start, seq_start = 0, seq_len = 0;
+        int ok = 1;
+        for (int i = 0; i < per; i++)
         {
-            seq_start = line_start;
-            seq_len = i - line_start;
+            size_t nl = nk_nliter_next(&it);
+            if (nl == SIZE_MAX)
+            {
+                ok = 0;
+                break;
+            }
+            if (i == 1)
+            {
+                seq_start = q;
+                seq_len = nl - q;
+            }
+            q = nl + 1;
         }
-        line++;
-        line_start = i + 1;
-        if (line < per)
-            continue;
-        line = 0;
-        size_t slen = strnlen(data + seq_start, seq_len);
-        if (slen <= (size_t)k) /* strictly longer than K, C:1347 */
+        if (!ok)
+            break; /* no further complete record */
+        rec_start = q;
+        size_t slen = it.nul_seen ? strnlen(data + seq_start, seq_len) : seq_len; /* strlen semantics, C:1347 */
+        if (slen <= (size_t)k) /* strictly longer than K */
             continue;
         if (slen >= NK_MAX_LINE)
         {
@@ -968,29 +1002,54 @@ int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed
         size_t need = (slen + 15) & ~(size_t)15, nops = slen - (size_t)k + 1;
         if (n_reads + 1 > c->seed_cap_reads || bytes + need > c->seed_cap_bytes || ops + nops > c->seed_cap_ops)
         {
-            rc = nk_seed_flush(c, n_reads, bytes, &f, seq_pos);
+            /* hand the full buffer to the GPUs (after the previous hand-off finished) and switch */
+            rc = nk_seed_join(&jobs[cur ^ 1]);
             if (rc)
                 break;
+            jobs[cur].c = c;
+            jobs[cur].buf = cur;
+            jobs[cur].n_reads = n_reads;
+            jobs[cur].bytes = bytes;
+            jobs[cur].f = &f;
+            if (pthread_create(&jobs[cur].th, NULL, nk_seed_flush_thread, &jobs[cur]) != 0)
+            {
+                rc = nk_fail(c, NK_EINTERNAL, "cannot start the seeding thread");
+                break;
+            }
+            jobs[cur].running = 1;
+            cur ^= 1;
             n_reads = bytes = ops = 0;
         }
-        memcpy(c->seed_seq + bytes, data + seq_start, slen);
-        memset(c->seed_seq + bytes + slen, 0, need - slen);
-        nkd_read *rd = &c->seed_reads[n_reads];
+        uint8_t *dst = c->seed_seq[cur] + bytes;
+        memcpy(dst, data + seq_start, slen);
+        memset(dst + slen, 0, need - slen);
+        nkd_read *rd = &c->seed_reads[cur][n_reads];
         rd->seq_off = (uint32_t)bytes;
         rd->op_base = (uint32_t)ops;
         rd->len = (uint16_t)slen;
         rd->part = 0;
         rd->reserved = 0;
-        seq_pos[n_reads] = seq_start;
+        c->seed_pos[cur][n_reads] = seq_start;
         n_reads++;
         bytes += need;
         ops += nops;
         if (++done == records_to_seed)
             break;
     }
+    /* batches must reach the table in order: wait for the one in flight, then run the last one */
+    int rc2 = nk_seed_join(&jobs[cur ^ 1]);
     if (!rc)
-        rc = nk_seed_flush(c, n_reads, bytes, &f, seq_pos);
-    free(seq_pos);
+        rc = rc2;
+    if (!rc && n_reads)
+    {
+        jobs[cur].c = c;
+        jobs[cur].buf = cur;
+        jobs[cur].n_reads = n_reads;
+        jobs[cur].bytes = bytes;
+        jobs[cur].f = &f;
+        nk_seed_flush_thread(&jobs[cur]);
+        rc = jobs[cur].result;
+    }
     c->tot.seed_seconds += nk_now() - t0;
     return rc;
 }
