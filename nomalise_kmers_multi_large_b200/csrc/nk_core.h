@@ -337,11 +337,7 @@ NK_HD NkSlot nk_load_slot(const NkSlot *p)
      * untouched during the launch or only need ">= depth-1", and an unseen claim TAG reads as "empty at step
      * start", which is what a TAG means.  asm volatile keeps the compiler from merging re-reads in the walk loop. */
     uint4 v;
-#ifdef NK_LOAD_CG
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#else
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#endif
     NkSlot s;
     s.key = ((unsigned long long)v.y << 32) | v.x;
     s.count = (int)v.z;
