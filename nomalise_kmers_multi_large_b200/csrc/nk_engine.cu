@@ -481,6 +481,11 @@ struct CudaBackend
 
     /* entries a warp reserves per global atomic: large enough to make the atomics negligible, small enough
      * that the holes of (SMs x 8 x 8) warps stay a small fraction of the list */
+    static unsigned env_chunk(const char *name, unsigned dflt)
+    {
+        const char *e = getenv(name);
+        return e && atoi(e) >= 32 ? (unsigned)atoi(e) : dflt;
+    }
     void chunk_sizes(unsigned *c, unsigned pend_cap, unsigned open_cap, unsigned claim_cap, unsigned slow_cap,
                      unsigned spec_cap)
     {
@@ -489,8 +494,8 @@ struct CudaBackend
             unsigned v = cap / (4u * warps);
             return v < 32u ? 32u : (v > mx ? mx : v);
         };
-        c[NK_LIST_PEND] = pick(pend_cap, 384);
-        c[NK_LIST_OPEN] = pick(open_cap, 192);
+        c[NK_LIST_PEND] = pick(pend_cap, env_chunk("NKB200_CHUNK_PEND", 384));
+        c[NK_LIST_OPEN] = pick(open_cap, env_chunk("NKB200_CHUNK_OPEN", 192));
         c[NK_LIST_CLAIM] = pick(claim_cap, 32);
         c[NK_LIST_SLOW] = pick(slow_cap, 32);
         c[NK_LIST_SPEC] = pick(spec_cap, 64);

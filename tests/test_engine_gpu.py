@@ -16,6 +16,10 @@ CASES = [
     dict(k=31, canonical=False, depth=5, cap0=1009, paired=True, n_parts=2),
     dict(k=21, canonical=True, depth=12, cap0=3001, paired=True, n_parts=4),
     dict(k=7, canonical=True, depth=3, cap0=16384, paired=False, n_parts=2),
+    # reads up to the 1023-base line limit (C:397): several packing iterations per read, more events per read than
+    # two list chunks hold (global-atomic fallback of the chunked appends)
+    dict(k=27, canonical=True, depth=3, cap0=60013, paired=True, n_parts=2, read_len=(400, 1023), genome_len=20000,
+         records_per_step=24, n_seed_reads=30),
     dict(k=25, canonical=True, depth=12, cap0=1000003, paired=True, n_parts=8, genome_len=200000,
          records_per_step=400, read_len=(150, 150), n_seed_reads=2000),
 ]
