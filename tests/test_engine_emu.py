@@ -26,7 +26,9 @@ CASES = [
 @pytest.mark.parametrize("seed", [1, 2])
 def test_emulated_engine_matches_oracle(emu_lib, case, seed, monkeypatch):
     monkeypatch.setenv("NK_EMU_SEED", str(seed * 7919))
-    info = ec.run_case(emu_lib, seed=seed, steps=3, records_per_step=60, **case)
+    kw = dict(steps=3, records_per_step=60)
+    kw.update(case)
+    info = ec.run_case(emu_lib, seed=seed, **kw)
     assert info["ops"] > 0
 
 
