@@ -761,8 +761,8 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         if (e && atoi(e) > 0)
             sp = (uint32_t)atoi(e);
         else
-        {
-            sp = 32768u;
+        { /* about 75 M operations per device step whatever the number of resident partitions */
+            sp = 262144u;
             while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > (96ull << 20))
                 sp /= 2;
         }
