@@ -153,6 +153,24 @@ int nkd_part_stats_get(nkd_engine *e, int part, nkd_part_stats *out);
 /* print_kmer_table's data source (C:354-385): slot-ordered copy of partition's table */
 int nkd_export(nkd_engine *e, int part, uint64_t *keys, int32_t *counts, uint64_t capacity);
 
+/* print_kmer_table on the device (C:354-385): the "KMER\tcount\n" lines of entries [first, first+n) of a
+ * table, in slot order, formatted by a kernel; only the text crosses PCIe.  part = partition index,
+ * NKD_PART_SEED (the seed table, before nkd_seed_finish) or NKD_PART_MERGED (after nkd_merge_finish;
+ * entries are then the distinct k-mers in ascending order).  text must hold n * (k + 13) bytes for a
+ * table, n * (k + 22) for the merged table; *bytes = text length. */
+#define NKD_PART_SEED (-1)
+#define NKD_PART_MERGED (-2)
+int nkd_dump_text(nkd_engine *e, int part, uint64_t first, uint64_t n, char *text, size_t text_cap, size_t *bytes);
+/* stored (k-mer, count) pairs of a table in slot order, compacted on the device; *n = their number (= used) */
+int nkd_compact(nkd_engine *e, int part, uint64_t *keys, int64_t *counts, uint64_t cap_entries, uint64_t *n);
+/* merged table across partitions (the author's TODO, C:25-26): every stored k-mer once, ascending, with
+ * its counts summed over the partitions.  begin(total entries) -> add_part (a partition of this engine)
+ * / add (pairs compacted on another GPU) -> finish -> nkd_dump_text(e, NKD_PART_MERGED, ...). */
+int nkd_merge_begin(nkd_engine *e, uint64_t max_entries);
+int nkd_merge_add_part(nkd_engine *e, int part);
+int nkd_merge_add(nkd_engine *e, const uint64_t *keys, const int64_t *counts, uint64_t n);
+int nkd_merge_finish(nkd_engine *e, uint64_t *n_unique);
+
 /* test hook: per-read (high, total) of the step just run (sequence_to_hash's two outputs, C:1459-1499);
  * valid between nkd_run and the next nkd_stage */
 int nkd_read_scores(nkd_engine *e, uint32_t *high, uint32_t *total, size_t n_reads);
@@ -185,6 +203,10 @@ typedef struct
     const int *devices; /* NULL = 0..n_devices-1 */
     int part_first, part_count;
     uint32_t step_pairs; /* records per partition per step, 0 = default */
+    /* extras the reference leaves to the user (C:25-26, README): written by nk_finish next to the
+     * per-partition files; both need a context that owns every partition */
+    int merged_table;  /* output_kmer_merged.k{K}_norm{D}.tsv: all partitions' k-mers, ascending, counts summed */
+    int merged_output; /* output_forward/output_reverse.k{K}_norm{D}.fastq: partitions concatenated in order */
 } nk_config;
 
 typedef struct nk_ctx nk_ctx;

@@ -72,7 +72,7 @@ class PipelineConfig(C.Structure):
                 ("dump_tables", C.c_int), ("verbose", C.c_int), ("n_forward_files", C.c_int),
                 ("have_reverse", C.c_int), ("out_dir", C.c_char_p), ("n_devices", C.c_int),
                 ("devices", C.POINTER(C.c_int)), ("part_first", C.c_int), ("part_count", C.c_int),
-                ("step_pairs", C.c_uint32)]
+                ("step_pairs", C.c_uint32), ("merged_table", C.c_int), ("merged_output", C.c_int)]
 
 
 class Totals(C.Structure):
@@ -93,7 +93,9 @@ class Totals(C.Structure):
 ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step", "nkd_seed_finish", "nkd_seed_stats",
                   "nkd_seed_export", "nkd_stage", "nkd_run", "nkd_fetch", "nkd_last_run_ms", "nkd_part_stats_get",
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
-                  "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores"]
+                  "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
+                  "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish"]
+PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
                     "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main",
@@ -120,6 +122,12 @@ def _declare_engine(lib):
     lib.nkd_extract_keys.argtypes = [vp, u8p, sz, vp, sz, vp, sz, u8p]
     lib.nkd_run_stats_get.argtypes = [vp, C.POINTER(RunStats)]
     lib.nkd_read_scores.argtypes = [vp, vp, vp, sz]
+    lib.nkd_dump_text.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp, sz, C.POINTER(sz)]
+    lib.nkd_compact.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.nkd_merge_begin.argtypes = [vp, C.c_uint64]
+    lib.nkd_merge_add_part.argtypes = [vp, C.c_int]
+    lib.nkd_merge_add.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.nkd_merge_finish.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.nkd_device_count.restype = C.c_int
     return lib
 
@@ -287,6 +295,32 @@ class Engine:
         keys, counts = np.empty(cap, np.uint64), np.empty(cap, np.int32)
         self._check(self.lib.nkd_export(self.h, part, keys.ctypes.data, counts.ctypes.data, cap))
         return keys, counts
+
+    def dump_text(self, part, first, n):
+        """print_kmer_table's lines for entries [first, first+n), formatted on the device (C:354-385)"""
+        buf = np.empty(max(1, n * (self.cfg.k + (22 if part == PART_MERGED else 13))), np.uint8)
+        got = C.c_size_t(0)
+        self._check(self.lib.nkd_dump_text(self.h, part, first, n, buf.ctypes.data, buf.size, C.byref(got)))
+        return buf[:got.value].tobytes()
+
+    def compact(self, part, cap_entries):
+        keys, counts = np.empty(max(1, cap_entries), np.uint64), np.empty(max(1, cap_entries), np.int64)
+        n = C.c_uint64(0)
+        self._check(self.lib.nkd_compact(self.h, part, keys.ctypes.data, counts.ctypes.data, cap_entries, C.byref(n)))
+        return keys[:n.value], counts[:n.value]
+
+    def merge(self, parts=(), extra=None, max_entries=0):
+        """merged table: partitions of this engine plus optional (keys, counts) arrays; returns distinct k-mers"""
+        self._check(self.lib.nkd_merge_begin(self.h, max_entries))
+        for p in parts:
+            self._check(self.lib.nkd_merge_add_part(self.h, p))
+        if extra is not None:
+            k = np.ascontiguousarray(extra[0], np.uint64)
+            v = np.ascontiguousarray(extra[1], np.int64)
+            self._check(self.lib.nkd_merge_add(self.h, k.ctypes.data, v.ctypes.data, len(k)))
+        n = C.c_uint64(0)
+        self._check(self.lib.nkd_merge_finish(self.h, C.byref(n)))
+        return n.value
 
     def extract_keys(self, buf, descs, n_ops):
         keys = np.empty(n_ops, np.uint64)

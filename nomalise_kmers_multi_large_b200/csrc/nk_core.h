@@ -859,4 +859,70 @@ NK_HD void nk_decide_op(const NkRun &P, unsigned rec, int paired, float coverage
     accept[rec] = (unsigned char)keep;
 }
 
+/* ---------------------------------------------------------------- table dump (C:354-385, C:1128-1136) */
+
+/* where a dump reads its (k-mer, count) entries: a table in slot order (print_kmer_table), or the
+ * merged arrays (all partitions, sorted by k-mer, counts summed: the TODO of C:25-26) */
+struct NkDumpSrc
+{
+    const NkSlot *tab;
+    const unsigned long long *keys;
+    const long long *vals;
+};
+
+NK_HD void nk_dump_entry(const NkDumpSrc &s, unsigned long long i, unsigned long long &key, long long &val)
+{
+    if (s.tab)
+    {
+        NkSlot e = s.tab[i];
+        key = e.key;
+        val = (long long)e.count;
+    }
+    else
+    {
+        key = s.keys[i];
+        val = s.vals[i];
+    }
+}
+
+#define NK_DUMP_MAXLEN 54 /* 31 bases, tab, sign, 19 digits, newline, and one spare */
+
+/* bytes of "KMER\tcount\n" (fprintf "%s\t%d\n", C:378); empty slots print nothing (C:372) */
+NK_HD unsigned nk_dump_len(unsigned long long key, long long val, int k)
+{
+    if (key == 0)
+        return 0;
+    unsigned long long m = val < 0 ? 0ull - (unsigned long long)val : (unsigned long long)val;
+    unsigned d = 1;
+    while (m >= 10)
+    {
+        m /= 10;
+        d++;
+    }
+    return (unsigned)k + 2u + d + (val < 0 ? 1u : 0u);
+}
+
+/* decode_kmer_plain (C:1128-1136): first base in the top bits, A C G T = 0 1 2 3 */
+NK_HD void nk_dump_format(unsigned long long key, long long val, int k, char *out, unsigned len)
+{
+    for (int b = k - 1; b >= 0; b--)
+    {
+        out[b] = (char)((0x54474341u >> ((unsigned)(key & 3) * 8u)) & 0xFFu); /* "ACGT" */
+        key >>= 2;
+    }
+    out[k] = '\t';
+    out[len - 1] = '\n';
+    unsigned long long m = val < 0 ? 0ull - (unsigned long long)val : (unsigned long long)val;
+    unsigned at = len - 2;
+    do
+    {
+        out[at--] = (char)('0' + (unsigned)(m % 10));
+        m /= 10;
+    } while (m);
+    if (val < 0)
+        out[at] = '-';
+}
+
+#define NK_DUMP_TILE 512 /* entries whose text one block assembles in shared memory per pass */
+
 #endif /* NK_CORE_H */

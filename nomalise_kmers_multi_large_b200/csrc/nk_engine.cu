@@ -13,10 +13,18 @@
  *   k_commit / k_untag              store claimed keys / forget an abandoned run
  *   k_rehash_place / k_rehash_fill  exact table growth                  [expand_local_hash_table C:1055]
  *   k_decide   float32 ratio test per record                                          [C:1641-1646]
- * The only library call is cub::DeviceRadixSort for the (rare) time-ordered slow path.
+ *   k_dump_measure / k_dump_text / k_dump_pairs   -P table dump formatted on the device, compaction
+ *                                                 for the merged table        [print_kmer_table C:354]
+ * Library calls: cub::DeviceRadixSort for the (rare) time-ordered slow path; cub scan / sort /
+ * reduce-by-key in the table dump and the merged table (not on the scoring path).
  */
 #include <cuda_runtime.h>
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cuda/std/functional>
 
 #include <cstdio>
 #include <string>
@@ -351,6 +359,120 @@ __global__ void __launch_bounds__(256) k_decide(const NkRun P, unsigned n_record
         nk_decide_op(P, i, paired, coverage, accept);
 }
 
+/* ------------------------------------------------------------------ table dump (C:354-385) */
+
+/* pass 1: text bytes (or stored entries) of every tile of NK_DUMP_TILE consecutive entries */
+__global__ void __launch_bounds__(256) k_dump_measure(const NkDumpSrc src, unsigned long long lo, unsigned long long n,
+                                                      int k, int text, unsigned long long *tile_units)
+{
+    typedef cub::BlockReduce<unsigned, 256> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        unsigned u = 0;
+#pragma unroll
+        for (int j = 0; j < NK_DUMP_TILE / 256; j++)
+        {
+            unsigned long long i = tile * NK_DUMP_TILE + threadIdx.x * (NK_DUMP_TILE / 256) + j;
+            if (i < n)
+            {
+                unsigned long long key;
+                long long val;
+                nk_dump_entry(src, lo + i, key, val);
+                u += text ? nk_dump_len(key, val, k) : (key != 0);
+            }
+        }
+        unsigned sum = Reduce(tmp).Sum(u);
+        if (threadIdx.x == 0)
+            tile_units[tile] = sum;
+        __syncthreads();
+    }
+}
+
+/* pass 2: every thread formats its entries into the block's shared buffer at its scanned offset; the
+ * block then copies the tile's text to its place in the output with coalesced stores */
+__global__ void __launch_bounds__(256) k_dump_text(const NkDumpSrc src, unsigned long long lo, unsigned long long n, int k,
+                                                   const unsigned long long *tile_off, char *text)
+{
+    typedef cub::BlockScan<unsigned, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ char buf[NK_DUMP_TILE * NK_DUMP_MAXLEN];
+    constexpr int PER = NK_DUMP_TILE / 256;
+    unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        unsigned long long key[PER];
+        long long val[PER];
+        unsigned len[PER], mine = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+        {
+            unsigned long long i = tile * NK_DUMP_TILE + threadIdx.x * PER + j;
+            key[j] = 0;
+            val[j] = 0;
+            if (i < n)
+                nk_dump_entry(src, lo + i, key[j], val[j]);
+            len[j] = nk_dump_len(key[j], val[j], k);
+            mine += len[j];
+        }
+        unsigned at;
+        Scan(tmp).ExclusiveSum(mine, at);
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+        {
+            if (len[j])
+                nk_dump_format(key[j], val[j], k, buf + at, len[j]);
+            at += len[j];
+        }
+        __syncthreads();
+        unsigned long long o = tile_off[tile];
+        unsigned total = (unsigned)(tile_off[tile + 1] - o);
+        for (unsigned b = threadIdx.x; b < total; b += 256)
+            text[o + b] = buf[b];
+        __syncthreads();
+    }
+}
+
+/* pass 2 of a compaction: stored (key, count) pairs in slot order */
+__global__ void __launch_bounds__(256) k_dump_pairs(const NkDumpSrc src, unsigned long long lo, unsigned long long n,
+                                                    const unsigned long long *tile_off, unsigned long long *keys_out,
+                                                    long long *vals_out)
+{
+    typedef cub::BlockScan<unsigned, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    constexpr int PER = NK_DUMP_TILE / 256;
+    unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        unsigned long long key[PER];
+        long long val[PER];
+        unsigned mine = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+        {
+            unsigned long long i = tile * NK_DUMP_TILE + threadIdx.x * PER + j;
+            key[j] = 0;
+            val[j] = 0;
+            if (i < n)
+                nk_dump_entry(src, lo + i, key[j], val[j]);
+            mine += key[j] != 0;
+        }
+        unsigned at;
+        Scan(tmp).ExclusiveSum(mine, at);
+        unsigned long long o = tile_off[tile] + at;
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+            if (key[j])
+            {
+                keys_out[o] = key[j];
+                vals_out[o] = val[j];
+                o++;
+            }
+        __syncthreads();
+    }
+}
+
 /* ------------------------------------------------------------------ backend */
 
 struct CudaBackend
@@ -619,6 +741,57 @@ struct CudaBackend
     {
         if (n_records)
             k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept), launches++;
+    }
+
+    /* table dump: tile sizes, their exclusive scan in place (tile[n_tiles] = total), then the writers */
+    bool dump_scan(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, int k, int text,
+                   unsigned long long *d_tile)
+    {
+        unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        zero(d_tile + tiles, sizeof(unsigned long long));
+        k_dump_measure<<<grid_for(tiles, 1), 256, 0, stream>>>(src, lo, n, k, text, d_tile), launches++;
+        size_t bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_tile, d_tile, (long long)(tiles + 1), stream);
+        void *tmp = alloc(bytes);
+        if (!tmp)
+            return false;
+        ok(cub::DeviceScan::ExclusiveSum(tmp, bytes, d_tile, d_tile, (long long)(tiles + 1), stream), "tile scan");
+        launches++;
+        release(tmp);
+        return true;
+    }
+    void dump_text(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, int k,
+                   const unsigned long long *d_tile, char *d_text)
+    {
+        unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        k_dump_text<<<grid_for(tiles, 1), 256, 0, stream>>>(src, lo, n, k, d_tile, d_text), launches++;
+    }
+    void dump_pairs(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, const unsigned long long *d_tile,
+                    unsigned long long *keys_out, long long *vals_out)
+    {
+        unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        k_dump_pairs<<<grid_for(tiles, 1), 256, 0, stream>>>(src, lo, n, d_tile, keys_out, vals_out), launches++;
+    }
+    /* merged table: sort the concatenated (k-mer, count) pairs of all partitions by k-mer and sum the counts
+     * of equal k-mers; *d_n_out receives the number of distinct k-mers */
+    bool merge_pairs(unsigned long long *keys, long long *vals, unsigned long long n, int key_bits,
+                     unsigned long long *keys_tmp, long long *vals_tmp, unsigned long long *d_n_out)
+    {
+        size_t b1 = 0, b2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_tmp, vals, vals_tmp, (long long)n, 0, key_bits, stream);
+        cub::DeviceReduce::ReduceByKey(nullptr, b2, keys_tmp, keys, vals_tmp, vals, d_n_out, cuda::std::plus<>(), (long long)n,
+                                       stream);
+        void *tmp = alloc(b1 > b2 ? b1 : b2);
+        if (!tmp)
+            return false;
+        ok(cub::DeviceRadixSort::SortPairs(tmp, b1, keys, keys_tmp, vals, vals_tmp, (long long)n, 0, key_bits, stream),
+           "merge sort");
+        ok(cub::DeviceReduce::ReduceByKey(tmp, b2, keys_tmp, keys, vals_tmp, vals, d_n_out, cuda::std::plus<>(), (long long)n,
+                                          stream),
+           "merge reduce");
+        launches += 2;
+        release(tmp);
+        return true;
     }
 };
 

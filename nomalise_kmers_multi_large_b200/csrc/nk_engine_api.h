@@ -127,6 +127,46 @@ int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_
         return h->e.fail(NK_EINVAL, "no such partition");
     return nkd_done(h, h->e.export_table(h->e.parts[part], keys, counts, capacity));
 }
+int nkd_dump_text(nkd_engine *h, int part, uint64_t first, uint64_t n, char *text, size_t text_cap, size_t *bytes)
+{
+    h->e.be.enter();
+    size_t b = 0;
+    int rc = nkd_done(h, h->e.dump_text(part, first, n, text, text_cap, &b));
+    if (bytes)
+        *bytes = b;
+    return rc;
+}
+int nkd_compact(nkd_engine *h, int part, uint64_t *keys, int64_t *counts, uint64_t cap_entries, uint64_t *n)
+{
+    h->e.be.enter();
+    uint64_t m = 0;
+    int rc = nkd_done(h, h->e.compact(part, nullptr, nullptr, keys, counts, cap_entries, &m));
+    if (n)
+        *n = m;
+    return rc;
+}
+int nkd_merge_begin(nkd_engine *h, uint64_t max_entries)
+{
+    h->e.be.enter();
+    return nkd_done(h, h->e.merge_begin(max_entries));
+}
+int nkd_merge_add_part(nkd_engine *h, int part)
+{
+    h->e.be.enter();
+    if (part < 0)
+        return h->e.fail(NK_EINVAL, "no such partition");
+    return nkd_done(h, h->e.merge_add_part(part));
+}
+int nkd_merge_add(nkd_engine *h, const uint64_t *keys, const int64_t *counts, uint64_t n)
+{
+    h->e.be.enter();
+    return nkd_done(h, h->e.merge_add(keys, counts, n));
+}
+int nkd_merge_finish(nkd_engine *h, uint64_t *n_unique)
+{
+    h->e.be.enter();
+    return nkd_done(h, h->e.merge_finish(n_unique));
+}
 int nkd_read_scores(nkd_engine *h, uint32_t *high, uint32_t *total, size_t n_reads)
 {
     h->e.be.enter();

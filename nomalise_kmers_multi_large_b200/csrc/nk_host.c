@@ -718,6 +718,11 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         free(c);
         return nk_fail(NULL, NK_EINVAL, "partition slice outside 0..%d", cfg->partitions);
     }
+    if ((cfg->merged_table || cfg->merged_output) && c->n_local != cfg->partitions)
+    {
+        free(c);
+        return nk_fail(NULL, NK_EINVAL, "merged table / merged output need a context that owns all %d partitions", cfg->partitions);
+    }
     c->threads = nk_host_threads();
     int ndev_avail = nkd_device_count();
     if (ndev_avail <= 0)
@@ -1054,8 +1059,12 @@ int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed
     return rc;
 }
 
-static int nk_write_dump(nk_ctx *c, const uint64_t *keys, const int32_t *counts, uint64_t cap, const char *tag, int gid)
-{ /* print_kmer_table, C:354-385: slot order, stored keys only */
+#define NK_DUMP_CHUNK (2u << 20) /* entries formatted per device pass */
+
+/* print_kmer_table (C:354-385): slot order, stored keys only.  The lines are formatted on the GPU
+ * (nkd_dump_text); the host only appends the text to the file. */
+static int nk_write_dump(nk_ctx *c, nkd_engine *e, int part, uint64_t entries, const char *tag, int gid)
+{
     char base[32];
     snprintf(base, sizeof base, "output_kmer%s", tag);
     char *name = nk_out_name(c->cfg.out_dir, base, c->cfg.k, c->depth_part, gid, "tsv");
@@ -1067,27 +1076,123 @@ static int nk_write_dump(nk_ctx *c, const uint64_t *keys, const int32_t *counts,
         return rc;
     }
     free(name);
-    char *wb = malloc(NK_WBUF);
-    setvbuf(o, wb, _IOFBF, NK_WBUF);
-    static const char sym[4] = {'A', 'C', 'G', 'T'};
-    char line[64];
-    int k = c->cfg.k;
-    for (uint64_t i = 0; i < cap; i++)
+    setvbuf(o, NULL, _IONBF, 0);
+    size_t per = (size_t)c->cfg.k + (part == NKD_PART_MERGED ? 22u : 13u);
+    uint64_t chunk = entries < NK_DUMP_CHUNK ? (entries ? entries : 1) : NK_DUMP_CHUNK;
+    char *text = nkd_alloc_pinned(chunk * per);
+    int rc = text ? NK_OK : nk_fail(c, NK_ENOMEM, "Memory allocation failed (table dump)");
+    for (uint64_t at = 0; !rc && at < entries; at += chunk)
     {
-        uint64_t x = keys[i];
-        if (!x)
-            continue;
-        for (int b = k - 1; b >= 0; b--)
-        {
-            line[b] = sym[x & 3];
-            x >>= 2;
-        }
-        int n = k + snprintf(line + k, sizeof line - (size_t)k, "\t%d\n", counts[i]);
-        fwrite(line, 1, (size_t)n, o);
+        uint64_t n = entries - at < chunk ? entries - at : chunk;
+        size_t bytes = 0;
+        rc = nkd_dump_text(e, part, at, n, text, chunk * per, &bytes);
+        if (rc)
+            nk_fail(c, rc, "%s", nkd_last_error(e));
+        else if (bytes && fwrite(text, 1, bytes, o) != bytes)
+            rc = nk_fail(c, NK_EIO, "error writing the k-mer table: %s", strerror(errno));
     }
-    fclose(o);
-    free(wb);
-    return NK_OK;
+    nkd_free_pinned(text);
+    if (fclose(o) != 0 && !rc)
+        rc = nk_fail(c, NK_EIO, "error closing the k-mer table: %s", strerror(errno));
+    return rc;
+}
+
+/* all partitions' stored k-mers once, ascending, counts summed (the TODO of C:25-26):
+ * output_kmer_merged.k{K}_norm{D}.tsv.  Partitions on the first GPU are compacted in place, the
+ * others on their own GPU and handed over through the host. */
+static int nk_write_merged_table(nk_ctx *c)
+{
+    uint64_t total = 0;
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nkd_part_stats st;
+        nkd_part_stats_get(c->dev[c->part[i].dev].eng, c->part[i].lidx, &st);
+        total += st.used;
+    }
+    nkd_engine *e0 = c->dev[0].eng;
+    int rc = nkd_merge_begin(e0, total);
+    if (rc)
+        return nk_fail(c, rc, "%s", nkd_last_error(e0));
+    for (int i = 0; i < c->n_local && !rc; i++)
+    {
+        nk_part *p = &c->part[i];
+        if (p->dev == 0)
+        {
+            if ((rc = nkd_merge_add_part(e0, p->lidx)) != 0)
+                nk_fail(c, rc, "%s", nkd_last_error(e0));
+            continue;
+        }
+        nkd_engine *e = c->dev[p->dev].eng;
+        nkd_part_stats st;
+        nkd_part_stats_get(e, p->lidx, &st);
+        uint64_t n = 0, cap = st.used ? st.used : 1;
+        uint64_t *keys = nkd_alloc_pinned(cap * sizeof *keys);
+        int64_t *vals = nkd_alloc_pinned(cap * sizeof *vals);
+        if (!keys || !vals)
+            rc = nk_fail(c, NK_ENOMEM, "Memory allocation failed (merged table)");
+        else if ((rc = nkd_compact(e, p->lidx, keys, vals, cap, &n)) != 0)
+            nk_fail(c, rc, "%s", nkd_last_error(e));
+        else if ((rc = nkd_merge_add(e0, keys, vals, n)) != 0)
+            nk_fail(c, rc, "%s", nkd_last_error(e0));
+        nkd_free_pinned(keys);
+        nkd_free_pinned(vals);
+    }
+    uint64_t distinct = 0;
+    if (!rc && (rc = nkd_merge_finish(e0, &distinct)) != 0)
+        nk_fail(c, rc, "%s", nkd_last_error(e0));
+    if (!rc)
+        rc = nk_write_dump(c, e0, NKD_PART_MERGED, distinct, "_merged", -1);
+    nkd_merge_begin(e0, 0); /* drop the merge buffers */
+    return rc;
+}
+
+/* one Trinity-ready file per mate: the partitions' outputs in partition order (the reference leaves the
+ * concatenation to the user): output_forward.k{K}_norm{D}.fastq / output_reverse.... */
+static int nk_concat_outputs(nk_ctx *c, const char *base)
+{
+    char *name = nk_out_name(c->cfg.out_dir, base, c->cfg.k, c->depth_part, -1, "fastq");
+    int out = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (out < 0)
+    {
+        int rc = nk_fail(c, NK_EIO, "Error opening file to write: %s", name);
+        free(name);
+        return rc;
+    }
+    free(name);
+    int rc = NK_OK;
+    char *buf = malloc(NK_WBUF);
+    for (int i = 0; i < c->n_local && !rc; i++)
+    {
+        char *pn = nk_out_name(c->cfg.out_dir, base, c->cfg.k, c->depth_part, c->part[i].gid, "fastq");
+        int in = open(pn, O_RDONLY);
+        if (in < 0)
+            rc = nk_fail(c, NK_EIO, "cannot reopen %s", pn);
+        for (ssize_t got = 0; !rc && (got = read(in, buf, NK_WBUF)) != 0;)
+        {
+            if (got < 0)
+            {
+                if (errno == EINTR)
+                    continue;
+                rc = nk_fail(c, NK_EIO, "error reading %s: %s", pn, strerror(errno));
+                break;
+            }
+            for (ssize_t done = 0; done < got && !rc;)
+            {
+                ssize_t w = write(out, buf + done, (size_t)(got - done));
+                if (w < 0 && errno != EINTR)
+                    rc = nk_fail(c, NK_EIO, "error writing the merged output: %s", strerror(errno));
+                else if (w > 0)
+                    done += w;
+            }
+        }
+        if (in >= 0)
+            close(in);
+        free(pn);
+    }
+    free(buf);
+    if (close(out) != 0 && !rc)
+        rc = nk_fail(c, NK_EIO, "error closing the merged output: %s", strerror(errno));
+    return rc;
 }
 
 static void nk_seed_finish_task(int d, void *a)
@@ -1105,17 +1210,7 @@ int nk_seed_finish(nk_ctx *c)
     { /* C:2251-2252 */
         nkd_part_stats st;
         nkd_seed_stats(c->dev[0].eng, &st);
-        uint64_t *keys = malloc(st.capacity * sizeof *keys);
-        int32_t *counts = malloc(st.capacity * sizeof *counts);
-        if (!keys || !counts)
-            return nk_fail(c, NK_ENOMEM, "Memory allocation failed (seed dump)");
-        int rc = nkd_seed_export(c->dev[0].eng, keys, counts, st.capacity);
-        if (!rc)
-            rc = nk_write_dump(c, keys, counts, st.capacity, "_seeds", -1);
-        else
-            nk_fail(c, rc, "%s", nkd_last_error(c->dev[0].eng));
-        free(keys);
-        free(counts);
+        int rc = nk_write_dump(c, c->dev[0].eng, NKD_PART_SEED, st.capacity, "_seeds", -1);
         if (rc)
             return rc;
     }
@@ -1883,17 +1978,16 @@ int nk_finish(nk_ctx *c)
             nkd_part_stats st;
             nkd_engine *e = c->dev[p->dev].eng;
             nkd_part_stats_get(e, p->lidx, &st);
-            uint64_t *keys = malloc(st.capacity * sizeof *keys);
-            int32_t *counts = malloc(st.capacity * sizeof *counts);
-            if (!keys || !counts)
-                rc = nk_fail(c, NK_ENOMEM, "Memory allocation failed (table dump)");
-            else if ((rc = nkd_export(e, p->lidx, keys, counts, st.capacity)) != 0)
-                nk_fail(c, rc, "%s", nkd_last_error(e));
-            else
-                rc = nk_write_dump(c, keys, counts, st.capacity, "", p->gid);
-            free(keys);
-            free(counts);
+            rc = nk_write_dump(c, e, p->lidx, st.capacity, "", p->gid);
         }
+    }
+    if (c->seeded && !rc && c->cfg.merged_table)
+        rc = nk_write_merged_table(c);
+    if (c->seeded && !rc && c->cfg.merged_output)
+    {
+        rc = nk_concat_outputs(c, "output_forward");
+        if (!rc && c->cfg.have_reverse)
+            rc = nk_concat_outputs(c, "output_reverse");
     }
     return rc;
 }
@@ -1927,7 +2021,9 @@ static void nk_usage(void)
             "\t\t[--memory_start|-m (integer Gb)]\tinitial table memory across all partitions\n"
             "\t\t[--cpu|-p (int; def 1)]\t\t\tnumber of partitions (the reference's threads); fixed by the user, spread over the GPUs\n"
             "\t\t[--verbose|-e] [--debug|-b level] [--print|-P] [--version|-v] [--help|-h]\n"
-            "\t\tB200 placement: --gpus N (or NKB200_GPUS) uses N GPUs of this node; results do not depend on N\n\n");
+            "\t\tB200 placement: --gpus N (or NKB200_GPUS) uses N GPUs of this node; results do not depend on N\n"
+            "\t\tB200 extras:    --merged-table\talso write output_kmer_merged.*.tsv: all threads' kmers, sorted, counts summed\n"
+            "\t\t                --merged-output\talso write output_forward/output_reverse.*.fastq without _thread: all threads concatenated\n\n");
 }
 
 static int nk_is_fa(const char *s) { return !strcasecmp(s, "fa") || !strcasecmp(s, "fasta") || !strcasecmp(s, "fsa") || !strcasecmp(s, "fas"); }
@@ -1965,7 +2061,8 @@ static int nk_parse(nk_cli *a, int argc, char **argv, int *gpus)
                                  {"coverage", 1, 0, 'g'}, {"filetype", 1, 0, 't'}, {"outformat", 1, 0, 'o'}, {"cpu", 1, 0, 'p'},
                                  {"memory_start", 1, 0, 'm'}, {"debug", 1, 0, 'b'}, {"verbose", 0, 0, 'e'}, {"help", 0, 0, 'h'},
                                  {"canonical", 0, 0, 'c'}, {"version", 0, 0, 'v'}, {"single", 0, 0, 's'}, {"print", 0, 0, 'P'},
-                                 {"gpus", 1, 0, 1000}, {0, 0, 0, 0}};
+                                 {"gpus", 1, 0, 1000}, {"merged-table", 0, 0, 1001}, {"merged-output", 0, 0, 1002},
+                                 {0, 0, 0, 0}};
     int o;
     optind = 1;
     while ((o = getopt_long(argc, argv, "f:r:k:d:g:t:o:p:m:b:ehcvsP", lo, NULL)) != -1)
@@ -1974,6 +2071,12 @@ static int nk_parse(nk_cli *a, int argc, char **argv, int *gpus)
         {
         case 1000:
             *gpus = atoi(optarg);
+            break;
+        case 1001:
+            c->merged_table = 1;
+            break;
+        case 1002:
+            c->merged_output = 1;
             break;
         case 'P':
             c->dump_tables = 1;

@@ -92,6 +92,12 @@ class NkEngine
     bool staged = false, ran = false;
     float last_total_ms = 0, last_probe_ms = 0;
 
+    /* merged table (all partitions, sorted by k-mer, counts summed) */
+    unsigned long long *d_mkeys[2] = {nullptr, nullptr};
+    long long *d_mvals[2] = {nullptr, nullptr};
+    uint64_t merge_cap = 0, merge_n = 0, merged_n = 0;
+    bool merged_ready = false;
+
     bool debug = getenv("NKB200_DEBUG") != nullptr;
 
     int fail(int code, const std::string &m)
@@ -177,6 +183,7 @@ class NkEngine
         be.release(d_ctr);
         be.release(d_parts);
         be.release(d_bloom);
+        merge_release();
         be.shutdown();
     }
 
@@ -749,6 +756,212 @@ class NkEngine
                 counts[o + i] = buf[i].count;
             }
         }
+        return NK_OK;
+    }
+
+    /* ------------------------------------------------------------ table dump and merged table */
+
+    void merge_release()
+    {
+        for (int i = 0; i < 2; i++)
+        {
+            be.release(d_mkeys[i]);
+            be.release(d_mvals[i]);
+            d_mkeys[i] = nullptr;
+            d_mvals[i] = nullptr;
+        }
+        merge_cap = merge_n = merged_n = 0;
+        merged_ready = false;
+    }
+
+    /* entries of a dump source: NKD_PART_SEED, NKD_PART_MERGED or a partition index */
+    int dump_source(int part, NkDumpSrc &src, uint64_t &limit)
+    {
+        src = NkDumpSrc{nullptr, nullptr, nullptr};
+        if (part == NKD_PART_MERGED)
+        {
+            if (!merged_ready)
+                return fail(NK_EINVAL, "no merged table: call nkd_merge_finish first");
+            src.keys = d_mkeys[0];
+            src.vals = d_mvals[0];
+            limit = merged_n;
+            return NK_OK;
+        }
+        const NkTable *t = part == NKD_PART_SEED ? &seed : (part >= 0 && part < (int)parts.size() ? &parts[part] : nullptr);
+        if (!t)
+            return fail(NK_EINVAL, "no such partition");
+        if (!t->tab)
+            return fail(NK_EINVAL, "table not resident");
+        src.tab = t->tab;
+        limit = t->cap;
+        return NK_OK;
+    }
+
+    /* print_kmer_table's lines (C:368-380) for entries [lo, lo+n) of a source, formatted on the device */
+    int dump_text(int part, uint64_t lo, uint64_t n, char *text, size_t text_cap, size_t *bytes)
+    {
+        NkDumpSrc src;
+        uint64_t limit = 0;
+        int rc = dump_source(part, src, limit);
+        if (rc)
+            return rc;
+        if (lo > limit || n > limit - lo)
+            return fail(NK_EINVAL, "nkd_dump_text: range beyond the table");
+        *bytes = 0;
+        if (n == 0)
+            return NK_OK;
+        uint64_t tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        unsigned long long *d_tile = (unsigned long long *)be.alloc((tiles + 1) * sizeof(unsigned long long));
+        if (!d_tile || !be.dump_scan(src, lo, n, cfg.k, 1, d_tile))
+        {
+            be.release(d_tile);
+            return fail(NK_ENOMEM, "nkd_dump_text: allocation failed");
+        }
+        unsigned long long total = 0;
+        be.d2h(&total, d_tile + tiles, sizeof total);
+        be.sync();
+        if (total > text_cap)
+        {
+            be.release(d_tile);
+            return fail(NK_EINVAL, "nkd_dump_text: text buffer too small");
+        }
+        if (total)
+        {
+            char *d_text = (char *)be.alloc(total);
+            if (!d_text)
+            {
+                be.release(d_tile);
+                return fail(NK_ENOMEM, "nkd_dump_text: allocation failed");
+            }
+            be.dump_text(src, lo, n, cfg.k, d_tile, d_text);
+            be.d2h(text, d_text, total);
+            be.sync();
+            be.release(d_text);
+            d2h_bytes += total;
+        }
+        be.release(d_tile);
+        *bytes = (size_t)total;
+        return NK_OK;
+    }
+
+    /* stored (k-mer, count) pairs of a table in slot order, packed on the device; dst on the device
+     * (d_keys/d_vals) or on the host (keys/vals) */
+    int compact(int part, unsigned long long *d_keys, long long *d_vals, uint64_t *keys, int64_t *vals, uint64_t cap_entries,
+                uint64_t *n_out)
+    {
+        NkDumpSrc src;
+        uint64_t limit = 0;
+        int rc = dump_source(part, src, limit);
+        if (rc)
+            return rc;
+        uint64_t tiles = (limit + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        unsigned long long *d_tile = (unsigned long long *)be.alloc((tiles + 1) * sizeof(unsigned long long));
+        if (!d_tile || !be.dump_scan(src, 0, limit, cfg.k, 0, d_tile))
+        {
+            be.release(d_tile);
+            return fail(NK_ENOMEM, "nkd_compact: allocation failed");
+        }
+        unsigned long long total = 0;
+        be.d2h(&total, d_tile + tiles, sizeof total);
+        be.sync();
+        *n_out = total;
+        if (total > cap_entries)
+        {
+            be.release(d_tile);
+            return fail(NK_EINVAL, "nkd_compact: more stored k-mers than the destination holds");
+        }
+        bool to_host = d_keys == nullptr;
+        if (to_host && total)
+        {
+            d_keys = (unsigned long long *)be.alloc(total * sizeof(unsigned long long));
+            d_vals = (long long *)be.alloc(total * sizeof(long long));
+            if (!d_keys || !d_vals)
+            {
+                be.release(d_keys);
+                be.release(d_vals);
+                be.release(d_tile);
+                return fail(NK_ENOMEM, "nkd_compact: allocation failed");
+            }
+        }
+        if (total)
+            be.dump_pairs(src, 0, limit, d_tile, d_keys, d_vals);
+        if (to_host && total)
+        {
+            be.d2h(keys, d_keys, total * sizeof(unsigned long long));
+            be.d2h(vals, d_vals, total * sizeof(long long));
+            be.sync();
+            be.release(d_keys);
+            be.release(d_vals);
+            d2h_bytes += total * 16;
+        }
+        be.release(d_tile);
+        return NK_OK;
+    }
+
+    int merge_begin(uint64_t max_entries)
+    {
+        merge_release();
+        if (max_entries >= (1ull << 31))
+            return fail(NK_EINVAL, "nkd_merge_begin: more than 2^31 entries");
+        merge_cap = std::max<uint64_t>(max_entries, 1);
+        bool ok = true;
+        for (int i = 0; i < 2; i++)
+        {
+            ok &= dalloc(d_mkeys[i], merge_cap);
+            ok &= dalloc(d_mvals[i], merge_cap);
+        }
+        if (!ok)
+        {
+            merge_release();
+            return fail(NK_ENOMEM, "nkd_merge_begin: allocation failed");
+        }
+        return NK_OK;
+    }
+    int merge_add_part(int part)
+    {
+        if (!merge_cap)
+            return fail(NK_EINVAL, "nkd_merge_add_part before nkd_merge_begin");
+        uint64_t n = 0;
+        int rc = compact(part, d_mkeys[0] + merge_n, d_mvals[0] + merge_n, nullptr, nullptr, merge_cap - merge_n, &n);
+        if (!rc)
+            merge_n += n;
+        return rc;
+    }
+    int merge_add(const uint64_t *keys, const int64_t *vals, uint64_t n)
+    {
+        if (!merge_cap)
+            return fail(NK_EINVAL, "nkd_merge_add before nkd_merge_begin");
+        if (n > merge_cap - merge_n)
+            return fail(NK_EINVAL, "nkd_merge_add: more entries than nkd_merge_begin announced");
+        be.h2d(d_mkeys[0] + merge_n, keys, n * sizeof(uint64_t));
+        be.h2d(d_mvals[0] + merge_n, vals, n * sizeof(int64_t));
+        be.sync();
+        h2d_bytes += n * 16;
+        merge_n += n;
+        return NK_OK;
+    }
+    int merge_finish(uint64_t *n_unique)
+    {
+        if (!merge_cap)
+            return fail(NK_EINVAL, "nkd_merge_finish before nkd_merge_begin");
+        merged_n = 0;
+        if (merge_n)
+        {
+            unsigned long long *d_n = (unsigned long long *)be.alloc(sizeof(unsigned long long));
+            if (!d_n || !be.merge_pairs(d_mkeys[0], d_mvals[0], merge_n, 2 * cfg.k, d_mkeys[1], d_mvals[1], d_n))
+            {
+                be.release(d_n);
+                return fail(NK_ENOMEM, "nkd_merge_finish: allocation failed");
+            }
+            unsigned long long nu = 0;
+            be.d2h(&nu, d_n, sizeof nu);
+            be.sync();
+            be.release(d_n);
+            merged_n = nu;
+        }
+        merged_ready = true;
+        if (n_unique)
+            *n_unique = merged_n;
         return NK_OK;
     }
 

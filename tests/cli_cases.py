@@ -106,3 +106,35 @@ def standard_cases(tmp: Path, n_pairs: int):
         ("p64_canonical_config3_shape", ["-f", f, "-r", r, "-k", 25, "-c", "-p", 64, "-d", 256, "-m", 1]),   # configs[2] flags
         ("depth_coverage_sweep_point", ["-f", f2, "-r", r2, "-k", 15, "-p", 4, "-d", 400, "-g", 0.96, "-m", 1, "-P"]),
     ]
+
+
+def check_merged_extras(binary, oracle_cli, args, tmp: Path, env=None):
+    """--merged-table / --merged-output (the reference leaves both to the user):
+    the per-partition files stay byte-identical to the oracle's, the merged k-mer table is every dumped
+    k-mer once, ascending, counts summed over the partitions, and the merged read files are the
+    partitions' files concatenated in partition order."""
+    want = run_cli(oracle_cli, list(args) + ["-P"], tmp / "oracle")
+    got = run_cli(binary, list(args) + ["-P", "--merged-table", "--merged-output"], tmp / "got", env=env)
+    assert got["rc"] == 0, got["stderr"][-500:]
+    extra = sorted(set(got["files"]) - set(want["files"]))
+    per_part = {n: h for n, h in got["files"].items() if n not in extra}
+    assert per_part == want["files"], "per-partition files changed"
+    out = tmp / "got"
+    threads = lambda base: sorted(out.glob(base + ".*_thread*"), key=lambda f: int(re.search(r"_thread(\d+)", f.name).group(1)))
+    sums = {}
+    for f in threads("output_kmer"):
+        for line in f.read_text().splitlines():
+            kmer, count = line.split("\t")
+            sums[kmer] = sums.get(kmer, 0) + int(count)
+    merged = [f for f in extra if f.startswith("output_kmer_merged.")]
+    assert len(merged) == 1, extra
+    text = (out / merged[0]).read_text()
+    assert text == "".join("%s\t%d\n" % kv for kv in sorted(sums.items())), "merged table differs"
+    for base in ("output_forward", "output_reverse"):
+        parts = threads(base)
+        if not parts:
+            continue
+        name = parts[0].name.replace("_thread0.", ".")
+        assert name in extra, (name, extra)
+        assert (out / name).read_bytes() == b"".join(f.read_bytes() for f in parts), base
+    return len(sums)

@@ -192,6 +192,90 @@ struct EmuBackend
         for (unsigned r : order(n_records))
             nk_decide_op(P, r, paired, coverage, accept);
     }
+    /* table dump and merged table: the same tile sizes / offsets / per-entry formatter as the kernels */
+    bool dump_scan(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, int k, int text,
+                   unsigned long long *tile)
+    {
+        unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE, run = 0;
+        for (unsigned long long t = 0; t < tiles; t++)
+        {
+            unsigned long long u = 0;
+            for (unsigned long long i = t * NK_DUMP_TILE; i < std::min<unsigned long long>(n, (t + 1) * NK_DUMP_TILE); i++)
+            {
+                unsigned long long key;
+                long long val;
+                nk_dump_entry(src, lo + i, key, val);
+                u += text ? nk_dump_len(key, val, k) : (key != 0);
+            }
+            tile[t] = run;
+            run += u;
+        }
+        tile[tiles] = run;
+        return true;
+    }
+    void dump_text(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, int k, const unsigned long long *tile,
+                   char *text)
+    {
+        unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        for (unsigned t : order((size_t)tiles))
+        {
+            unsigned long long at = tile[t];
+            for (unsigned long long i = (unsigned long long)t * NK_DUMP_TILE;
+                 i < std::min<unsigned long long>(n, ((unsigned long long)t + 1) * NK_DUMP_TILE); i++)
+            {
+                unsigned long long key;
+                long long val;
+                nk_dump_entry(src, lo + i, key, val);
+                unsigned len = nk_dump_len(key, val, k);
+                if (len)
+                    nk_dump_format(key, val, k, text + at, len);
+                at += len;
+            }
+        }
+    }
+    void dump_pairs(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, const unsigned long long *tile,
+                    unsigned long long *keys_out, long long *vals_out)
+    {
+        unsigned long long tiles = (n + NK_DUMP_TILE - 1) / NK_DUMP_TILE;
+        for (unsigned t : order((size_t)tiles))
+        {
+            unsigned long long at = tile[t];
+            for (unsigned long long i = (unsigned long long)t * NK_DUMP_TILE;
+                 i < std::min<unsigned long long>(n, ((unsigned long long)t + 1) * NK_DUMP_TILE); i++)
+            {
+                unsigned long long key;
+                long long val;
+                nk_dump_entry(src, lo + i, key, val);
+                if (key)
+                {
+                    keys_out[at] = key;
+                    vals_out[at++] = val;
+                }
+            }
+        }
+    }
+    bool merge_pairs(unsigned long long *keys, long long *vals, unsigned long long n, int, unsigned long long *,
+                     long long *, unsigned long long *n_out)
+    {
+        std::vector<unsigned> idx = order((size_t)n);
+        std::sort(idx.begin(), idx.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+        std::vector<unsigned long long> k2;
+        std::vector<long long> v2;
+        for (unsigned i : idx)
+        {
+            if (!k2.empty() && k2.back() == keys[i])
+                v2.back() += vals[i];
+            else
+            {
+                k2.push_back(keys[i]);
+                v2.push_back(vals[i]);
+            }
+        }
+        std::copy(k2.begin(), k2.end(), keys);
+        std::copy(v2.begin(), v2.end(), vals);
+        *n_out = k2.size();
+        return true;
+    }
 };
 
 #define NK_BACKEND EmuBackend
@@ -199,4 +283,9 @@ struct EmuBackend
 
 extern "C" void *nkd_alloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 16); }
 extern "C" void nkd_free_pinned(void *p) { free(p); }
-extern "C" int nkd_device_count(void) { return 1; }
+/* NK_EMU_DEVICES=n lets the CPU tests drive the host pipeline's multi-GPU placement (one emulated engine per "GPU") */
+extern "C" int nkd_device_count(void)
+{
+    const char *s = getenv("NK_EMU_DEVICES");
+    return s && atoi(s) > 0 ? atoi(s) : 1;
+}

@@ -33,6 +33,43 @@ def revcomp(s: bytes) -> bytes:
     return s.translate(bytes.maketrans(b"ACGTN", b"TGCAN"))[::-1]
 
 
+def table_text(keys, counts, k):
+    """print_kmer_table's output for a slot-ordered table (C:354-385)"""
+    out = []
+    for key, c in zip(keys.tolist(), counts.tolist()):
+        if key:
+            out.append("".join("ACGT"[(key >> (2 * (k - 1 - i))) & 3] for i in range(k)) + "\t%d\n" % c)
+    return "".join(out).encode()
+
+
+def check_dumps(eng, otabs, k):
+    """device-formatted -P dump, compaction and the merged table against the oracle's tables"""
+    sums = {}
+    for p, ot in enumerate(otabs):
+        okk, okc = ot.export()
+        want = table_text(okk, okc, k)
+        assert eng.dump_text(p, 0, ot.cap) == want, f"dump text differs, part {p}"
+        cut = (ot.cap // 3) | 1  # ranges need not be tile-aligned
+        assert eng.dump_text(p, 0, cut) + eng.dump_text(p, cut, ot.cap - cut) == want, f"ranged dump differs, part {p}"
+        ck, cc_ = eng.compact(p, ot.used)
+        nz = okk != 0
+        assert np.array_equal(ck, okk[nz]) and np.array_equal(cc_, okc[nz].astype(np.int64)), f"compaction differs, part {p}"
+        for key, c in zip(okk[nz].tolist(), okc[nz].tolist()):
+            sums[key] = sums.get(key, 0) + c
+    # merged table: all partitions, plus partition 0 once more through the host path, with large counts
+    k0, c0 = otabs[0].export()
+    nz = k0 != 0
+    big = c0[nz].astype(np.int64) + (1 << 33)
+    for key, c in zip(k0[nz].tolist(), big.tolist()):
+        sums[key] += c
+    total = sum(ot.used for ot in otabs) + int(nz.sum())
+    n = eng.merge(range(len(otabs)), extra=(k0[nz], big), max_entries=total)
+    assert n == len(sums)
+    ks = np.array(sorted(sums), np.uint64)
+    want = table_text(ks, np.array([sums[x] for x in ks.tolist()], np.int64), k)
+    assert eng.dump_text(capi.PART_MERGED, 0, n) == want, "merged table differs"
+
+
 def run_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_parts=2, cap0=4099, genome_len=3000,
              n_seed_reads=200, steps=4, records_per_step=150, paired=True, read_len=(40, 120), err=0.01,
              max_step_ops=None):
@@ -62,6 +99,7 @@ def run_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_par
         okk, okc = otab.export()
         assert np.array_equal(ek, okk), "seed keys differ"
         assert np.array_equal(ec, okc), "seed counts differ"
+        assert eng.dump_text(capi.PART_SEED, 0, otab.cap) == table_text(okk, okc, k), "seed dump text differs"
         eng.seed_finish()
         otabs = [otab.clone() for _ in range(n_parts)]
         # ---- steps
@@ -106,6 +144,7 @@ def run_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_par
                 assert np.array_equal(ek, okk), f"keys differ step {step} part {p}"
                 bad = np.flatnonzero(ec != okc)
                 assert bad.size == 0, f"counts differ step {step} part {p}: slots {bad[:8]} got {ec[bad[:8]]} want {okc[bad[:8]]}"
+        check_dumps(eng, otabs, k)
         for p in range(n_parts):
             st = eng.part_stats(p)
             info["slow_events"] += st["slow_events"]

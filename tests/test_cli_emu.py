@@ -34,6 +34,28 @@ def test_cli_matches_oracle(cases, name):
     cc.assert_same(got, want, name)
 
 
+@pytest.mark.parametrize("name", ["canonical_p8", "single_end", "p64_canonical_config3_shape"])
+def test_cli_merged_table_and_output(cases, name):
+    tmp, table = cases
+    args = [a for a in table[name] if a != "-P"]
+    n = cc.check_merged_extras(EMU_CLI, ol.ORACLE_CLI, args, tmp / ("merged_" + name), env={"NKB200_STEP_PAIRS": "64"})
+    assert n > 1000
+
+
+def test_cli_multi_device_placement(cases):
+    """partition t on GPU t mod G (SURVEY 8.B row e): same bytes for any G, including the merged extras whose
+    k-mers cross from the other GPUs through nkd_compact / nkd_merge_add"""
+    tmp, table = cases
+    args = table["canonical_p8"]
+    env = {"NKB200_STEP_PAIRS": "64", "NK_EMU_DEVICES": "3", "NKB200_GPUS": "3"}
+    want = cc.run_cli(ol.ORACLE_CLI, args, tmp / "multidev" / "oracle")
+    got = cc.run_cli(EMU_CLI, args, tmp / "multidev" / "emu", env=env)
+    verbose = cc.run_cli(EMU_CLI, args + ["-e"], tmp / "multidev" / "emu_verbose", env=env)
+    assert "on 3 GPU(s)" in verbose["stdout"], verbose["stdout"][-400:]
+    cc.assert_same(got, want, "3 emulated devices")
+    cc.check_merged_extras(EMU_CLI, ol.ORACLE_CLI, args, tmp / "multidev_merged", env=env)
+
+
 @pytest.mark.parametrize("argv,needle", [
     (["-k", "32"], "Only kmer sizes (32) of 5 to 31 are supported"),
     (["-d", "100", "-p", "64"], "must be at least 2 x number of CPUs"),

@@ -55,6 +55,14 @@ def test_cli_matches_reference_binary(cases, name, ref):
     cc.assert_same(got, want, name)
 
 
+@pytest.mark.parametrize("name", ["canonical_p8", "p64_canonical_config3_shape"])
+def test_cli_merged_table_and_output(cases, name):
+    """device-side dump formatting, compaction, sort + reduce for the merged table"""
+    tmp, table = cases
+    n = cc.check_merged_extras(capi.CLI_PATH, ol.ORACLE_CLI, table[name], tmp / ("merged_" + name))
+    assert n > 1000
+
+
 def test_cli_fatal_on_non_dna(cases):
     tmp, table = cases
     f, r = Path(table["canonical_p8"][1]), Path(table["canonical_p8"][3])
@@ -76,3 +84,4 @@ def test_results_do_not_depend_on_gpu_count(cases):
     one = cc.run_cli(capi.CLI_PATH, args, tmp / "g1", env={"NKB200_GPUS": "1"})
     two = cc.run_cli(capi.CLI_PATH, args, tmp / "g2", env={"NKB200_GPUS": "2"})
     cc.assert_same(two, one, "2 GPUs vs 1")
+    cc.check_merged_extras(capi.CLI_PATH, ol.ORACLE_CLI, args, tmp / "g2_merged", env={"NKB200_GPUS": "2"})
