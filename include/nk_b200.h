@@ -100,6 +100,9 @@ int nkd_seed_step(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd
                   int64_t *first_invalid);
 /* copy_hash_table for every resident partition (C:908-927, C:2279); frees the seed table */
 int nkd_seed_finish(nkd_engine *e);
+/* the same for an engine that shares its GPU with `src`: its partitions are copied from src's seed table, so
+ * a GPU driven by several engines (one stream each) is seeded once.  Call before nkd_seed_finish(src). */
+int nkd_seed_finish_from(nkd_engine *e, nkd_engine *src);
 int nkd_seed_stats(nkd_engine *e, nkd_part_stats *out);
 /* print_kmer_table's data source for the "_seeds" dump (C:2251-2252): slot-ordered table copy */
 int nkd_seed_export(nkd_engine *e, uint64_t *keys, int32_t *counts, uint64_t capacity);
@@ -149,6 +152,10 @@ typedef struct
 } nkd_run_stats;
 int nkd_run_stats_get(nkd_engine *e, nkd_run_stats *out);
 
+/* (start, end) of every scoring step in ms on the GPU's clock since a process-wide per-GPU epoch: engines that
+ * share one GPU (several streams) overlap, so that GPU's busy time is the union of their spans.  spans holds
+ * 2 floats per step; *n_spans = steps recorded so far. */
+int nkd_run_spans(nkd_engine *e, float *spans, size_t cap_spans, size_t *n_spans);
 int nkd_part_stats_get(nkd_engine *e, int part, nkd_part_stats *out);
 /* print_kmer_table's data source (C:354-385): slot-ordered copy of partition's table */
 int nkd_export(nkd_engine *e, int part, uint64_t *keys, int32_t *counts, uint64_t capacity);

@@ -94,7 +94,7 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_seed_export", "nkd_stage", "nkd_run", "nkd_fetch", "nkd_last_run_ms", "nkd_part_stats_get",
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
-                  "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish"]
+                  "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from"]
 PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
@@ -122,6 +122,8 @@ def _declare_engine(lib):
     lib.nkd_extract_keys.argtypes = [vp, u8p, sz, vp, sz, vp, sz, u8p]
     lib.nkd_run_stats_get.argtypes = [vp, C.POINTER(RunStats)]
     lib.nkd_read_scores.argtypes = [vp, vp, vp, sz]
+    lib.nkd_seed_finish_from.argtypes = [vp, vp]
+    lib.nkd_run_spans.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.nkd_dump_text.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp, sz, C.POINTER(sz)]
     lib.nkd_compact.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.nkd_merge_begin.argtypes = [vp, C.c_uint64]

@@ -27,6 +27,7 @@
 #include <cuda/std/functional>
 
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -532,6 +533,7 @@ struct CudaBackend
             return NK_ENODEVICE;
         }
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        epoch(dev);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
         {
@@ -659,6 +661,44 @@ struct CudaBackend
         t.used += 2;
     }
     void reset_timer(int i) { timers[i].used = 0; }
+    /* (start, end) of timer i's recorded pairs in ms since this GPU's process-wide epoch event: engines that
+     * share a GPU overlap, and their busy time is the union of these spans, not the sum */
+    void timer_spans(int i, std::vector<float> &out)
+    {
+        cudaEvent_t e0 = epoch(dev);
+        Timer &t = timers[i];
+        for (size_t j = 0; j + 1 < t.used; j += 2)
+        {
+            float a = 0, b = 0;
+            if (e0 && cudaEventElapsedTime(&a, e0, t.ev[j]) == cudaSuccess &&
+                cudaEventElapsedTime(&b, e0, t.ev[j + 1]) == cudaSuccess)
+            {
+                out.push_back(a);
+                out.push_back(b);
+            }
+            else
+                cudaGetLastError();
+        }
+    }
+    static cudaEvent_t epoch(int device)
+    {
+        static std::mutex mu;
+        static cudaEvent_t ev[64];
+        if (device < 0 || device >= 64)
+            return nullptr;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!ev[device])
+        {
+            cudaSetDevice(device);
+            if (cudaEventCreate(&ev[device]) != cudaSuccess || cudaEventRecord(ev[device], 0) != cudaSuccess ||
+                cudaEventSynchronize(ev[device]) != cudaSuccess)
+            {
+                cudaGetLastError();
+                ev[device] = nullptr;
+            }
+        }
+        return ev[device];
+    }
     float timer_ms(int i)
     {
         Timer &t = timers[i];

@@ -69,6 +69,13 @@ int nkd_stage_segments(nkd_engine *h, const uint8_t *seq_base, const nkd_segment
 }
 int nkd_seed_finish(nkd_engine *h) {
     h->e.be.enter(); return nkd_done(h, h->e.seed_finish()); }
+int nkd_seed_finish_from(nkd_engine *h, nkd_engine *src)
+{
+    h->e.be.enter();
+    if (!src || src == h)
+        return h->e.fail(NK_EINVAL, "nkd_seed_finish_from: bad source engine");
+    return nkd_done(h, h->e.seed_finish_from(src->e));
+}
 int nkd_seed_stats(nkd_engine *h, nkd_part_stats *out)
 {
     *out = h->e.seed.st;
@@ -109,6 +116,15 @@ int nkd_run_stats_get(nkd_engine *h, nkd_run_stats *out)
     out->launches = h->e.be.launches;
     out->h2d_bytes = h->e.h2d_bytes;
     out->d2h_bytes = h->e.d2h_bytes;
+    return NK_OK;
+}
+int nkd_run_spans(nkd_engine *h, float *spans, size_t cap_spans, size_t *n_spans)
+{
+    size_t n = h->e.spans.size() / 2;
+    if (n_spans)
+        *n_spans = n;
+    if (spans)
+        memcpy(spans, h->e.spans.data(), sizeof(float) * 2 * (n < cap_spans ? n : cap_spans));
     return NK_OK;
 }
 int nkd_part_stats_get(nkd_engine *h, int part, nkd_part_stats *out)

@@ -574,6 +574,7 @@ typedef struct
 typedef struct
 {
     int ordinal;
+    int lead; /* index of the first engine on the same GPU: it alone builds the seed table */
     nkd_engine *eng;
     int n_parts;
     int *parts; /* indices into ctx->part */
@@ -731,29 +732,49 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         free(c);
         return nk_fail(NULL, NK_ENODEVICE, "no CUDA device: the B200 path has no CPU fallback");
     }
-    c->n_dev = cfg->n_devices > 0 ? cfg->n_devices : 1;
-    if (c->n_dev > c->n_local)
-        c->n_dev = c->n_local;
+    /* Partition t lives on GPU t mod G: no data moves between GPUs on the hot path.  A GPU's partitions are
+     * dealt to (by default) two engines, each with its own stream, scratch lists and pipeline thread, so that
+     * one engine's list passes (classify, sort, rank, commit) and host round trips overlap the other's table
+     * probing on the same GPU. */
+    int epg = getenv("NKB200_ENGINES_PER_GPU") ? atoi(getenv("NKB200_ENGINES_PER_GPU")) : 2;
+    if (epg < 1 || epg > 8)
+        epg = 1;
+    int n_gpus = cfg->n_devices > 0 ? cfg->n_devices : 1;
+    if (n_gpus > c->n_local)
+        n_gpus = c->n_local;
+    int *first_eng = calloc((size_t)n_gpus + 1, sizeof(int)), *n_eng = calloc((size_t)n_gpus, sizeof(int));
+    for (int g = 0; g < n_gpus; g++)
+    {
+        int cnt = (c->n_local - g + n_gpus - 1) / n_gpus; /* partitions i with i mod n_gpus == g */
+        n_eng[g] = cnt < epg ? cnt : epg;
+        first_eng[g + 1] = first_eng[g] + n_eng[g];
+    }
+    c->n_dev = first_eng[n_gpus];
     c->dev = calloc((size_t)c->n_dev, sizeof *c->dev);
     c->part = calloc((size_t)c->n_local, sizeof *c->part);
     c->fs = calloc((size_t)cfg->partitions, sizeof(uint64_t));
     c->fe = calloc((size_t)cfg->partitions, sizeof(uint64_t));
     c->rs = calloc((size_t)cfg->partitions, sizeof(uint64_t));
     c->re = calloc((size_t)cfg->partitions, sizeof(uint64_t));
-    for (int d = 0; d < c->n_dev; d++)
-    {
-        c->dev[d].ordinal = cfg->devices ? cfg->devices[d] : d;
-        c->dev[d].parts = calloc((size_t)c->n_local, sizeof(int));
-    }
+    for (int g = 0; g < n_gpus; g++)
+        for (int d = first_eng[g]; d < first_eng[g + 1]; d++)
+        {
+            c->dev[d].ordinal = cfg->devices ? cfg->devices[g] : g;
+            c->dev[d].lead = first_eng[g];
+            c->dev[d].parts = calloc((size_t)c->n_local, sizeof(int));
+        }
     for (int i = 0; i < c->n_local; i++)
-    { /* partition t lives on GPU t mod G: no data moves between GPUs on the hot path */
+    {
         nk_part *p = &c->part[i];
+        int g = i % n_gpus;
         p->gid = c->part_first + i;
-        p->dev = i % c->n_dev;
+        p->dev = first_eng[g] + (i / n_gpus) % n_eng[g];
         nk_dev *dv = &c->dev[p->dev];
         p->lidx = dv->n_parts;
         dv->parts[dv->n_parts++] = i;
     }
+    free(first_eng);
+    free(n_eng);
     /* step sizing: records per partition per step; operations and bytes follow from 150-base reads,
      * longer reads simply end a partition's batch earlier */
     int max_dev_parts = 0;
@@ -918,6 +939,9 @@ static void nk_seed_task(int d, void *a)
     nk_seed_job *j = a;
     nk_dev *dv = &j->c->dev[d];
     j->inv[d] = -1;
+    j->rc[d] = NK_OK;
+    if (dv->lead != d)
+        return; /* engines sharing a GPU copy the lead engine's seed table in nk_seed_finish */
     j->rc[d] = nkd_seed_step(dv->eng, j->c->seed_seq[j->buf], j->bytes, j->c->seed_reads[j->buf], j->n_reads, &j->inv[d]);
 }
 
@@ -1204,7 +1228,13 @@ static int nk_concat_outputs(nk_ctx *c, const char *base)
 static void nk_seed_finish_task(int d, void *a)
 {
     nk_ctx *c = a;
-    c->dev[d].rc = nkd_seed_finish(c->dev[d].eng);
+    c->dev[d].rc = c->dev[d].lead == d ? nkd_seed_finish(c->dev[d].eng) : NK_OK;
+}
+
+static void nk_seed_adopt_task(int d, void *a)
+{
+    nk_ctx *c = a;
+    c->dev[d].rc = c->dev[d].lead == d ? NK_OK : nkd_seed_finish_from(c->dev[d].eng, c->dev[c->dev[d].lead].eng);
 }
 
 int nk_seed_finish(nk_ctx *c)
@@ -1220,6 +1250,10 @@ int nk_seed_finish(nk_ctx *c)
         if (rc)
             return rc;
     }
+    nk_parallel_for(c->n_dev, c->n_dev, nk_seed_adopt_task, c); /* while the lead engines still hold the seed table */
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].rc)
+            return nk_fail(c, c->dev[d].rc, "%s", nkd_last_error(c->dev[d].eng));
     nk_parallel_for(c->n_dev, c->n_dev, nk_seed_finish_task, c);
     for (int d = 0; d < c->n_dev; d++)
         if (c->dev[d].rc)
@@ -1927,6 +1961,55 @@ int nk_process_planned(nk_ctx *c, const char *fwd, size_t fwd_size, const char *
     return nk_process(c, fwd, fwd_size, rev, rev ? rev_size : 0, rev != NULL, plan);
 }
 
+static int nk_span_cmp(const void *a, const void *b)
+{
+    float x = *(const float *)a, y = *(const float *)b;
+    return x < y ? -1 : x > y;
+}
+
+/* length of the union of the step spans of every engine on one GPU (nkd_run_spans) */
+static double nk_gpu_busy_ms(nk_ctx *c, int ordinal, double fallback)
+{
+    size_t total = 0, engines = 0;
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].ordinal == ordinal)
+        {
+            size_t n = 0;
+            nkd_run_spans(c->dev[d].eng, NULL, 0, &n);
+            total += n;
+            engines++;
+        }
+    if (engines < 2 || !total)
+        return fallback;
+    float *sp = malloc(total * 2 * sizeof *sp);
+    if (!sp)
+        return fallback;
+    size_t at = 0;
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].ordinal == ordinal)
+        {
+            size_t n = 0;
+            nkd_run_spans(c->dev[d].eng, sp + 2 * at, total - at, &n);
+            at += n < total - at ? n : total - at;
+        }
+    qsort(sp, at, 2 * sizeof *sp, nk_span_cmp);
+    double busy = 0, lo = sp[0], hi = sp[1];
+    for (size_t i = 1; i < at; i++)
+    {
+        if (sp[2 * i] > hi)
+        {
+            busy += hi - lo;
+            lo = sp[2 * i];
+            hi = sp[2 * i + 1];
+        }
+        else if (sp[2 * i + 1] > hi)
+            hi = sp[2 * i + 1];
+    }
+    busy += hi - lo;
+    free(sp);
+    return busy;
+}
+
 int nk_totals_get(nk_ctx *c, nk_totals *out)
 {
     *out = c->tot;
@@ -1939,7 +2022,13 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
     {
         nkd_run_stats rs;
         nkd_run_stats_get(c->dev[d].eng, &rs);
-        out->run_ms += rs.run_ms;
+        /* engines sharing a GPU run concurrently: that GPU's busy time is the union of their step spans */
+        int first = 1;
+        for (int o = 0; o < d; o++)
+            if (c->dev[o].ordinal == c->dev[d].ordinal)
+                first = 0;
+        if (first)
+            out->run_ms += nk_gpu_busy_ms(c, c->dev[d].ordinal, rs.run_ms);
         out->probe_ms += rs.probe_ms;
         out->launches += rs.launches;
         out->probe_launches += rs.probe_launches;

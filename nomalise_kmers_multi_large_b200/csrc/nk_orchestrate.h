@@ -89,6 +89,7 @@ class NkEngine
     std::vector<unsigned> T;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     nkd_run_stats rs{};
+    std::vector<float> spans; /* (start, end) ms of every scoring step on the device clock */
     bool staged = false, ran = false;
     float last_total_ms = 0, last_probe_ms = 0;
 
@@ -647,6 +648,37 @@ class NkEngine
         return rc;
     }
 
+    /* copy_hash_table from another engine's seed table on the same GPU: engines that share a GPU seed once */
+    int seed_finish_from(NkEngine &src)
+    {
+        if (seeded)
+            return fail(NK_EINVAL, "nkd_seed_finish called twice");
+        if (!src.seed.tab || src.seeded)
+            return fail(NK_EINVAL, "nkd_seed_finish_from: the source engine no longer holds its seed table");
+        if (src.cfg.device != cfg.device || src.cfg.k != cfg.k || src.cfg.canonical != cfg.canonical)
+            return fail(NK_EINVAL, "nkd_seed_finish_from: engines differ in GPU or k-mer settings");
+        src.be.sync(); /* the source's seed steps are complete */
+        be.release(seed.tab);
+        seed = src.seed;
+        seed.tab = nullptr;
+        parts.resize(cfg.n_parts);
+        for (int p = 0; p < cfg.n_parts; p++)
+        {
+            NkTable &t = parts[p];
+            t = seed;
+            t.st = nkd_part_stats{};
+            t.st.capacity = seed.cap;
+            t.st.used = seed.used;
+            t.tab = (NkSlot *)be.alloc(seed.cap * sizeof(NkSlot));
+            if (!t.tab)
+                return fail(NK_ENOMEM, "Memory allocation failed (partition table copy)");
+            be.d2d(t.tab, src.seed.tab, seed.cap * sizeof(NkSlot));
+        }
+        be.sync();
+        seeded = true;
+        return NK_OK;
+    }
+
     int seed_finish()
     {
         if (seeded)
@@ -711,6 +743,7 @@ class NkEngine
         be.d2h(&h_ctr, d_ctr, 32);
         d2h_bytes += nrec + 32;
         be.sync();
+        be.timer_spans(0, spans);
         last_total_ms = be.timer_ms(0);
         last_probe_ms = be.timer_ms(1);
         rs.run_ms += last_total_ms;

@@ -43,6 +43,7 @@ struct EmuBackend
     void begin_timer(int) {}
     void end_timer(int) {}
     void reset_timer(int) {}
+    void timer_spans(int, std::vector<float> &) {}
     float timer_ms(int) { return 0.f; }
 
     std::vector<unsigned> order(size_t n)

@@ -34,6 +34,7 @@ int nkd_seed_step(nkd_engine *e, const uint8_t *s, size_t sb, const nkd_read *r,
     return 0;
 }
 int nkd_seed_finish(nkd_engine *e) { (void)e; return 0; }
+int nkd_seed_finish_from(nkd_engine *e, nkd_engine *s) { (void)e; (void)s; return 0; }
 int nkd_seed_stats(nkd_engine *e, nkd_part_stats *st) { memset(st, 0, sizeof *st); st->capacity = e->cfg.capacity0; return 0; }
 int nkd_stage_segments(nkd_engine *e, const uint8_t *seq, const nkd_segment *segs, int n, int paired)
 {
@@ -56,6 +57,7 @@ int nkd_fetch(nkd_engine *e, uint8_t *accept, size_t n, int64_t *inv)
     if (inv) *inv = -1;
     return 0;
 }
+int nkd_run_spans(nkd_engine *e, float *s, size_t c, size_t *n) { (void)e; (void)s; (void)c; if (n) *n = 0; return 0; }
 int nkd_run_stats_get(nkd_engine *e, nkd_run_stats *o) { (void)e; memset(o, 0, sizeof *o); return 0; }
 int nkd_part_stats_get(nkd_engine *e, int p, nkd_part_stats *o) { (void)p; memset(o, 0, sizeof *o); o->capacity = e->cfg.capacity0; return 0; }
 int nkd_dump_text(nkd_engine *e, int p, uint64_t f, uint64_t n, char *t, size_t c, size_t *b) { (void)e; (void)p; (void)f; (void)n; (void)t; (void)c; *b = 0; return 0; }
