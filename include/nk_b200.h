@@ -263,6 +263,7 @@ typedef struct
     uint64_t ops, touches, probe_touches, slow_events, expansions;
     double class_ms[8]; /* see nkd_run_stats */
     uint64_t pend_events, open_ops;
+    uint64_t engines; /* engines (stream + scratch + pipeline thread) of this context, over all its GPUs */
 } nk_totals;
 
 int nk_totals_get(nk_ctx *c, nk_totals *out);

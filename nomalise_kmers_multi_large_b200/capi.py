@@ -84,7 +84,7 @@ class Totals(C.Structure):
                 ("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("ops", C.c_uint64),
                 ("touches", C.c_uint64), ("probe_touches", C.c_uint64), ("slow_events", C.c_uint64),
                 ("expansions", C.c_uint64), ("class_ms", C.c_double * 8), ("pend_events", C.c_uint64),
-                ("open_ops", C.c_uint64)]
+                ("open_ops", C.c_uint64), ("engines", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "class_ms" else getattr(self, n)) for n, _ in self._fields_}

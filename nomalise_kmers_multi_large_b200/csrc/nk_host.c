@@ -733,10 +733,10 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         return nk_fail(NULL, NK_ENODEVICE, "no CUDA device: the B200 path has no CPU fallback");
     }
     /* Partition t lives on GPU t mod G: no data moves between GPUs on the hot path.  A GPU's partitions are
-     * dealt to (by default) two engines, each with its own stream, scratch lists and pipeline thread, so that
+     * dealt to (by default) up to four engines, each with its own stream, scratch lists and pipeline thread, so that
      * one engine's list passes (classify, sort, rank, commit) and host round trips overlap the other's table
      * probing on the same GPU. */
-    int epg = getenv("NKB200_ENGINES_PER_GPU") ? atoi(getenv("NKB200_ENGINES_PER_GPU")) : 2;
+    int epg = getenv("NKB200_ENGINES_PER_GPU") ? atoi(getenv("NKB200_ENGINES_PER_GPU")) : 4;
     if (epg < 1 || epg > 8)
         epg = 1;
     int n_gpus = cfg->n_devices > 0 ? cfg->n_devices : 1;
@@ -788,9 +788,12 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         if (e && atoi(e) > 0)
             sp = (uint32_t)atoi(e);
         else
-        { /* about 75 M operations per device step whatever the number of resident partitions */
+        { /* about 75 M operations per launch of a GPU's only engine, half that when several engines share
+           * the GPU (measured: profiles/r01_sweep_engines.txt); launches below ~20 M operations waste their
+           * list chunks and are avoided */
+            uint64_t target = (c->n_dev > n_gpus ? 48ull : 96ull) << 20;
             sp = 262144u;
-            while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > (96ull << 20))
+            while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > target)
                 sp /= 2;
         }
     }
@@ -2040,6 +2043,7 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
         for (int k = 0; k < 8; k++)
             out->class_ms[k] += rs.class_ms[k];
     }
+    out->engines = (uint64_t)c->n_dev;
     if (c->seeded)
         for (int i = 0; i < c->n_local; i++)
         {
