@@ -228,7 +228,7 @@ def run_ours(args):
     out_dir = Path(tempfile.mkdtemp(prefix=f"out_r{rank}_", dir=shm_dir()))
     sampler = ClockSampler(local) if rank == 0 else None
     steps = []
-    for it in range(args.warmup + args.steps):
+    def one_pass(timed):
         ctxs = [Pipeline(k=K, depth=DEPTH, coverage=COVERAGE, canonical=True, partitions=PARTS,
                          memory_gb=args.memory, n_forward_files=1, have_reverse=True, out_dir=out_dir,
                          devices=(local,), part_first=rank * per_rank, part_count=per_rank)]
@@ -240,7 +240,7 @@ def run_ours(args):
         seed_s = time.perf_counter() - t_seed
         barrier(dist, local)
         if sampler:
-            sampler.active = it >= args.warmup
+            sampler.active = timed
         t0 = time.perf_counter()
         if world > 1:
             # the byte ranges are computed once (rank 0, all host cores) and handed to the ranks: 256 bytes of control
@@ -268,8 +268,22 @@ def run_ours(args):
         agg["wall_s"], agg["seed_s"] = wall, seed_s
         for c in ctxs:
             c.close()
+        return agg
+
+    for it in range(args.warmup + args.steps):
+        agg = one_pass(it >= args.warmup)
         if it >= args.warmup:
             steps.append(agg)
+    # k_probe timed without the GPU's other engines running beside it: one extra, untimed pass with one engine per GPU
+    isolated = None
+    if not args.no_isolated_probe:
+        prev = os.environ.get("NKB200_ENGINES_PER_GPU")
+        os.environ["NKB200_ENGINES_PER_GPU"] = "1"
+        isolated = one_pass(False)
+        if prev is None:
+            del os.environ["NKB200_ENGINES_PER_GPU"]
+        else:
+            os.environ["NKB200_ENGINES_PER_GPU"] = prev
     if sampler:
         sampler.stop()
     shutil.rmtree(out_dir, ignore_errors=True)
@@ -281,6 +295,8 @@ def run_ours(args):
             "slow_events", "expansions", "h2d_bytes", "d2h_bytes", "probe_ms", "index_seconds", "device_seconds",
             "write_seconds", "seed_s", "pend_events", "open_ops", "engines"] + ["ms_" + n for n in CLASSES]
     sums = dict(zip(keys, all_sum(dist, local, [sum(s[k] for s in steps) for k in keys])))
+    ikeys = ["probe_ms", "probe_launches", "probe_touches", "processed", "run_ms"]
+    iso = dict(zip(ikeys, all_sum(dist, local, [isolated[k] for k in ikeys]))) if isolated else None
     if rank != 0:
         return
     pairs = sums["processed"] / n
@@ -328,6 +344,14 @@ def run_ours(args):
                      "pending_list_entries": sums["pend_events"] / n, "open_list_entries": sums["open_ops"] / n,
                      "expansions_in_scoring": sums["expansions"] / n},
     }
+    if iso and iso["probe_ms"] > 0:
+        ibytes = 20.0 * iso["probe_touches"] + (2 * READ_LEN + 1) * iso["processed"]
+        iach = ibytes / (iso["probe_ms"] / 1e3) / 1e9      # summed over ranks on both sides: per-GPU rate
+        line["roofline"]["isolated"] = {
+            "achieved": iach, "frac": iach / peak, "avg_launch_ms": iso["probe_ms"] / max(iso["probe_launches"], 1),
+            "algorithmic_bytes_per_launch": ibytes / max(iso["probe_launches"], 1),
+            "device_ms": iso["run_ms"] / max(world, 1),
+            "how": "one extra untimed pass with one engine per GPU (NKB200_ENGINES_PER_GPU=1): k_probe has the GPU to itself"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = time_reference(args.sample_pairs)
@@ -373,6 +397,8 @@ def main():
     ap.add_argument("--sample-pairs", type=int, default=100_000)
     ap.add_argument("--memory", type=int, default=0, help="-m for the tables (0 = reference default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-isolated-probe", action="store_true",
+                    help="skip the extra untimed pass that times k_probe with one engine per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
