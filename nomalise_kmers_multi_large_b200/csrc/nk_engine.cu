@@ -481,6 +481,7 @@ struct CudaBackend
     int dev = -1, sms = 148;
     unsigned long long launches = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t sync_ev = nullptr;
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     std::string cuda_err;
@@ -532,6 +533,12 @@ struct CudaBackend
             err = cuda_err;
             return NK_ENODEVICE;
         }
+        if (!getenv("NKB200_SPIN_SYNC") &&
+            cudaEventCreateWithFlags(&sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
+        {
+            cudaGetLastError();
+            sync_ev = nullptr;
+        }
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         epoch(dev);
         cudaMemPool_t pool;
@@ -553,6 +560,9 @@ struct CudaBackend
         for (auto &t : timers)
             for (auto e : t.ev)
                 cudaEventDestroy(e);
+        if (sync_ev)
+            cudaEventDestroy(sync_ev);
+        sync_ev = nullptr;
         if (sort_tmp)
             cudaFreeAsync(sort_tmp, stream);
         if (stream)
@@ -601,7 +611,19 @@ struct CudaBackend
     void h2d(void *d, const void *h, size_t n) { ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream), "H2D copy"); }
     void d2h(void *h, const void *d, size_t n) { ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream), "D2H copy"); }
     void d2d(void *d, const void *s, size_t n) { ok(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream), "D2D copy"); }
-    void sync() { ok(cudaStreamSynchronize(stream), "stream synchronize"); }
+    /* Waiting on a blocking-sync event puts the host thread to sleep instead of spinning in the driver: the
+     * engines' threads wait most of the time, and the cores they would burn are the ones the host stages
+     * (record indexing, output writing) are short of.  NKB200_SPIN_SYNC=1 restores the spinning wait. */
+    void sync()
+    {
+        if (!sync_ev)
+        {
+            ok(cudaStreamSynchronize(stream), "stream synchronize");
+            return;
+        }
+        if (ok(cudaEventRecord(sync_ev, stream), "event record"))
+            ok(cudaEventSynchronize(sync_ev), "event synchronize");
+    }
 
     /* entries a warp reserves per global atomic: large enough to make the atomics negligible, small enough
      * that the holes of (SMs x 8 x 8) warps stay a small fraction of the list */
@@ -610,6 +632,7 @@ struct CudaBackend
         const char *e = getenv(name);
         return e && atoi(e) >= 32 ? (unsigned)atoi(e) : dflt;
     }
+    unsigned min_list_entries() const { return (unsigned)sms * 8u * 8u * 2u * 32u * 3u; }
     void chunk_sizes(unsigned *c, unsigned pend_cap, unsigned open_cap, unsigned claim_cap, unsigned slow_cap,
                      unsigned spec_cap)
     {

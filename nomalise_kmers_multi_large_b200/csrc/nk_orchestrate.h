@@ -123,6 +123,13 @@ class NkEngine
         uint64_t ops = std::max<uint64_t>(c.max_step_ops, 1024);
         open_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_OPEN_FRAC", 1.0) + 1024);
         pend_cap = (unsigned)std::min<double>(4e9, ops * nk_env_double("NKB200_PEND_FRAC", 2.0) + 1024);
+        /* small steps: every warp of a launch may hold two reserved chunks per list, so a list shorter than
+         * a few times that is all holes and the step would only shrink its windows and retry */
+        if (!getenv("NKB200_OPEN_FRAC") && !getenv("NKB200_PEND_FRAC"))
+        {
+            open_cap = std::max(open_cap, be.min_list_entries());
+            pend_cap = std::max(pend_cap, be.min_list_entries());
+        }
         claim_cap = open_cap;
         spec_cap = open_cap;
         /* every listed event can turn into one slow record; chunked reservation wastes at most a chunk per warp */

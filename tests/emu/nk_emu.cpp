@@ -39,6 +39,7 @@ struct EmuBackend
     void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void sync() {}
     bool prepare_sort(size_t, std::string &) { return true; }
+    unsigned min_list_entries() const { return 0; }
     void chunk_sizes(unsigned *c, unsigned, unsigned, unsigned, unsigned, unsigned) { c[0] = c[1] = c[2] = c[3] = c[4] = 0; }
     void begin_timer(int) {}
     void end_timer(int) {}

@@ -46,6 +46,17 @@ static void nk_prof_stop(const char *path)
     for (long i = 0; i < n; i++)
         fprintf(o, "%llx\n", nk_samples[i]);
     fclose(o);
+    /* the address map, so that samples inside shared libraries can be attributed to their module */
+    char mp[512];
+    snprintf(mp, sizeof mp, "%s.maps", path);
+    FILE *mi = fopen("/proc/self/maps", "r"), *mo = fopen(mp, "w");
+    if (mi && mo)
+        for (int ch; (ch = fgetc(mi)) != EOF;)
+            fputc(ch, mo);
+    if (mi)
+        fclose(mi);
+    if (mo)
+        fclose(mo);
 }
 
 static char *slurp(const char *path, size_t *n)
@@ -79,7 +90,7 @@ int main(int argc, char **argv)
         memset(&c, 0, sizeof c);
         c.k = 25; c.depth = 100; c.coverage = 0.9f; c.canonical = 1; c.in_fastq = c.out_fastq = 1;
         c.partitions = parts; c.n_forward_files = 1; c.have_reverse = 1; c.out_dir = "/dev/shm/nk_hostbench"; c.n_devices = 1;
-        c.memory_gb = 1;
+        c.memory_gb = getenv("NK_HB_MEMORY") ? atoi(getenv("NK_HB_MEMORY")) : 0;
         if (system("rm -rf /dev/shm/nk_hostbench && mkdir -p /dev/shm/nk_hostbench")) return 1;
         nk_ctx *x;
         if (nk_create(&c, &x)) { fprintf(stderr, "%s\n", nk_create_error()); return 1; }
