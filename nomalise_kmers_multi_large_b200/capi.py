@@ -242,6 +242,17 @@ class Engine:
     def seed_finish(self):
         self._check(self.lib.nkd_seed_finish(self.h))
 
+    def seed_finish_from(self, src):
+        """copy_hash_table from another engine's seed table on the same GPU (call before src.seed_finish())"""
+        self._check(self.lib.nkd_seed_finish_from(self.h, src.h))
+
+    def run_spans(self):
+        n = C.c_size_t(0)
+        self.lib.nkd_run_spans(self.h, None, 0, C.byref(n))
+        buf = np.zeros(2 * max(1, n.value), np.float32)
+        self.lib.nkd_run_spans(self.h, buf.ctypes.data, n.value, C.byref(n))
+        return buf[:2 * n.value].reshape(-1, 2)
+
     def seed_stats(self):
         st = PartStats()
         self._check(self.lib.nkd_seed_stats(self.h, C.byref(st)))

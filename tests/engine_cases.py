@@ -156,3 +156,45 @@ def run_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_par
         return info
     finally:
         eng.close()
+
+
+def run_shared_seed_case(lib, *, k=15, canonical=True, depth=3, cap0=4099, seed=5, device_clock=False):
+    """Two engines on one GPU: the second takes its partitions from the first one's seed table
+    (nkd_seed_finish_from) and must then behave exactly like an engine that seeded itself."""
+    rng = np.random.default_rng(seed)
+    genome = make_genome(rng, 2500)
+    seed_reads = [sample_read(rng, genome, 40, 100) for _ in range(150)]
+    mk = lambda: capi.Engine(k=k, canonical=canonical, depth_per_part=depth, coverage=0.9, n_parts=2, capacity0=cap0,
+                             max_step_reads=4096, max_step_bytes=1 << 20, max_step_ops=1 << 20, lib=lib)
+    lead, follower = mk(), mk()
+    try:
+        buf, descs, _ = capi.pack_reads(seed_reads, None, k)
+        lead.seed_step(buf, descs)
+        otab = ol.OracleTable(cap0)
+        for s_ in seed_reads:
+            otab.seed(s_, k, canonical)
+        follower.seed_finish_from(lead)
+        lead.seed_finish()
+        otabs = [otab.clone() for _ in range(2)]
+        seqs, parts, want = [], [], []
+        for p in range(2):
+            for _ in range(100):
+                f, r = sample_read(rng, genome, 40, 100), revcomp(sample_read(rng, genome, 40, 100))
+                seqs += [f, r]
+                parts += [p, p]
+                scores = [otabs[p].score(m, k, canonical, depth) for m in (f, r)]  # both mates always touch the table
+                want.append(int(all(ol.keep_mate(h, t, 0.9) for h, t in scores)))
+        buf, descs, _ = capi.pack_reads(seqs, parts, k)
+        for eng in (follower, lead):
+            acc, inv = eng.step(buf, descs, True)
+            assert inv == -1 and acc.tolist() == want
+            for p in range(2):
+                ek, ec_ = eng.export(p)
+                okk, okc = otabs[p].export()
+                assert np.array_equal(ek, okk) and np.array_equal(ec_, okc)
+        spans = follower.run_spans()   # one (start, end) per scoring step on the GPU's clock; the emulation has no clock
+        assert spans.shape == ((1, 2) if device_clock else (0, 2))
+        assert not device_clock or spans[0, 1] > spans[0, 0] >= 0
+    finally:
+        follower.close()
+        lead.close()

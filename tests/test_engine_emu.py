@@ -38,3 +38,7 @@ def test_emulated_engine_scratch_overflow_is_exact(emu_lib, monkeypatch):
     monkeypatch.setenv("NKB200_PEND_FRAC", "0.03")
     info = ec.run_case(emu_lib, seed=3, k=15, canonical=True, depth=3, cap0=4099, n_parts=2, steps=2, records_per_step=80)
     assert info["ops"] > 0
+
+
+def test_emulated_engines_share_one_seed_table(emu_lib):
+    ec.run_shared_seed_case(emu_lib)

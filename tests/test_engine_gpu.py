@@ -42,6 +42,11 @@ def test_engine_is_deterministic_under_tight_scratch(cuda_lib):
                     records_per_step=60)
 
 
+def test_engines_share_one_seed_table(cuda_lib):
+    """several engines (streams) per GPU seed once: nkd_seed_finish_from"""
+    ec.run_shared_seed_case(cuda_lib, device_clock=True)
+
+
 def test_engine_scratch_overflow_is_exact(cuda_lib, monkeypatch):
     monkeypatch.setenv("NKB200_OPEN_FRAC", "0.02")
     monkeypatch.setenv("NKB200_PEND_FRAC", "0.03")
