@@ -1746,6 +1746,11 @@ static void *nk_device_pipeline(void *a)
     if (pp->t_index >= threads)
         pp->t_index = threads - 1;
     pp->t_write = threads - pp->t_index;
+    if (dv->n_parts >= threads - 1)
+        /* many partitions per engine (-p 64): which stage is the heavier one depends on the share of records
+         * that is kept, so both stages get all of this pipeline's threads and the OS balances them (20 M pairs
+         * at -p 64: 1.36 -> 0.98 s) */
+        pp->t_index = pp->t_write = threads;
     dv->rc = NK_OK;
     pthread_mutex_init(&pp->mu, NULL);
     pthread_cond_init(&pp->cv, NULL);
