@@ -334,7 +334,8 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": probe_bytes / max(sums["probe_launches"], 1),
                      "avg_launch_ms": sums["probe_ms"] / max(sums["probe_launches"], 1),
-                     "share_of_step": sums["probe_ms"] / max(world, 1) / dev_ms if dev_ms else None,
+                     # share of the kernels' stream time (engines overlap, so not of the GPU-busy time)
+                     "share_of_step": sums["probe_ms"] / max(sum(sums["ms_" + c] for c in CLASSES), 1e-9),
                      "touches_per_op": sums["touches"] / max(sums["ops"], 1),
                      "note": "avg_launch_ms is measured while the GPU's other engines run their kernels concurrently"},
         "kernel_ms_per_step": {n: sums["ms_" + n] / n_ / max(world, 1) for n in CLASSES},
