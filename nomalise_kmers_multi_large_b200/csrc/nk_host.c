@@ -620,9 +620,12 @@ const char *nk_last_error(const nk_ctx *c) { return c ? c->err : g_create_err; }
 
 static int nk_fail(nk_ctx *c, int code, const char *fmt, ...)
 {
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER; /* engines dump their tables concurrently */
     va_list ap;
     va_start(ap, fmt);
+    pthread_mutex_lock(&mu);
     vsnprintf(c ? c->err : g_create_err, 768, fmt, ap);
+    pthread_mutex_unlock(&mu);
     va_end(ap);
     return code;
 }
@@ -2079,6 +2082,20 @@ int nk_partition_stats(nk_ctx *c, int partition, nkd_part_stats *out)
     return NK_OK;
 }
 
+static void nk_dump_task(int d, void *a)
+{
+    nk_ctx *c = a;
+    nk_dev *dv = &c->dev[d];
+    dv->rc = NK_OK;
+    for (int i = 0; i < dv->n_parts && !dv->rc; i++)
+    {
+        nk_part *p = &c->part[dv->parts[i]];
+        nkd_part_stats st;
+        nkd_part_stats_get(dv->eng, p->lidx, &st);
+        dv->rc = nk_write_dump(c, dv->eng, p->lidx, st.capacity, "", p->gid);
+    }
+}
+
 int nk_finish(nk_ctx *c)
 { /* C:2398-2413 */
     if (c->finished)
@@ -2094,16 +2111,23 @@ int nk_finish(nk_ctx *c)
         if (p->out_r && fclose(p->out_r) != 0 && !rc)
             rc = nk_fail(c, NK_EIO, "error closing output: %s", strerror(errno));
         p->out_r = NULL;
-        if (c->cfg.dump_tables && c->seeded && !rc)
-        {
-            nkd_part_stats st;
-            nkd_engine *e = c->dev[p->dev].eng;
-            nkd_part_stats_get(e, p->lidx, &st);
-            rc = nk_write_dump(c, e, p->lidx, st.capacity, "", p->gid);
-        }
     }
+    double t0 = nk_now();
+    if (c->cfg.dump_tables && c->seeded && !rc)
+    { /* every engine formats and writes its own partitions' tables; engines work side by side */
+        nk_parallel_for(c->n_dev, c->n_dev, nk_dump_task, c);
+        for (int d = 0; d < c->n_dev && !rc; d++)
+            rc = c->dev[d].rc;
+        if (c->cfg.verbose)
+            printf("B200: k-mer tables written in %.3f s\n", nk_now() - t0);
+    }
+    t0 = nk_now();
     if (c->seeded && !rc && c->cfg.merged_table)
+    {
         rc = nk_write_merged_table(c);
+        if (c->cfg.verbose)
+            printf("B200: merged k-mer table written in %.3f s\n", nk_now() - t0);
+    }
     if (c->seeded && !rc && c->cfg.merged_output)
     {
         rc = nk_concat_outputs(c, "output_forward");
