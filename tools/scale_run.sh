@@ -15,6 +15,7 @@ t0=$(date +%s.%N)
 t1=$(date +%s.%N)
 python3 -c "print('wall %.2f s' % ($t1 - $t0))"
 grep -h "Initial hash\|Seeding took\|Final Report\|Records:\|Cumulative Max\|Total runtime\|Overall processing\|^B200:" "$W/out/log.txt"
+grep -h "^\[nk" "$W/out/log.txt" | grep -v "seed flush" | head -${NK_DEBUG_LINES:-0}
 ls -la "$W/out" | grep "output_kmer" | awk '{s+=$5} END {printf "k-mer table text: %.2f GB in %d files\n", s/1e9, NR}'
 ls "$W/out" | wc -l; du -sh "$W/out" | cut -f1
 nvidia-smi --query-gpu=memory.used,memory.total --format=csv,noheader
