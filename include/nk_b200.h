@@ -11,9 +11,10 @@
  *   nk_*   host pipeline: byte ranges -> record index -> pinned staging ->
  *          device steps -> accepted records written per partition.  This is
  *          what a maintainer of the reference binds.
- *   nkd_*  one device engine per GPU: HBM-resident per-partition tables and
- *          the sm_100a kernels (extract / probe / resolve / decide / rehash).
- *          Used by nk_*, by the parity tests and by bench.py's kernel-only leg.
+ *   nkd_*  device engines: HBM-resident per-partition tables, one CUDA stream,
+ *          step scratch and the sm_100a kernels (probe / resolve / decide /
+ *          rehash / dump).  The host pipeline drives up to four per GPU.  Used
+ *          by nk_*, by the parity tests and by bench.py's kernel-only figures.
  *
  * Every function returns 0 on success and a negative NK_E* code otherwise;
  * nk_last_error() / nkd_last_error() give the message.  There is no CPU
@@ -82,7 +83,7 @@ typedef struct
     int canonical;       /* C:1472-1476 */
     int depth_per_part;  /* cfg.depth_per_cpu, C:674 */
     float coverage;      /* cfg.coverage as float32, C:216 */
-    int n_parts;         /* partitions resident on this GPU */
+    int n_parts;         /* partitions this engine holds */
     uint64_t capacity0;  /* cfg.initial_hash_size, C:676-684 */
     uint64_t max_step_reads; /* staging limits of one step */
     uint64_t max_step_bytes;
@@ -257,7 +258,8 @@ typedef struct
     uint64_t max_used;                    /* reporting.max_total_kmers */
     double seed_seconds, process_seconds, index_seconds, device_seconds, write_seconds;
     uint64_t h2d_bytes, d2h_bytes;
-    /* device-side figures summed over the GPUs of this context (scoring steps only) */
+    /* device-side figures of this context (scoring steps only).  run_ms: per GPU the union of its engines'
+     * step spans (nkd_run_spans), summed over the GPUs; the others are sums over the engines */
     double run_ms, probe_ms;
     uint64_t launches, probe_launches;
     uint64_t ops, touches, probe_touches, slow_events, expansions;
