@@ -15,13 +15,14 @@ class Pipeline:
 
     def __init__(self, k=15, depth=100, coverage=0.9, canonical=False, in_fastq=True, out_fastq=True, memory_gb=0,
                  partitions=1, dump_tables=False, n_forward_files=1, have_reverse=True, out_dir=".", devices=(0,),
-                 part_first=0, part_count=0, step_pairs=0, lib=None):
+                 part_first=0, part_count=0, step_pairs=0, merged_table=False, merged_output=False, lib=None):
         self.lib = lib if lib is not None else capi.load_library()
         self._devs = (C.c_int * len(devices))(*devices)
         self._out_dir = str(out_dir).encode()
         self.cfg = capi.PipelineConfig(k, depth, coverage, int(canonical), int(in_fastq), int(out_fastq), memory_gb,
                                        partitions, int(dump_tables), 0, n_forward_files, int(have_reverse),
-                                       self._out_dir, len(devices), self._devs, part_first, part_count, step_pairs)
+                                       self._out_dir, len(devices), self._devs, part_first, part_count, step_pairs,
+                                       int(merged_table), int(merged_output))
         self.h = C.c_void_p()
         rc = self.lib.nk_create(C.byref(self.cfg), C.byref(self.h))
         if rc != capi.NK_OK:

@@ -46,3 +46,25 @@ def test_two_ranks_equal_one_process(tmp_path):
     assert got == want["files"]
     totals = json.loads((out / "totals.json").read_text())
     assert (totals["processed"], totals["printed"], totals["skipped"], totals["max_used"]) == want["counters"][-1]
+
+
+def test_merged_extras_need_every_partition(tmp_path):
+    """--merged-table / --merged-output are whole-run outputs: a context that owns a slice of the partitions
+    (one rank of a multi-process launch) must refuse them instead of writing a partial file."""
+    import ctypes
+
+    import pytest
+
+    from nomalise_kmers_multi_large_b200 import capi
+    from nomalise_kmers_multi_large_b200.pipeline import Pipeline
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "emu")], check=True, capture_output=True)
+    lib = ctypes.CDLL(str(EMU_LIB))
+    capi._declare_engine(lib)
+    capi._declare_pipeline(lib)
+    for extra in ({"merged_table": True}, {"merged_output": True}):
+        with pytest.raises(capi.NkError) as err:
+            Pipeline(k=21, depth=16, partitions=4, memory_gb=1, out_dir=tmp_path, part_first=0, part_count=2, lib=lib, **extra)
+        assert "owns all 4 partitions" in str(err.value)
+    with Pipeline(k=21, depth=16, partitions=4, memory_gb=1, out_dir=tmp_path, merged_table=True, merged_output=True,
+                  lib=lib) as p:
+        assert p.totals()["engines"] >= 1
