@@ -351,7 +351,7 @@ def run_ours(args):
         line["roofline"]["isolated"] = {
             "achieved": iach, "frac": iach / peak, "avg_launch_ms": iso["probe_ms"] / max(iso["probe_launches"], 1),
             "algorithmic_bytes_per_launch": ibytes / max(iso["probe_launches"], 1),
-            "device_ms": iso["run_ms"] / max(world, 1),
+            "device_ms": iso["run_ms"] / max(world, 1), "share_of_step": iso["probe_ms"] / max(iso["run_ms"], 1e-9),
             "how": "one extra untimed pass with one engine per GPU (NKB200_ENGINES_PER_GPU=1): k_probe has the GPU to itself"}
     if world == 1 and not args.no_cpu_baseline:
         try:
