@@ -6,12 +6,16 @@ untimed, before every step because scoring mutates the tables; the reference's o
 after seeding, C:2308).  The workload is BASELINE.json configs[1]: 10 M synthetic 150-base read pairs with
 transcriptome-skewed coverage, -k 25 --canonical -p 8 -d 100, default table capacity (67,108,879 slots per
 partition, growing x1.5), on one B200.  With --gpus N the same fixed 8 partitions are spread over N ranks
-(partition t on rank t mod N, no data-path collective) -- strong scaling, results identical for every N.
+(a contiguous slice per rank, no data-path collective) -- strong scaling, results identical for every N.
 
-  value   pairs / device time of the pass (CUDA events around every nkd_run; inputs already in HBM)
+  value   pairs / GPU-busy time of the pass: CUDA events around every device step; a GPU's engines (streams)
+          overlap, so their step spans are merged (union) on the GPU clock.  The kernels read the step's
+          sequence bytes from pinned host memory; with the bytes copied to HBM first (NKB200_NO_ZEROCOPY=1)
+          the device time is the same (profiles/README.md)
   e2e     pairs / wall time of nk_process_paired on HOST buffers (partitioning, record indexing, pinned
           staging, H2D, kernels, D2H, writing the accepted records)
-  roofline  k_probe: (20 B x slots it visits + sequence bytes + 1 B/pair) / its CUDA-event time vs measured HBM peak
+  roofline  k_probe: (20 B x slots it visits + sequence bytes + 1 B/pair) / its CUDA-event time vs measured HBM peak;
+          roofline.isolated = the same from one extra untimed pass in which k_probe has the GPU to itself
   cpu_baseline / --impl reference  the reference binary (oracle/_ref) on the box's host cores, same flags,
           bounded sample, timed from its own per-thread completion lines with the sleep(1) stagger removed.
 """
