@@ -397,9 +397,12 @@ class NkEngine
                             (unsigned long long)tabs[p]->cap, h_ctr.claims[p], (unsigned long long)h_ctr.real_ops[p]);
                 fprintf(stderr, "\n");
             }
-            if (h_ctr.overflow & NK_OVF_WALK)
-                return fail(NK_EINTERNAL, "probe walk exceeded the supported length (table degenerate)");
-            bool ovf = (h_ctr.overflow & (NK_OVF_OPEN | NK_OVF_PEND | NK_OVF_CLAIM)) != 0;
+            /* A walk that hits the watchdog usually means the speculative pass claimed more slots than the table
+             * has free ones (a step full of new k-mers): the growth the reference would have done in the middle of
+             * the step has not happened yet.  Treated like a list overflow: undo, halve the windows, and let the
+             * threshold cut of a shorter window grow the table in time. */
+            bool walk = (h_ctr.overflow & NK_OVF_WALK) != 0;
+            bool ovf = walk || (h_ctr.overflow & (NK_OVF_OPEN | NK_OVF_PEND | NK_OVF_CLAIM)) != 0;
             bool cut = false;
             std::vector<unsigned> nhi(hi);
             if (ovf)
@@ -415,7 +418,8 @@ class NkEngine
                         }
                     }
                 if (!cut)
-                    return fail(NK_ENOMEM, "step scratch too small for a single operation");
+                    return walk ? fail(NK_EINTERNAL, "probe walk exceeded the supported length (table degenerate)")
+                                : fail(NK_ENOMEM, "step scratch too small for a single operation");
             }
             else
             {

@@ -42,3 +42,12 @@ def test_emulated_engine_scratch_overflow_is_exact(emu_lib, monkeypatch):
 
 def test_emulated_engines_share_one_seed_table(emu_lib):
     ec.run_shared_seed_case(emu_lib)
+
+
+def test_emulated_step_that_overfills_the_table(emu_lib, monkeypatch):
+    """A step whose new k-mers outnumber the table's free slots: the speculative pass fills the table, walks hit the
+    watchdog, and the step must fall back to shorter windows (growing the table in time) instead of failing."""
+    monkeypatch.setenv("NK_EMU_SEED", "271928365")
+    info = ec.run_case(emu_lib, seed=126076854, k=7, canonical=False, depth=6, coverage=0.5, n_parts=1, cap0=257,
+                       genome_len=6000, n_seed_reads=20, steps=4, records_per_step=40, paired=True, read_len=(100, 160), err=0.0)
+    assert info["expansions"] >= 3

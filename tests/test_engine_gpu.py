@@ -47,6 +47,13 @@ def test_engines_share_one_seed_table(cuda_lib):
     ec.run_shared_seed_case(cuda_lib, device_clock=True)
 
 
+def test_step_that_overfills_the_table(cuda_lib):
+    """more new k-mers in one step than the table has free slots: shorter windows, growth in time, same results"""
+    info = ec.run_case(cuda_lib, seed=126076854, k=7, canonical=False, depth=6, coverage=0.5, n_parts=1, cap0=257,
+                       genome_len=6000, n_seed_reads=20, steps=4, records_per_step=40, paired=True, read_len=(100, 160), err=0.0)
+    assert info["expansions"] >= 3
+
+
 def test_engine_scratch_overflow_is_exact(cuda_lib, monkeypatch):
     monkeypatch.setenv("NKB200_OPEN_FRAC", "0.02")
     monkeypatch.setenv("NKB200_PEND_FRAC", "0.03")
