@@ -318,6 +318,9 @@ class NkEngine
     {
         size_t np = tabs.size();
         std::vector<unsigned> lo(np, 0), hi(np);
+        /* after an overflow the windows regrow by doubling instead of jumping back to the whole remainder, which
+         * would overflow again and repeat the halving cascade for every few operations of progress */
+        std::vector<unsigned> regrow(np, 0); /* 0 = no limit; else the size of the last window that was tried */
         for (size_t p = 0; p < np; p++)
             hi[p] = T[p];
         uint64_t gsum = 0;
@@ -414,6 +417,7 @@ class NkEngine
                         if (w > 1)
                         {
                             nhi[p] = lo[p] + w / 2;
+                            regrow[p] = w / 2;
                             cut = true;
                         }
                     }
@@ -535,6 +539,14 @@ class NkEngine
                 t.st.touches += h_ctr.touches[p];
                 lo[p] = hi[p];
                 hi[p] = T[p];
+                if (regrow[p])
+                {
+                    regrow[p] = regrow[p] > (1u << 30) ? regrow[p] : regrow[p] * 2;
+                    if (T[p] - lo[p] > regrow[p])
+                        hi[p] = lo[p] + regrow[p];
+                    else
+                        regrow[p] = 0; /* the remainder fits the regrown window: back to normal */
+                }
             }
             if (mode == NK_MODE_SCORE && np > 0)
             {
