@@ -50,21 +50,28 @@ def test_two_ranks_equal_one_process(tmp_path):
 
 def test_merged_extras_need_every_partition(tmp_path):
     """--merged-table / --merged-output are whole-run outputs: a context that owns a slice of the partitions
-    (one rank of a multi-process launch) must refuse them instead of writing a partial file."""
-    import ctypes
-
-    import pytest
-
-    from nomalise_kmers_multi_large_b200 import capi
-    from nomalise_kmers_multi_large_b200.pipeline import Pipeline
+    (one rank of a multi-process launch) must refuse them instead of writing a partial file.  Runs in its own
+    process: the emulation library exports the product's symbol names and must not share a process with it."""
     subprocess.run(["make", "-C", str(ROOT / "tests" / "emu")], check=True, capture_output=True)
-    lib = ctypes.CDLL(str(EMU_LIB))
-    capi._declare_engine(lib)
-    capi._declare_pipeline(lib)
-    for extra in ({"merged_table": True}, {"merged_output": True}):
-        with pytest.raises(capi.NkError) as err:
-            Pipeline(k=21, depth=16, partitions=4, memory_gb=1, out_dir=tmp_path, part_first=0, part_count=2, lib=lib, **extra)
-        assert "owns all 4 partitions" in str(err.value)
-    with Pipeline(k=21, depth=16, partitions=4, memory_gb=1, out_dir=tmp_path, merged_table=True, merged_output=True,
-                  lib=lib) as p:
-        assert p.totals()["engines"] >= 1
+    code = f"""
+import ctypes, sys
+sys.path.insert(0, {str(ROOT)!r})
+from nomalise_kmers_multi_large_b200 import capi
+from nomalise_kmers_multi_large_b200.pipeline import Pipeline
+lib = ctypes.CDLL({str(EMU_LIB)!r})
+capi._declare_engine(lib)
+capi._declare_pipeline(lib)
+for extra in ({{"merged_table": True}}, {{"merged_output": True}}):
+    try:
+        Pipeline(k=21, depth=16, partitions=4, memory_gb=1, out_dir={str(tmp_path)!r}, part_first=0, part_count=2, lib=lib, **extra)
+    except capi.NkError as e:
+        assert "owns all 4 partitions" in str(e), str(e)
+    else:
+        raise SystemExit("a partial context accepted " + str(extra))
+with Pipeline(k=21, depth=16, partitions=4, memory_gb=1, out_dir={str(tmp_path)!r}, merged_table=True, merged_output=True,
+              lib=lib) as p:
+    assert p.totals()["engines"] >= 1
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.stdout[-500:], r.stderr[-1500:])
