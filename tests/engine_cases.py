@@ -198,3 +198,14 @@ def run_shared_seed_case(lib, *, k=15, canonical=True, depth=3, cap0=4099, seed=
     finally:
         follower.close()
         lead.close()
+
+
+def random_case(rnd):
+    """One random engine configuration (tools/stress/stress_engine_emu.py and the randomised emu test share it)."""
+    k = rnd.choice([5, 7, 11, 15, 21, 25, 31])
+    return dict(seed=rnd.randrange(1 << 30), k=k, canonical=rnd.random() < 0.5, depth=rnd.choice([2, 3, 4, 6, 12, 40]),
+                coverage=rnd.choice([0.5, 0.9, 0.96, 1.0]), n_parts=rnd.choice([1, 2, 3, 5]),
+                cap0=rnd.choice([257, 1031, 4099, 16411, 65537]), genome_len=rnd.choice([400, 1500, 6000]),
+                n_seed_reads=rnd.choice([0, 20, 200]), steps=rnd.choice([1, 2, 4]), records_per_step=rnd.choice([5, 40, 150]),
+                paired=rnd.random() < 0.7, read_len=rnd.choice([(k, k + 3), (40, 120), (100, 160), (k, 300)]),
+                err=rnd.choice([0.0, 0.01, 0.05]))

@@ -51,3 +51,23 @@ def test_emulated_step_that_overfills_the_table(emu_lib, monkeypatch):
     info = ec.run_case(emu_lib, seed=126076854, k=7, canonical=False, depth=6, coverage=0.5, n_parts=1, cap0=257,
                        genome_len=6000, n_seed_reads=20, steps=4, records_per_step=40, paired=True, read_len=(100, 160), err=0.0)
     assert info["expansions"] >= 3
+
+
+def test_emulated_engine_random_configurations(emu_lib, monkeypatch):
+    """a fixed-seed slice of tools/stress/stress_engine_emu.py: random k, depth, capacities from 257 slots, partitions,
+    read shapes, list sizes and launch orders, each compared with the oracle after every step"""
+    import random
+    rnd = random.Random(20240823)
+    for i in range(120):
+        cfg = ec.random_case(rnd)
+        monkeypatch.setenv("NK_EMU_SEED", str(rnd.randrange(1 << 30)))
+        if i % 5 == 0:
+            monkeypatch.setenv("NKB200_OPEN_FRAC", "0.05")
+            monkeypatch.setenv("NKB200_PEND_FRAC", "0.1")
+        else:
+            monkeypatch.delenv("NKB200_OPEN_FRAC", raising=False)
+            monkeypatch.delenv("NKB200_PEND_FRAC", raising=False)
+        try:
+            ec.run_case(emu_lib, **cfg)
+        except Exception as e:
+            raise AssertionError(f"case {i} {cfg}: {e!r}") from e

@@ -9,13 +9,7 @@ lib = ctypes.CDLL(str(__import__('pathlib').Path(__file__).resolve().parents[2] 
 rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 t0 = time.time(); n = 0; fails = 0
 while time.time() - t0 < float(sys.argv[2] if len(sys.argv) > 2 else 600):
-    k = rnd.choice([5, 7, 11, 15, 21, 25, 31])
-    cfg = dict(seed=rnd.randrange(1 << 30), k=k, canonical=rnd.random() < 0.5, depth=rnd.choice([2, 3, 4, 6, 12, 40]),
-               coverage=rnd.choice([0.5, 0.9, 0.96, 1.0]), n_parts=rnd.choice([1, 2, 3, 5]),
-               cap0=rnd.choice([257, 1031, 4099, 16411, 65537]), genome_len=rnd.choice([400, 1500, 6000]),
-               n_seed_reads=rnd.choice([0, 20, 200]), steps=rnd.choice([1, 2, 4]), records_per_step=rnd.choice([5, 40, 150]),
-               paired=rnd.random() < 0.7, read_len=rnd.choice([(k, k + 3), (40, 120), (100, 160), (k, 300)]),
-               err=rnd.choice([0.0, 0.01, 0.05]))
+    cfg = ec.random_case(rnd)
     os.environ['NK_EMU_SEED'] = str(rnd.randrange(1 << 30))
     if rnd.random() < 0.2:
         os.environ['NKB200_OPEN_FRAC'] = '0.05'; os.environ['NKB200_PEND_FRAC'] = '0.1'
