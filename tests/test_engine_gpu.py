@@ -94,3 +94,17 @@ def test_codec_matches_oracle(cuda_lib, k, canonical):
         n = len(s) - k + 1
         assert np.array_equal(keys[a:a + n], want[a:a + n]), f"read {i} len {len(s)}"
     assert list(np.flatnonzero(inv)) == bad
+
+
+def test_engine_random_configurations(cuda_lib):
+    """the first 60 configurations of the randomised engine stress (tests/engine_cases.random_case, same fixed seed as
+    the emulation test): capacities from 257 slots, k 5..31, 1-5 partitions, ragged read lengths"""
+    import random
+    rnd = random.Random(20240823)
+    for i in range(60):
+        cfg = ec.random_case(rnd)
+        rnd.randrange(1 << 30)   # the emulation test draws its launch-order seed here; keep the streams aligned
+        try:
+            ec.run_case(cuda_lib, **cfg)
+        except Exception as e:
+            raise AssertionError(f"case {i} {cfg}: {e!r}") from e
