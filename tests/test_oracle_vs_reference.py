@@ -38,6 +38,9 @@ GOLDEN = [
      "b4ad25dfb3f1249abe8f3d8bdfbab7df", "eef52816ce26f8bfea442ace601b8a51", "ecebb87b6ee2ded0b8b74236076fa460"),
     (["-f", "a1.fastq", "-r", "a1.fastq", "-k", "15", "-d", "8", "-p", "2"], (7445, 5608, 1837, 248238), 15, 4, 2,
      "9454638bd82210f33b380ca86235cb07", "9454638bd82210f33b380ca86235cb07", None),
+    # mixed paired + single-end input lists (the second forward file has no mate)
+    (["-f", "a1.fastq", "a2.fastq", "-r", "b1.fastq", "-s", "-k", "15", "-d", "4", "-p", "2"], (19948, 13957, 5991, 924786), 15, 2, 2,
+     "de5059c8d6101832b462a81580232861", "090d6555b16001e594af630d7ef45212", None),
 ]
 
 
@@ -54,6 +57,17 @@ def test_oracle_reproduces_survey_goldens(tmp_path, g):
     assert cat_md5(tmp_path, "output_reverse", k, norm, parts) == md5r
     if md5d:
         assert cat_md5(tmp_path, "output_kmer", k, norm, parts, "tsv") == md5d
+
+
+@needs_fixtures
+def test_oracle_reproduces_survey_counts_k31_fasta_out(tmp_path):
+    """SURVEY 8 golden list: a1,b1 -k 31 -d 4 -p 2 -o fa -> 5000 / 3784 / 1216, max used 399,565 (the survey recorded no
+    md5 for this one; the files are compared with the reference binary in test_oracle_matches_reference_binary)."""
+    ol.build_oracle()
+    res = cc.run_cli(ol.ORACLE_CLI, ["-f", FIX / "a1.fastq", "-r", FIX / "b1.fastq", "-k", 31, "-d", 4, "-p", 2, "-o", "fa"], tmp_path)
+    assert res["rc"] == 0 and res["counters"][-1] == (5000, 3784, 1216, 399565)
+    first = (tmp_path / "output_forward.k31_norm2_thread0.fastq").read_bytes().split(b"\n", 2)
+    assert first[0].startswith(b">") and first[0].endswith(b"/1")   # fq -> fa appends /1, /2 (SURVEY known-answers)
 
 
 @needs_fixtures
