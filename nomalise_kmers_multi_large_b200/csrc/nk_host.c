@@ -575,6 +575,7 @@ typedef struct
 {
     int ordinal;
     int lead; /* index of the first engine on the same GPU: it alone builds the seed table */
+    pthread_mutex_t step_lock; /* of the lead engine: serialises a GPU's device steps when serial_steps is set */
     nkd_engine *eng;
     int n_parts;
     int *parts; /* indices into ctx->part */
@@ -598,6 +599,7 @@ struct nk_ctx
     int threads;
     uint32_t step_pairs, step_ops, step_bytes;
     int dev_group; /* partitions per device launch group, 0 = all resident partitions */
+    int serial_steps; /* NKB200_SERIAL_STEPS: one device step at a time per GPU (the host pipelines still overlap) */
     /* seeding */
     uint8_t *seed_seq[2]; /* two staging buffers: one is parsed into while the GPUs seed from the other */
     nkd_read *seed_reads[2];
@@ -764,6 +766,7 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         {
             c->dev[d].ordinal = cfg->devices ? cfg->devices[g] : g;
             c->dev[d].lead = first_eng[g];
+            pthread_mutex_init(&c->dev[d].step_lock, NULL);
             c->dev[d].parts = calloc((size_t)c->n_local, sizeof(int));
         }
     for (int i = 0; i < c->n_local; i++)
@@ -803,6 +806,7 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
     if (sp < 16)
         sp = 16;
     c->dev_group = getenv("NKB200_GROUP") ? atoi(getenv("NKB200_GROUP")) : 0;
+    c->serial_steps = getenv("NKB200_SERIAL_STEPS") != NULL;
     int grp = c->dev_group > 0 && c->dev_group < max_dev_parts ? c->dev_group : max_dev_parts;
     c->step_pairs = sp;
     c->step_ops = sp * 288u < 4096u ? 4096u : sp * 288u;
@@ -1583,11 +1587,18 @@ static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_inv
         int64_t inv = -1;
         if (recs)
         {
+            /* experiment knob: with serial_steps the engines of a GPU take turns, so that every kernel has the GPU
+             * to itself (clean per-kernel times) while the host stages of the pipelines still interleave */
+            pthread_mutex_t *turn = c->serial_steps ? &c->dev[dv->lead].step_lock : NULL;
+            if (turn)
+                pthread_mutex_lock(turn);
             rc = nkd_stage_segments(dv->eng, sb->seq, sb->segs, nseg, c->paired);
             if (!rc)
                 rc = nkd_run(dv->eng);
             if (!rc)
                 rc = nkd_fetch(dv->eng, sb->accept + sb->n_records, recs, &inv);
+            if (turn)
+                pthread_mutex_unlock(turn);
         }
         if (inv >= 0 && *first_invalid < 0)
             *first_invalid = (int64_t)sb->n_records + inv;
