@@ -44,7 +44,9 @@ enum
     NK_ENOMEM = -3,    /* host or device allocation failed (reference: exit 1, C:1073) */
     NK_EDATA = -4,     /* input is not DNA / malformed (reference: FATAL + exit 1, C:1418) */
     NK_EIO = -5,       /* cannot open / write a file */
-    NK_EINTERNAL = -6
+    NK_EINTERNAL = -6,
+    NK_EIRREGULAR = -7 /* nkd_stage_raw only: the text holds a NUL byte or a line of 1024+ chars, where read_line
+                          (C:394-409) splits differently; nothing was staged, use the host-parsed step instead */
 };
 
 /* ---------------------------------------------------------------- device engine */
@@ -88,6 +90,7 @@ typedef struct
     uint64_t max_step_reads; /* staging limits of one step */
     uint64_t max_step_bytes;
     uint64_t max_step_ops;
+    uint64_t max_raw_bytes; /* raw record text of one step (nkd_stage_raw); 0 = that path is not used */
 } nkd_config;
 
 /* init_hash_table (C:890): allocates the zeroed seed table of capacity0 slots and the step scratch */
@@ -129,6 +132,34 @@ typedef struct
     uint32_t part, ops;
 } nkd_segment;
 int nkd_stage_segments(nkd_engine *e, const uint8_t *seq_base, const nkd_segment *segs, int n_segs, int paired);
+/* A step handed over as raw record text (the worker loop's read_line x4 / x2 per mate, C:1605-1631, done on
+ * the device): per partition one window of the forward file and, when paired, one of the reverse file, each
+ * holding exactly n_records complete records (every line ended by '\n').  The windows lie in one page-locked
+ * step buffer at 16-byte aligned offsets; bytes between windows must be neither '\n' nor NUL.  The device finds
+ * the line ends, applies the length gate (C:1430-1443: a record with a mate shorter than k vanishes), numbers
+ * the operations and scores as nkd_run does.  At most one segment per partition. */
+typedef struct
+{
+    uint32_t part; /* engine-local partition */
+    uint32_t n_records;
+    uint32_t fwd_off, fwd_bytes;
+    uint32_t rev_off, rev_bytes;
+} nkd_raw_segment;
+/* what came of a segment: where its accepted records' text lies in the output buffer (forward file's
+ * records in order, then the reverse file's: the bytes process_thread_chunk_* prints, C:1649-1666, N->A in
+ * sequence lines, fastq_to_fasta for emit_mode 1) and its counters (C:1667, C:1672). */
+typedef struct
+{
+    uint64_t fwd_off, fwd_bytes, rev_off, rev_bytes;
+    uint64_t processed, printed;
+} nkd_raw_result;
+/* returns NK_EIRREGULAR (and stages nothing) when the text needs the byte-exact host parser */
+int nkd_stage_raw(nkd_engine *e, const uint8_t *raw, size_t raw_bytes, const nkd_raw_segment *segs, int n_segs,
+                  int paired, int lines_per_record);
+/* after nkd_run: emit_mode 0 = records verbatim (fq->fq, fa->fa), 1 = FASTQ records as FASTA (paired fq->fa),
+ * 2 = nothing (single-end fq->fa, C:1995-1999).  out = page-locked buffer of out_cap bytes. */
+int nkd_fetch_raw(nkd_engine *e, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results,
+                  int64_t *first_invalid);
 /* page-locked host memory for the staging buffers (cudaMallocHost / cudaFreeHost) */
 void *nkd_alloc_pinned(size_t bytes);
 void nkd_free_pinned(void *p);
@@ -252,6 +283,17 @@ int nk_process_planned(nk_ctx *c, const char *fwd, size_t fwd_size, const char *
                        const uint64_t *fwd_starts, const uint64_t *fwd_ends, const uint64_t *rev_starts,
                        const uint64_t *rev_ends);
 
+/* Planning for launches with one process per GPU: the byte ranges and the raw-text steps both start from
+ * the number of line ends in fixed chunks of the files (count_records_seqfile's scan, C:1302-1320).  Each
+ * rank counts a share of the chunks (nk_count_chunk_lines), the ranks exchange the counts, and every rank
+ * passes all of them to nk_process_indexed, which then does what nk_process_paired / nk_process_single do
+ * without scanning the files again.  counts has ceil(size / nk_line_chunk_bytes()) entries per file. */
+size_t nk_line_chunk_bytes(void);
+int nk_count_chunk_lines(const char *data, size_t size, size_t chunk_first, size_t n_chunks, uint32_t *counts,
+                         int threads);
+int nk_process_indexed(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size,
+                       const uint32_t *fwd_counts, const uint32_t *rev_counts);
+
 typedef struct
 {
     uint64_t processed, printed, skipped; /* reporting.total_* (C:198-205) */
@@ -266,6 +308,9 @@ typedef struct
     double class_ms[8]; /* see nkd_run_stats */
     uint64_t pend_events, open_ops;
     uint64_t engines; /* engines (stream + scratch + pipeline thread) of this context, over all its GPUs */
+    /* device steps by kind: raw record text parsed on the device (the default) / records parsed by the host
+     * (NKB200_HOST_PARSE=1, or text the device declined: NUL bytes, lines of 1024+ chars, a cut last record) */
+    uint64_t raw_steps, parsed_steps;
 } nk_totals;
 
 int nk_totals_get(nk_ctx *c, nk_totals *out);

@@ -20,7 +20,8 @@ LIB_PATH = PKG_DIR / "csrc" / "libnk_b200.so"
 CLI_PATH = PKG_DIR / "csrc" / "normalise_kmers_multi_large_b200"
 
 NK_OK = 0
-ERRORS = {-1: "NK_EINVAL", -2: "NK_ENODEVICE", -3: "NK_ENOMEM", -4: "NK_EDATA", -5: "NK_EIO", -6: "NK_EINTERNAL"}
+ERRORS = {-1: "NK_EINVAL", -2: "NK_ENODEVICE", -3: "NK_ENOMEM", -4: "NK_EDATA", -5: "NK_EIO", -6: "NK_EINTERNAL",
+          -7: "NK_EIRREGULAR"}
 
 
 class NkError(RuntimeError):
@@ -62,7 +63,18 @@ class EngineConfig(C.Structure):
     """nkd_config"""
     _fields_ = [("device", C.c_int), ("k", C.c_int), ("canonical", C.c_int), ("depth_per_part", C.c_int),
                 ("coverage", C.c_float), ("n_parts", C.c_int), ("capacity0", C.c_uint64),
-                ("max_step_reads", C.c_uint64), ("max_step_bytes", C.c_uint64), ("max_step_ops", C.c_uint64)]
+                ("max_step_reads", C.c_uint64), ("max_step_bytes", C.c_uint64), ("max_step_ops", C.c_uint64),
+                ("max_raw_bytes", C.c_uint64)]
+
+
+class RawSegment(C.Structure):
+    """nkd_raw_segment"""
+    _fields_ = [(n, C.c_uint32) for n in ("part", "n_records", "fwd_off", "fwd_bytes", "rev_off", "rev_bytes")]
+
+
+class RawResult(C.Structure):
+    """nkd_raw_result"""
+    _fields_ = [(n, C.c_uint64) for n in ("fwd_off", "fwd_bytes", "rev_off", "rev_bytes", "processed", "printed")]
 
 
 class PipelineConfig(C.Structure):
@@ -84,7 +96,8 @@ class Totals(C.Structure):
                 ("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("ops", C.c_uint64),
                 ("touches", C.c_uint64), ("probe_touches", C.c_uint64), ("slow_events", C.c_uint64),
                 ("expansions", C.c_uint64), ("class_ms", C.c_double * 8), ("pend_events", C.c_uint64),
-                ("open_ops", C.c_uint64), ("engines", C.c_uint64)]
+                ("open_ops", C.c_uint64), ("engines", C.c_uint64), ("raw_steps", C.c_uint64),
+                ("parsed_steps", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "class_ms" else getattr(self, n)) for n, _ in self._fields_}
@@ -94,12 +107,14 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_seed_export", "nkd_stage", "nkd_run", "nkd_fetch", "nkd_last_run_ms", "nkd_part_stats_get",
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
-                  "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from"]
+                  "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from",
+                  "nkd_stage_raw", "nkd_fetch_raw"]
 PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
                     "nk_partition_stats", "nk_finish", "nk_partition_ranges", "nk_count_records", "nk_main",
-                    "nk_plan_ranges", "nk_process_planned"]
+                    "nk_plan_ranges", "nk_process_planned", "nk_line_chunk_bytes", "nk_count_chunk_lines",
+                    "nk_process_indexed"]
 
 
 def _declare_engine(lib):
@@ -131,6 +146,8 @@ def _declare_engine(lib):
     lib.nkd_merge_add.argtypes = [vp, vp, vp, C.c_uint64]
     lib.nkd_merge_finish.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.nkd_device_count.restype = C.c_int
+    lib.nkd_stage_raw.argtypes = [vp, u8p, sz, C.POINTER(RawSegment), C.c_int, C.c_int, C.c_int]
+    lib.nkd_fetch_raw.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64)]
     return lib
 
 
@@ -157,6 +174,9 @@ def _declare_pipeline(lib):
     lib.nk_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     lib.nk_plan_ranges.argtypes = [vp, sz, vp, sz, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_char_p, sz]
     lib.nk_process_planned.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp]
+    lib.nk_line_chunk_bytes.restype = sz
+    lib.nk_count_chunk_lines.argtypes = [vp, sz, sz, sz, vp, C.c_int]
+    lib.nk_process_indexed.argtypes = [vp, vp, sz, vp, sz, vp, vp]
     return lib
 
 
@@ -205,10 +225,11 @@ class Engine:
     """One per-GPU engine (nkd_*)."""
 
     def __init__(self, k=15, canonical=False, depth_per_part=100, coverage=0.9, n_parts=1, capacity0=67108879,
-                 max_step_reads=1 << 16, max_step_bytes=1 << 24, max_step_ops=1 << 22, device=0, lib=None):
+                 max_step_reads=1 << 16, max_step_bytes=1 << 24, max_step_ops=1 << 22, device=0, lib=None,
+                 max_raw_bytes=1 << 25):
         self.lib = lib if lib is not None else load_library()
         self.cfg = EngineConfig(device, k, int(canonical), depth_per_part, coverage, n_parts, capacity0,
-                                max_step_reads, max_step_bytes, max_step_ops)
+                                max_step_reads, max_step_bytes, max_step_ops, max_raw_bytes)
         self.h = C.c_void_p()
         rc = self.lib.nkd_create(C.byref(self.cfg), C.byref(self.h))
         if rc != NK_OK:
@@ -282,6 +303,35 @@ class Engine:
         self.stage(buf, descs, paired)
         self.run()
         return self.fetch()
+
+    def step_raw(self, windows, paired, lines_per_record=4, emit_mode=0):
+        """nkd_stage_raw + nkd_run + nkd_fetch_raw.  windows = [(part, n_records, fwd_bytes, rev_bytes or None)];
+        returns ([(fwd_text, rev_text, processed, printed)], first_invalid)."""
+        segs = (RawSegment * len(windows))()
+        parts_bytes, at = [], 0
+        for i, (part, n, fwd, rev) in enumerate(windows):
+            segs[i].part, segs[i].n_records = part, n
+            for mate, text in enumerate((fwd, rev) if paired else (fwd,)):
+                if mate == 0:
+                    segs[i].fwd_off, segs[i].fwd_bytes = at, len(text)
+                else:
+                    segs[i].rev_off, segs[i].rev_bytes = at, len(text)
+                pad = (-len(text)) % 16
+                parts_bytes.append(text + b" " * pad)
+                at += len(text) + pad
+        raw = np.frombuffer(b"".join(parts_bytes), dtype=np.uint8).copy()
+        self._check(self.lib.nkd_stage_raw(self.h, raw.ctypes.data, raw.size, segs, len(windows), int(paired),
+                                           lines_per_record))
+        self._check(self.lib.nkd_run(self.h))
+        out = np.zeros(raw.size + 4 * sum(w[1] for w in windows) + 64, np.uint8)
+        res = (RawResult * len(windows))()
+        inv = C.c_int64(-1)
+        self._check(self.lib.nkd_fetch_raw(self.h, emit_mode, out.ctypes.data, out.size, res, C.byref(inv)))
+        got = []
+        for r in res:
+            got.append((out[r.fwd_off:r.fwd_off + r.fwd_bytes].tobytes(), out[r.rev_off:r.rev_off + r.rev_bytes].tobytes(),
+                        int(r.processed), int(r.printed)))
+        return got, inv.value
 
     def read_scores(self, n_reads):
         hi, tot = np.empty(n_reads, np.uint32), np.empty(n_reads, np.uint32)

@@ -39,6 +39,7 @@
 #define NK_HD static inline
 #endif
 
+#define NK_LINE_SPLIT 1024u /* read_line cuts a line after 1023 chars (C:139, C:397): lines this long are split */
 #define NK_TAG (1ull << 63)
 #define NK_TMAX 0x7FFFFFFFu
 #define NK_T_BITS 28 /* operations per partition per step < 2^28 (slow-path sort key budget) */
@@ -856,6 +857,8 @@ NK_HD void nk_decide_op(const NkRun &P, unsigned rec, int paired, float coverage
     int keep = nk_keep_mate(P.high[r0], P.total[r0], coverage);
     if (paired)
         keep = keep && nk_keep_mate(P.high[r0 + 1], P.total[r0 + 1], coverage);
+    if (P.reads[r0].len == 0)
+        keep = 2; /* raw-text steps: the record failed the length gate on the device and does not count (C:1430-1443) */
     accept[rec] = (unsigned char)keep;
 }
 
@@ -924,5 +927,223 @@ NK_HD void nk_dump_format(unsigned long long key, long long val, int k, char *ou
 }
 
 #define NK_DUMP_TILE 512 /* entries whose text one block assembles in shared memory per pass */
+
+/* ---------------------------------------------------------------- raw record text on the device
+ *
+ * The host hands a step over as raw FASTQ/FASTA bytes: per partition one window of the forward file and one of
+ * the reverse file holding the same number of complete records (process_thread_chunk_*'s read_line x4/x2 loop,
+ * C:1605-1631, C:394-409).  The device finds the line ends, derives every record's sequence line, applies the
+ * length gate (C:1430-1443), scores, and assembles the accepted records' output text (C:1649-1666, C:852-876)
+ * so that the host only copies bytes in and write()s bytes out.  A window with a NUL byte or a line of 1024+
+ * chars (where read_line would split differently) is reported back and that work goes through the host parser. */
+
+struct NkRawWin /* device copy of one nkd_raw_segment */
+{
+    unsigned f_off, f_bytes, r_off, r_bytes; /* byte ranges in the step's raw buffer (r_bytes = 0: single-end) */
+    unsigned n_records, part;
+    unsigned f_line0, r_line0; /* index of the window's first line end in the step-wide list */
+    unsigned rec0;             /* first record in the step's record numbering */
+    unsigned out0;             /* first entry of the window in the output-length array: forward records, then reverse */
+    unsigned pad0, pad1;
+};
+
+#define NK_RAW_TILE 4096u /* bytes of raw text whose line ends one block counts / lists per pass */
+#define NK_RAW_NUL 1u     /* a NUL byte inside the step's text */
+#define NK_RAW_LONG 2u    /* a line of NK_LINE_SPLIT or more chars */
+#define NK_RAW_SHAPE 4u   /* a window does not end on the line end of its last record */
+
+enum
+{
+    NK_EMIT_VERBATIM = 0, /* fq->fq, fa->fa: the record's lines, N->A in the sequence line (C:1426, C:1661-1665) */
+    NK_EMIT_FASTA = 1,    /* fq->fa, paired: fastq_to_fasta (C:852-876) */
+    NK_EMIT_NONE = 2      /* fq->fa, single-end: counted as printed, nothing written (C:1995-1999) */
+};
+
+struct NkRaw
+{
+    const unsigned char *raw;
+    unsigned raw_bytes; /* multiple of 16 */
+    const NkRawWin *wins;
+    unsigned n_wins, n_records, stride /* mates per record */, per /* lines per record */;
+    int k, emit_mode;
+    unsigned *tile; /* line ends per tile, then their exclusive scan; [n_tiles] = total */
+    unsigned *nlpos;
+    unsigned nlpos_cap;
+    NkRead *reads;
+    unsigned *nops, *opscan; /* operations per read and their exclusive scan ([n_reads] = total) */
+    unsigned *t_out;         /* operations per window (= per partition of the step) */
+    unsigned *flags;         /* NK_RAW_* */
+    const unsigned char *accept;
+    unsigned *outlen, *outoff; /* per (window, mate, record) and its exclusive scan */
+    unsigned char *out;
+    unsigned long long *summary; /* per window: fwd offset, fwd bytes, rev offset, rev bytes, processed, printed */
+    unsigned inv_rec;            /* first record with a non-DNA byte (NK_TMAX = none) */
+};
+
+/* window of record i: the last window whose rec0 <= i */
+NK_HD unsigned nk_raw_window_of(const NkRaw &R, unsigned i)
+{
+    unsigned lo = 0, hi = R.n_wins - 1;
+    while (lo < hi)
+    {
+        unsigned mid = (lo + hi + 1) >> 1;
+        if (R.wins[mid].rec0 <= i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+struct NkRawRec /* one mate of one record, as byte offsets into the raw buffer */
+{
+    unsigned start, end; /* first byte, one past its last line end */
+    unsigned hdr_len, seq_off, seq_len;
+    unsigned longest; /* longest of its lines */
+};
+
+NK_HD NkRawRec nk_raw_record(const NkRaw &R, const NkRawWin &w, unsigned r, int mate)
+{
+    const unsigned line0 = (mate ? w.r_line0 : w.f_line0) + R.per * r;
+    const unsigned woff = mate ? w.r_off : w.f_off;
+    NkRawRec x;
+    x.start = r == 0 ? woff : R.nlpos[line0 - 1] + 1u;
+    const unsigned e0 = R.nlpos[line0], e1 = R.nlpos[line0 + 1];
+    x.hdr_len = e0 - x.start;
+    x.seq_off = e0 + 1u;
+    x.seq_len = e1 - e0 - 1u;
+    x.longest = x.hdr_len > x.seq_len ? x.hdr_len : x.seq_len;
+    unsigned prev = e1;
+    for (unsigned l = 2; l < R.per; l++)
+    {
+        unsigned e = R.nlpos[line0 + l];
+        if (e - prev - 1u > x.longest)
+            x.longest = e - prev - 1u;
+        prev = e;
+    }
+    x.end = prev + 1u;
+    return x;
+}
+
+/* record i of the step: sequence lines of its mates, the length gate, operations per read */
+NK_HD void nk_raw_record_op(const NkRaw &R, unsigned i)
+{
+    const unsigned wi = nk_raw_window_of(R, i);
+    const NkRawWin w = R.wins[wi];
+    const unsigned r = i - w.rec0;
+    NkRawRec m[2];
+    bool kept = true;
+    unsigned flags = 0;
+    for (unsigned s = 0; s < R.stride; s++)
+    {
+        m[s] = nk_raw_record(R, w, r, (int)s);
+        if (m[s].longest >= NK_LINE_SPLIT)
+            flags |= NK_RAW_LONG;
+        if ((int)m[s].seq_len < R.k)
+            kept = false; /* either mate shorter than K: the record vanishes, C:1430-1443 */
+        if (r + 1 == w.n_records && m[s].end != (s ? w.r_off + w.r_bytes : w.f_off + w.f_bytes))
+            flags |= NK_RAW_SHAPE;
+    }
+    if (flags)
+        nk_red_or32(R.flags, flags);
+    for (unsigned s = 0; s < R.stride; s++)
+    {
+        NkRead rd;
+        rd.seq_off = m[s].seq_off;
+        rd.op_base = 0;
+        rd.len = (unsigned short)(kept && !(flags & NK_RAW_LONG) ? m[s].seq_len : 0u);
+        rd.part = (unsigned short)w.part;
+        rd.reserved = 0;
+        R.reads[R.stride * i + s] = rd;
+        R.nops[R.stride * i + s] = rd.len ? (unsigned)rd.len - (unsigned)R.k + 1u : 0u;
+    }
+}
+
+/* read j: its first operation's number inside its partition's step; the window's first read reports the total */
+NK_HD void nk_raw_opbase_op(const NkRaw &R, unsigned j)
+{
+    const unsigned i = j / R.stride;
+    const unsigned wi = nk_raw_window_of(R, i);
+    const NkRawWin w = R.wins[wi];
+    const unsigned first = R.stride * w.rec0;
+    R.reads[j].op_base = R.opscan[j] - R.opscan[first];
+    if (j == first)
+        R.t_out[wi] = R.opscan[first + R.stride * w.n_records] - R.opscan[first];
+}
+
+/* output bytes of entry e = (window, mate, record); returns the window through wi and whether the record counts */
+NK_HD unsigned nk_emit_len_op(const NkRaw &R, unsigned e, unsigned &wi, unsigned &mate, unsigned &rec, int &counted,
+                              int &printed)
+{
+    unsigned lo = 0, hi = R.n_wins - 1; /* last window whose out0 <= e */
+    while (lo < hi)
+    {
+        unsigned mid = (lo + hi + 1) >> 1;
+        if (R.wins[mid].out0 <= e)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    wi = lo;
+    const NkRawWin w = R.wins[wi];
+    unsigned off = e - w.out0;
+    mate = off >= w.n_records ? 1u : 0u;
+    const unsigned r = off - mate * w.n_records;
+    rec = w.rec0 + r;
+    const unsigned char a = R.accept[rec];
+    /* the reference stops at the first non-DNA record (C:1445-1454): later records of that partition do not count */
+    const bool cut = R.inv_rec >= w.rec0 && R.inv_rec < w.rec0 + w.n_records && rec >= R.inv_rec;
+    counted = (a != 2 && !cut) ? 1 : 0;
+    printed = (a == 1 && !cut) ? 1 : 0;
+    if (!printed || R.emit_mode == NK_EMIT_NONE)
+        return 0;
+    const NkRawRec x = nk_raw_record(R, w, r, (int)mate);
+    if (R.emit_mode == NK_EMIT_VERBATIM)
+        return x.end - x.start;
+    /* ">" + header[1:] + "/1"|"/2" unless it already ends so + "\n" + sequence + "\n" */
+    const unsigned char *h = R.raw + x.start;
+    const unsigned char tag = mate ? '2' : '1';
+    const bool has = x.hdr_len >= 2 && h[x.hdr_len - 2] == '/' && h[x.hdr_len - 1] == tag;
+    return 1u + (x.hdr_len > 1 ? x.hdr_len - 1u : 0u) + (has ? 0u : 2u) + 1u + x.seq_len + 1u;
+}
+
+/* byte b of an entry's output text */
+NK_HD unsigned char nk_emit_byte(const NkRaw &R, const NkRawRec &x, unsigned mate, unsigned b, unsigned len)
+{
+    if (R.emit_mode == NK_EMIT_VERBATIM)
+    {
+        const unsigned p = x.start + b;
+        unsigned char c = R.raw[p];
+        return (c == 'N' && p >= x.seq_off && p < x.seq_off + x.seq_len) ? (unsigned char)'A' : c;
+    }
+    const unsigned hl = x.hdr_len > 1 ? x.hdr_len - 1u : 0u;
+    const unsigned seq_at = len - x.seq_len - 1u; /* the sequence and its line end close the text */
+    if (b == 0)
+        return '>';
+    if (b <= hl)
+        return R.raw[x.start + b];
+    if (b >= seq_at)
+    {
+        if (b == len - 1u)
+            return '\n';
+        unsigned char c = R.raw[x.seq_off + (b - seq_at)];
+        return c == 'N' ? (unsigned char)'A' : c;
+    }
+    if (b == seq_at - 1u)
+        return '\n';
+    return (b == hl + 1u) ? (unsigned char)'/' : (unsigned char)(mate ? '2' : '1'); /* the two suffix bytes */
+}
+
+/* per window: where its forward / reverse text lies in the step's output and what it counted */
+NK_HD void nk_emit_summary_op(const NkRaw &R, unsigned wi)
+{
+    const NkRawWin w = R.wins[wi];
+    unsigned long long *s = R.summary + 6u * wi;
+    const unsigned f0 = R.outoff[w.out0], f1 = R.outoff[w.out0 + w.n_records];
+    s[0] = f0;
+    s[1] = f1 - f0;
+    s[2] = f1;
+    s[3] = R.stride == 2 ? R.outoff[w.out0 + 2u * w.n_records] - f1 : 0u;
+}
 
 #endif /* NK_CORE_H */

@@ -121,6 +121,8 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
         const uint4 rraw = __ldg(reinterpret_cast<const uint4 *>(P.reads + r));
         const unsigned seq_off = rraw.x, op_base = rraw.y, len = rraw.z & 0xFFFFu;
         const unsigned part = one_part ? 0u : (rraw.z >> 16);
+        if (len == 0)
+            continue; /* raw-text steps: a record that failed the length gate keeps its place but has no windows */
         const NkPart pd = P.parts[part];
         const int nwin = (int)len - P.k + 1;
         if (op_base + (unsigned)nwin <= pd.lo || op_base >= pd.hi)
@@ -137,13 +139,41 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
             nk_chunk_rotate(P, NK_LIST_OPEN, &P.ctr->n_open, P.open_cap);
         }
         const unsigned nchunks = (len + 15u) >> 4;
+        /* parsed steps stage every sequence at a 16-byte boundary; in raw-text steps it starts wherever its line
+         * starts, and a lane assembles its 16 bases from the two aligned chunks they straddle (shift is warp-uniform) */
+        const unsigned shift = seq_off & 15u;
+        const uint4 *chunks = reinterpret_cast<const uint4 *>(P.seq + (seq_off - shift));
         unsigned bad = 0;
         for (unsigned c = lane; c < nchunks + 2u; c += 32u)
         {
             unsigned w = 0;
             if (c < nchunks)
             {
-                uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.seq + seq_off) + c);
+                uint4 v = __ldg(chunks + c);
+                if (shift)
+                {
+                    const uint4 u = __ldg(chunks + c + 1);
+                    const unsigned sh = (shift & 3u) * 8u;
+                    unsigned a0, a1, a2, a3, a4;
+                    switch (shift >> 2)
+                    {
+                    case 0:
+                        a0 = v.x, a1 = v.y, a2 = v.z, a3 = v.w, a4 = u.x;
+                        break;
+                    case 1:
+                        a0 = v.y, a1 = v.z, a2 = v.w, a3 = u.x, a4 = u.y;
+                        break;
+                    case 2:
+                        a0 = v.z, a1 = v.w, a2 = u.x, a3 = u.y, a4 = u.z;
+                        break;
+                    default:
+                        a0 = v.w, a1 = u.x, a2 = u.y, a3 = u.z, a4 = u.w;
+                    }
+                    v.x = __funnelshift_r(a0, a1, sh);
+                    v.y = __funnelshift_r(a1, a2, sh);
+                    v.z = __funnelshift_r(a2, a3, sh);
+                    v.w = __funnelshift_r(a3, a4, sh);
+                }
                 w = nk_pack16(v, (int)len - 16 * (int)c, bad);
             }
             words[c] = w;
@@ -474,6 +504,153 @@ __global__ void __launch_bounds__(256) k_dump_pairs(const NkDumpSrc src, unsigne
     }
 }
 
+
+/* ------------------------------------------------------------------ raw record text (C:1605-1631, C:394-409 on the device) */
+
+/* newline / NUL bits of 16 bytes: bit i of the result is byte i */
+__device__ __forceinline__ unsigned nk_eq_mask16(uint4 v, unsigned pattern)
+{
+    unsigned in[4] = {v.x, v.y, v.z, v.w}, m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        unsigned t = __vcmpeq4(in[j], pattern) & 0x08040201u;
+        m |= ((t | (t >> 8) | (t >> 16) | (t >> 24)) & 0xFu) << (4 * j);
+    }
+    return m;
+}
+
+/* pass 1: line ends per tile of NK_RAW_TILE bytes; NUL bytes anywhere are reported */
+__global__ void __launch_bounds__(256) k_raw_count(const NkRaw R, unsigned n_tiles)
+{
+    typedef cub::BlockReduce<unsigned, 256> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const unsigned at = tile * NK_RAW_TILE + threadIdx.x * 16u;
+        unsigned c = 0;
+        if (at < R.raw_bytes)
+        {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(R.raw + at));
+            c = __popc(nk_eq_mask16(v, 0x0A0A0A0Au));
+            if (nk_eq_mask16(v, 0u))
+                atomicOr(R.flags, NK_RAW_NUL);
+        }
+        unsigned sum = Reduce(tmp).Sum(c);
+        if (threadIdx.x == 0)
+            R.tile[tile] = sum;
+        __syncthreads();
+    }
+}
+
+/* pass 2: the positions, in order, at the tile's scanned offset */
+__global__ void __launch_bounds__(256) k_raw_positions(const NkRaw R, unsigned n_tiles)
+{
+    typedef cub::BlockScan<unsigned, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        R.flags[1] = R.tile[n_tiles];
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    {
+        const unsigned at = tile * NK_RAW_TILE + threadIdx.x * 16u;
+        unsigned m = 0;
+        if (at < R.raw_bytes)
+            m = nk_eq_mask16(__ldg(reinterpret_cast<const uint4 *>(R.raw + at)), 0x0A0A0A0Au);
+        unsigned before;
+        Scan(tmp).ExclusiveSum((unsigned)__popc(m), before);
+        unsigned idx = R.tile[tile] + before;
+        while (m)
+        {
+            unsigned b = __ffs(m) - 1u;
+            m &= m - 1u;
+            if (idx < R.nlpos_cap)
+                R.nlpos[idx] = at + b;
+            idx++;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_raw_records(const NkRaw R)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < R.n_records; i += gridDim.x * blockDim.x)
+        nk_raw_record_op(R, i);
+}
+__global__ void __launch_bounds__(256) k_raw_opbase(const NkRaw R)
+{
+    const unsigned n = R.n_records * R.stride;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        nk_raw_opbase_op(R, j);
+}
+
+/* output bytes per (window, mate, record) and the windows' processed / printed counters (C:1667, C:1672) */
+__global__ void __launch_bounds__(256) k_emit_measure(const NkRaw R, unsigned n_out)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    for (unsigned base = (blockIdx.x * 8u + (threadIdx.x >> 5)) * 32u; base < n_out; base += gridDim.x * 256u)
+    {
+        const unsigned e = base + lane;
+        unsigned wi = 0xFFFFFFFFu, mate = 0, rec = 0, len = 0;
+        int counted = 0, printed = 0;
+        if (e < n_out)
+        {
+            len = nk_emit_len_op(R, e, wi, mate, rec, counted, printed);
+            R.outlen[e] = len;
+            if (mate)
+                counted = printed = 0; /* a record counts once */
+        }
+        const unsigned w0 = __shfl_sync(0xFFFFFFFFu, wi, 0);
+        if (__all_sync(0xFFFFFFFFu, wi == w0))
+        {
+            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)counted), p = __reduce_add_sync(0xFFFFFFFFu, (unsigned)printed);
+            if (lane == 0 && w0 != 0xFFFFFFFFu)
+            {
+                if (c)
+                    atomicAdd(&R.summary[6u * w0 + 4u], (unsigned long long)c);
+                if (p)
+                    atomicAdd(&R.summary[6u * w0 + 5u], (unsigned long long)p);
+            }
+        }
+        else if (wi != 0xFFFFFFFFu)
+        {
+            if (counted)
+                atomicAdd(&R.summary[6u * wi + 4u], 1ull);
+            if (printed)
+                atomicAdd(&R.summary[6u * wi + 5u], 1ull);
+        }
+    }
+}
+
+/* warp per entry: the accepted record's text at its scanned offset */
+__global__ void __launch_bounds__(256) k_emit_copy(const NkRaw R, unsigned n_out)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    for (unsigned e = blockIdx.x * 8u + (threadIdx.x >> 5); e < n_out; e += gridDim.x * 8u)
+    {
+        const unsigned o = R.outoff[e], len = R.outoff[e + 1] - o;
+        if (len == 0)
+            continue;
+        unsigned lo = 0, hi = R.n_wins - 1;
+        while (lo < hi)
+        {
+            unsigned mid = (lo + hi + 1) >> 1;
+            if (R.wins[mid].out0 <= e)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const NkRawWin w = R.wins[lo];
+        const unsigned off = e - w.out0, mate = off >= w.n_records ? 1u : 0u;
+        const NkRawRec x = nk_raw_record(R, w, off - mate * w.n_records, (int)mate);
+        for (unsigned b = lane; b < len; b += 32u)
+            R.out[o + b] = nk_emit_byte(R, x, mate, b, len);
+    }
+}
+__global__ void k_emit_summary(const NkRaw R)
+{
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < R.n_wins; w += gridDim.x * blockDim.x)
+        nk_emit_summary_op(R, w);
+}
+
 /* ------------------------------------------------------------------ backend */
 
 struct CudaBackend
@@ -565,6 +742,8 @@ struct CudaBackend
         sync_ev = nullptr;
         if (sort_tmp)
             cudaFreeAsync(sort_tmp, stream);
+        if (scan_tmp)
+            cudaFreeAsync(scan_tmp, stream);
         if (stream)
         {
             cudaStreamSynchronize(stream);
@@ -804,6 +983,57 @@ struct CudaBackend
     {
         if (n_records)
             k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept), launches++;
+    }
+
+    /* raw record text: line ends -> records -> operation numbering */
+    void *scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    bool prepare_scan(size_t n, std::string &err)
+    {
+        size_t bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, (unsigned *)nullptr, (unsigned *)nullptr, (long long)n, stream);
+        if (bytes <= scan_tmp_bytes)
+            return true;
+        release(scan_tmp);
+        scan_tmp = alloc(bytes);
+        scan_tmp_bytes = scan_tmp ? bytes : 0;
+        if (!scan_tmp)
+            err = "cannot allocate scan scratch";
+        return scan_tmp != nullptr;
+    }
+    void scan_u32(unsigned *data, size_t n)
+    {
+        size_t bytes = scan_tmp_bytes;
+        ok(cub::DeviceScan::ExclusiveSum(scan_tmp, bytes, data, data, (long long)n, stream), "exclusive scan");
+        launches++;
+    }
+    void scan_u32(const unsigned *in, unsigned *out, size_t n)
+    {
+        size_t bytes = scan_tmp_bytes;
+        ok(cub::DeviceScan::ExclusiveSum(scan_tmp, bytes, in, out, (long long)n, stream), "exclusive scan");
+        launches++;
+    }
+    void raw_index(const NkRaw &R)
+    {
+        const unsigned n_tiles = (R.raw_bytes + NK_RAW_TILE - 1) / NK_RAW_TILE, n_reads = R.n_records * R.stride;
+        zero(R.tile + n_tiles, sizeof(unsigned));
+        k_raw_count<<<grid_for(n_tiles, 1), 256, 0, stream>>>(R, n_tiles), launches++;
+        scan_u32(R.tile, (size_t)n_tiles + 1);
+        k_raw_positions<<<grid_for(n_tiles, 1), 256, 0, stream>>>(R, n_tiles), launches++;
+        zero(R.nops + n_reads, sizeof(unsigned));
+        k_raw_records<<<grid_for(R.n_records, 256), 256, 0, stream>>>(R), launches++;
+        scan_u32(R.nops, R.opscan, (size_t)n_reads + 1);
+        k_raw_opbase<<<grid_for(n_reads, 256), 256, 0, stream>>>(R), launches++;
+    }
+    /* accepted records' text, forward then reverse per window, and the windows' counters */
+    void raw_emit(const NkRaw &R)
+    {
+        const unsigned n_out = R.n_records * R.stride;
+        zero(R.outlen + n_out, sizeof(unsigned));
+        k_emit_measure<<<grid_for(n_out, 256), 256, 0, stream>>>(R, n_out), launches++;
+        scan_u32(R.outlen, R.outoff, (size_t)n_out + 1);
+        k_emit_copy<<<grid_for(n_out, 8), 256, 0, stream>>>(R, n_out), launches++;
+        k_emit_summary<<<1, 256, 0, stream>>>(R), launches++;
     }
 
     /* table dump: tile sizes, their exclusive scan in place (tile[n_tiles] = total), then the writers */

@@ -102,6 +102,17 @@ int nkd_fetch(nkd_engine *h, uint8_t *accept, size_t n_records, int64_t *first_i
     h->e.be.enter();
     return nkd_done(h, h->e.fetch(accept, n_records, first_invalid));
 }
+int nkd_stage_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes, const nkd_raw_segment *segs, int n_segs, int paired,
+                  int lines_per_record)
+{
+    h->e.be.enter();
+    return nkd_done(h, h->e.stage_raw(raw, raw_bytes, segs, n_segs, paired, lines_per_record));
+}
+int nkd_fetch_raw(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid)
+{
+    h->e.be.enter();
+    return nkd_done(h, h->e.fetch_raw(emit_mode, out, out_cap, results, first_invalid));
+}
 int nkd_last_run_ms(nkd_engine *h, float *total_ms, float *probe_ms)
 {
     if (total_ms)

@@ -49,31 +49,93 @@ static double nk_now(void)
 }
 
 typedef void (*nk_task_fn)(int index, void *arg);
-typedef struct
+
+/* Persistent worker pool shared by every context of the process: the pipeline stages hand it index ranges many
+ * times per step, and creating / joining threads for each of them (round 1) cost more than some of the stages.
+ * A caller works on its own job too, so nested and concurrent jobs always make progress. */
+typedef struct nk_job
 {
     nk_task_fn fn;
     void *arg;
-    int n;
-    int next;
-    pthread_mutex_t mu;
-} nk_pf;
+    int n, limit;  /* tasks; most workers that may serve it besides the caller */
+    int next, done, helpers;
+    struct nk_job *link;
+} nk_job;
 
-static void *nk_pf_worker(void *a)
+static struct
 {
-    nk_pf *pf = a;
+    pthread_mutex_t mu;
+    pthread_cond_t work, finished;
+    nk_job *jobs;
+    int n_threads, started;
+} nk_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0};
+
+static int nk_host_threads(void);
+
+static void nk_job_work(nk_job *j)
+{
     for (;;)
     {
-        pthread_mutex_lock(&pf->mu);
-        int i = pf->next++;
-        pthread_mutex_unlock(&pf->mu);
-        if (i >= pf->n)
+        int i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->n)
             break;
-        pf->fn(i, pf->arg);
+        j->fn(i, j->arg);
+        if (__atomic_add_fetch(&j->done, 1, __ATOMIC_ACQ_REL) == j->n)
+        {
+            pthread_mutex_lock(&nk_pool.mu);
+            pthread_cond_broadcast(&nk_pool.finished);
+            pthread_mutex_unlock(&nk_pool.mu);
+        }
+    }
+}
+
+static void *nk_pool_worker(void *unused)
+{
+    (void)unused;
+    pthread_mutex_lock(&nk_pool.mu);
+    for (;;)
+    {
+        nk_job *j = nk_pool.jobs;
+        while (j && (__atomic_load_n(&j->next, __ATOMIC_RELAXED) >= j->n || j->helpers >= j->limit))
+            j = j->link;
+        if (!j)
+        {
+            pthread_cond_wait(&nk_pool.work, &nk_pool.mu);
+            continue;
+        }
+        j->helpers++;
+        pthread_mutex_unlock(&nk_pool.mu);
+        nk_job_work(j);
+        pthread_mutex_lock(&nk_pool.mu);
+        j->helpers--;
+        pthread_cond_broadcast(&nk_pool.finished); /* the owner may be waiting for its helpers to let go */
     }
     return NULL;
 }
 
-/* run fn(0..n-1) on up to nthreads threads */
+static void nk_pool_start(void)
+{
+    pthread_mutex_lock(&nk_pool.mu);
+    if (!nk_pool.started)
+    {
+        nk_pool.started = 1;
+        int want = nk_host_threads();
+        if (want > 256)
+            want = 256;
+        for (int t = 0; t < want; t++)
+        {
+            pthread_t th;
+            if (pthread_create(&th, NULL, nk_pool_worker, NULL) == 0)
+            {
+                pthread_detach(th);
+                nk_pool.n_threads++;
+            }
+        }
+    }
+    pthread_mutex_unlock(&nk_pool.mu);
+}
+
+/* run fn(0..n-1) on up to nthreads threads (the caller is one of them) */
 static void nk_parallel_for(int n, int nthreads, nk_task_fn fn, void *arg)
 {
     if (nthreads > n)
@@ -84,17 +146,31 @@ static void nk_parallel_for(int n, int nthreads, nk_task_fn fn, void *arg)
             fn(i, arg);
         return;
     }
-    nk_pf pf = {fn, arg, n, 0, PTHREAD_MUTEX_INITIALIZER};
-    pthread_t th[64];
-    if (nthreads > 64)
-        nthreads = 64;
-    int started = 0;
-    for (int t = 0; t < nthreads - 1; t++)
-        if (pthread_create(&th[started], NULL, nk_pf_worker, &pf) == 0)
-            started++;
-    nk_pf_worker(&pf);
-    for (int t = 0; t < started; t++)
-        pthread_join(th[t], NULL);
+    nk_pool_start();
+    nk_job job = {fn, arg, n, nthreads - 1, 0, 0, 0, NULL};
+    pthread_mutex_lock(&nk_pool.mu);
+    job.link = nk_pool.jobs;
+    nk_pool.jobs = &job;
+    pthread_cond_broadcast(&nk_pool.work);
+    pthread_mutex_unlock(&nk_pool.mu);
+    nk_job_work(&job);
+    pthread_mutex_lock(&nk_pool.mu);
+    while (__atomic_load_n(&job.done, __ATOMIC_ACQUIRE) < n || job.helpers > 0)
+        pthread_cond_wait(&nk_pool.finished, &nk_pool.mu);
+    for (nk_job **pp = &nk_pool.jobs; *pp; pp = &(*pp)->link)
+        if (*pp == &job)
+        {
+            *pp = job.link;
+            break;
+        }
+    pthread_mutex_unlock(&nk_pool.mu);
+}
+
+/* boolean environment switches: unset, empty and "0" mean off */
+static int nk_env_on(const char *name)
+{
+    const char *s = getenv(name);
+    return s && *s && strcmp(s, "0") != 0;
 }
 
 static int nk_host_threads(void)
@@ -354,36 +430,63 @@ static inline size_t nk_nliter_next(nk_nliter *it)
     }
 }
 
-/* per-file line index: newline counts of fixed chunks, built on all host cores */
-#define NK_LI_CHUNK ((size_t)4 << 20)
+/* per-file line index: newline counts of fixed chunks, built on all host cores.  The partitioner looks up
+ * "the n-th line end after this offset" in it (C:1265-1300), and so does the raw-text pipeline when it cuts a
+ * partition's byte range into steps of whole records. */
+#define NK_LI_CHUNK ((size_t)256 << 10)
 typedef struct
 {
     const nk_buf *f;
-    int nchunks;
-    uint64_t *cum; /* cum[i] = newlines in chunks [0, i) */
+    int nchunks;       /* chunks of the whole file */
+    int c_lo, c_hi;    /* chunks that were counted: offsets outside [c_lo, c_hi) * NK_LI_CHUNK cannot be looked up */
+    uint64_t *cum;     /* cum[i] = newlines in chunks [c_lo, i) for c_lo <= i <= c_hi */
 } nk_lineidx;
 
 static void nk_lineidx_task(int i, void *a)
 {
     nk_lineidx *li = a;
-    size_t lo = (size_t)i * NK_LI_CHUNK, hi = lo + NK_LI_CHUNK;
+    int c = li->c_lo + i;
+    size_t lo = (size_t)c * NK_LI_CHUNK, hi = lo + NK_LI_CHUNK;
     if (hi > li->f->size)
         hi = li->f->size;
-    li->cum[i + 1] = nk_count_newlines(li->f->data + lo, hi - lo);
+    li->cum[c + 1] = nk_count_newlines(li->f->data + lo, hi - lo);
 }
 
-static void nk_lineidx_build_n(nk_lineidx *li, const nk_buf *f, int threads);
-static void nk_lineidx_build(nk_lineidx *li, const nk_buf *f) { nk_lineidx_build_n(li, f, nk_host_threads()); }
-static void nk_lineidx_build_n(nk_lineidx *li, const nk_buf *f, int threads)
+/* counts of the chunks that overlap [byte_lo, byte_hi) */
+static void nk_lineidx_build_range(nk_lineidx *li, const nk_buf *f, int threads, size_t byte_lo, size_t byte_hi)
 {
     if (!nk_mask64)
         nk_mask64 = nk_mask64_pick();
     li->f = f;
     li->nchunks = (int)((f->size + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
-    li->cum = calloc((size_t)li->nchunks + 1, sizeof(uint64_t));
-    nk_parallel_for(li->nchunks, threads, nk_lineidx_task, li);
-    for (int i = 0; i < li->nchunks; i++)
+    if (byte_hi > f->size)
+        byte_hi = f->size;
+    li->c_lo = (int)(byte_lo / NK_LI_CHUNK);
+    li->c_hi = (int)((byte_hi + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
+    if (li->c_hi > li->nchunks)
+        li->c_hi = li->nchunks;
+    if (li->c_lo > li->c_hi)
+        li->c_lo = li->c_hi;
+    li->cum = calloc((size_t)li->nchunks + 2, sizeof(uint64_t));
+    nk_parallel_for(li->c_hi - li->c_lo, threads, nk_lineidx_task, li);
+    li->cum[li->c_lo] = 0;
+    for (int i = li->c_lo; i < li->c_hi; i++)
         li->cum[i + 1] += li->cum[i];
+}
+static void nk_lineidx_build_n(nk_lineidx *li, const nk_buf *f, int threads) { nk_lineidx_build_range(li, f, threads, 0, f->size); }
+static void nk_lineidx_build(nk_lineidx *li, const nk_buf *f) { nk_lineidx_build_n(li, f, nk_host_threads()); }
+
+/* the same index from per-chunk counts somebody else made (nk_count_chunk_lines: ranks of a multi-process
+ * launch count a share of the chunks each and exchange the counts) */
+static void nk_lineidx_from_counts(nk_lineidx *li, const nk_buf *f, const uint32_t *counts)
+{
+    li->f = f;
+    li->nchunks = (int)((f->size + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
+    li->c_lo = 0;
+    li->c_hi = li->nchunks;
+    li->cum = calloc((size_t)li->nchunks + 2, sizeof(uint64_t));
+    for (int i = 0; i < li->nchunks; i++)
+        li->cum[i + 1] = li->cum[i] + counts[i];
 }
 
 static void nk_lineidx_free(nk_lineidx *li)
@@ -392,12 +495,14 @@ static void nk_lineidx_free(nk_lineidx *li)
     li->cum = NULL;
 }
 
-/* offset of the newline with global 0-based index g, or SIZE_MAX */
+static uint64_t nk_lineidx_total(const nk_lineidx *li) { return li->cum ? li->cum[li->c_hi] : 0; }
+
+/* offset of the newline with index g (0-based, counted from the first counted chunk), or SIZE_MAX */
 static size_t nk_lineidx_find(const nk_lineidx *li, uint64_t g)
 {
-    if (li->nchunks == 0 || g >= li->cum[li->nchunks])
+    if (li->c_hi == li->c_lo || g >= li->cum[li->c_hi])
         return SIZE_MAX;
-    int lo = 0, hi = li->nchunks - 1; /* last chunk whose cum <= g */
+    int lo = li->c_lo, hi = li->c_hi - 1; /* last chunk whose cum <= g */
     while (lo < hi)
     {
         int mid = (lo + hi + 1) / 2;
@@ -412,16 +517,18 @@ static size_t nk_lineidx_find(const nk_lineidx *li, uint64_t g)
     return base + nk_kth_newline(li->f->data + base, n, g - li->cum[lo] + 1);
 }
 
-/* newlines in [0, pos) */
+/* newlines in [first counted chunk, pos) */
 static uint64_t nk_lineidx_before(const nk_lineidx *li, size_t pos)
 {
-    if (pos == 0 || li->nchunks == 0)
+    if (li->c_hi == li->c_lo)
         return 0;
     if (pos > li->f->size)
         pos = li->f->size;
     int c = (int)(pos / NK_LI_CHUNK);
-    if (c >= li->nchunks)
-        return li->cum[li->nchunks];
+    if (c < li->c_lo)
+        return 0;
+    if (c >= li->c_hi)
+        return li->cum[li->c_hi];
     return li->cum[c] + nk_count_newlines(li->f->data + (size_t)c * NK_LI_CHUNK, pos - (size_t)c * NK_LI_CHUNK);
 }
 
@@ -437,7 +544,7 @@ uint64_t nk_count_records(const char *data, size_t size, int fastq)
     nk_buf f = {data, size};
     nk_lineidx li;
     nk_lineidx_build(&li, &f);
-    uint64_t r = nk_records_from_lines(&f, li.nchunks ? li.cum[li.nchunks] : 0, fastq);
+    uint64_t r = nk_records_from_lines(&f, nk_lineidx_total(&li), fastq);
     nk_lineidx_free(&li);
     return r;
 }
@@ -546,7 +653,17 @@ typedef struct
     nk_span *spans;                 /* stride records (fwd, rev) */
     uint32_t ops;
     int64_t fatal_record; /* length-gate passed but the engine reported a non-DNA byte */
+    /* raw-text steps: the file ranges [f0, f1) / [r0, r1) of the step's raw_n records */
+    size_t f0, f1, r0, r1;
+    uint32_t raw_n;
 } nk_pstep;
+
+typedef struct
+{
+    uint8_t *dst;
+    const char *src;
+    size_t n;
+} nk_copy;
 
 typedef struct
 {
@@ -555,6 +672,15 @@ typedef struct
     nk_pstep *ps;    /* per device-local partition */
     nkd_segment *segs;
     size_t n_records;
+    /* raw-text steps (page-locked): record text in, accepted records' text out */
+    uint8_t *raw, *out;
+    size_t raw_bytes;
+    nkd_raw_segment *rsegs;
+    nkd_raw_result *rres;
+    int *rseg_li; /* engine-local partition of each raw segment */
+    int n_rsegs;
+    nk_copy *copies;
+    int n_copies;
 } nk_stepbuf;
 
 typedef struct
@@ -567,6 +693,11 @@ typedef struct
     uint64_t processed, printed, skipped;
     double t_start;
     uint64_t last_processed;
+    /* raw-text pipeline: whole records [raw_next, raw_total) of the partition's ranges are still to be staged;
+     * line_f / line_r = index of the partition's first line end in the files' line indexes; the GPU stage moves
+     * commit_* past every step it has finished, which is where the host parser takes over if it has to */
+    uint64_t raw_total, raw_next, line_f, line_r;
+    size_t raw_fp, raw_rp, commit_fp, commit_rp;
 } nk_part;
 
 #define NK_NBUF 3 /* index step i+1, run step i on the GPU and write step i-1 at the same time */
@@ -580,6 +711,8 @@ typedef struct
     int n_parts;
     int *parts; /* indices into ctx->part */
     nk_stepbuf sb[NK_NBUF];
+    int have_parsed_bufs, have_raw_bufs; /* staging is allocated when a pipeline of that kind first runs */
+    size_t max_step_bytes;
     double index_s, device_s, write_s;
     uint64_t h2d, d2h;
     int rc;
@@ -600,6 +733,10 @@ struct nk_ctx
     uint32_t step_pairs, step_ops, step_bytes;
     int dev_group; /* partitions per device launch group, 0 = all resident partitions */
     int serial_steps; /* NKB200_SERIAL_STEPS: one device step at a time per GPU (the host pipelines still overlap) */
+    int raw_mode;     /* steps go to the device as raw record text (default); NKB200_HOST_PARSE=1 parses on the host */
+    uint32_t raw_part_bytes; /* raw text per partition, mate and step */
+    nk_lineidx lif, lir;     /* line indexes of the files being processed */
+    uint64_t raw_steps, parsed_steps;
     /* seeding */
     uint8_t *seed_seq[2]; /* two staging buffers: one is parsed into while the GPUs seed from the other */
     nkd_read *seed_reads[2];
@@ -657,6 +794,12 @@ static void nk_free_stepbuf(nk_stepbuf *sb, int n_parts)
     free(sb->segs);
     nkd_free_pinned(sb->seq);
     nkd_free_pinned(sb->accept);
+    nkd_free_pinned(sb->raw);
+    nkd_free_pinned(sb->out);
+    free(sb->rsegs);
+    free(sb->rres);
+    free(sb->rseg_li);
+    free(sb->copies);
     memset(sb, 0, sizeof *sb);
 }
 
@@ -806,11 +949,17 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
     if (sp < 16)
         sp = 16;
     c->dev_group = getenv("NKB200_GROUP") ? atoi(getenv("NKB200_GROUP")) : 0;
-    c->serial_steps = getenv("NKB200_SERIAL_STEPS") != NULL;
+    c->serial_steps = nk_env_on("NKB200_SERIAL_STEPS");
+    c->raw_mode = !nk_env_on("NKB200_HOST_PARSE");
     int grp = c->dev_group > 0 && c->dev_group < max_dev_parts ? c->dev_group : max_dev_parts;
+    if (grp < max_dev_parts)
+        c->raw_mode = 0; /* launch groups exist for the parsed path only (an experiment knob) */
     c->step_pairs = sp;
-    c->step_ops = sp * 288u < 4096u ? 4096u : sp * 288u;
+    /* operations and bytes a partition's share of a step may hold: a 150-base pair is ~660 bytes of FASTQ and at
+     * most 292 operations; a raw-text step is cut so that bytes / 2 (FASTQ: sequence + quality) stays below step_ops */
+    c->step_ops = sp * 336u < 4096u ? 4096u : sp * 336u;
     c->step_bytes = (sp * 2u * 176u + 4096u) & ~15u;
+    c->raw_part_bytes = (sp * 384u + 16384u) & ~15u;
     for (int d = 0; d < c->n_dev; d++)
     {
         nk_dev *dv = &c->dev[d];
@@ -827,6 +976,8 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         ec.max_step_reads = (uint64_t)eg * sp * 2u + 16;
         ec.max_step_bytes = (uint64_t)dv->n_parts * c->step_bytes + 64;
         ec.max_step_ops = (uint64_t)eg * c->step_ops + 64;
+        ec.max_raw_bytes = c->raw_mode ? (uint64_t)dv->n_parts * 2u * (c->raw_part_bytes + 16u) : 0;
+        dv->max_step_bytes = (size_t)ec.max_step_bytes;
         int rc = nkd_create(&ec, &dv->eng);
         if (rc)
         {
@@ -837,29 +988,13 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         for (int b = 0; b < NK_NBUF; b++)
         {
             nk_stepbuf *sb = &dv->sb[b];
-            sb->seq = nkd_alloc_pinned((size_t)ec.max_step_bytes + 64);
-            sb->accept = nkd_alloc_pinned((size_t)dv->n_parts * sp + 16);
             sb->ps = calloc((size_t)dv->n_parts, sizeof *sb->ps);
             sb->segs = calloc((size_t)dv->n_parts, sizeof *sb->segs);
-            if (!sb->seq || !sb->accept || !sb->ps || !sb->segs)
+            if (!sb->ps || !sb->segs)
             {
                 nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (staging buffers)");
                 nk_destroy(c);
                 return NK_ENOMEM;
-            }
-            memset(sb->seq, 0, (size_t)ec.max_step_bytes + 64);
-            for (int i = 0; i < dv->n_parts; i++)
-            {
-                sb->ps[i].reads = nkd_alloc_pinned((size_t)sp * 2u * sizeof(nkd_read));
-                sb->ps[i].spans = malloc((size_t)sp * 2u * sizeof(nk_span));
-                sb->ps[i].seq_lo = (size_t)i * c->step_bytes;
-                sb->ps[i].seq_end = sb->ps[i].seq_lo + c->step_bytes;
-                if (!sb->ps[i].reads || !sb->ps[i].spans)
-                {
-                    nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (staging buffers)");
-                    nk_destroy(c);
-                    return NK_ENOMEM;
-                }
             }
         }
     }
@@ -889,6 +1024,59 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         memset(c->seed_seq[b], 0, c->seed_cap_bytes + 64);
     }
     *out = c;
+    return NK_OK;
+}
+
+/* Page-locked staging of an engine's NK_NBUF steps, allocated when a pipeline of that kind first runs (pinning
+ * memory costs ~0.4 s per GB): parsed steps hold sequence lines + read descriptors + accept flags, raw-text steps
+ * hold record text in and the accepted records' text out. */
+static int nk_alloc_parsed_bufs(nk_ctx *c, nk_dev *dv)
+{
+    if (dv->have_parsed_bufs)
+        return NK_OK;
+    const uint32_t sp = c->step_pairs;
+    for (int b = 0; b < NK_NBUF; b++)
+    {
+        nk_stepbuf *sb = &dv->sb[b];
+        sb->seq = nkd_alloc_pinned(dv->max_step_bytes + 64);
+        sb->accept = nkd_alloc_pinned((size_t)dv->n_parts * sp + 16);
+        if (!sb->seq || !sb->accept)
+            return NK_ENOMEM;
+        memset(sb->seq, 0, dv->max_step_bytes + 64);
+        for (int i = 0; i < dv->n_parts; i++)
+        {
+            sb->ps[i].reads = nkd_alloc_pinned((size_t)sp * 2u * sizeof(nkd_read));
+            sb->ps[i].spans = malloc((size_t)sp * 2u * sizeof(nk_span));
+            sb->ps[i].seq_lo = (size_t)i * c->step_bytes;
+            sb->ps[i].seq_end = sb->ps[i].seq_lo + c->step_bytes;
+            if (!sb->ps[i].reads || !sb->ps[i].spans)
+                return NK_ENOMEM;
+        }
+    }
+    dv->have_parsed_bufs = 1;
+    return NK_OK;
+}
+
+#define NK_COPY_PIECE ((size_t)1 << 20) /* bytes one pool task copies into the staging buffer */
+
+static int nk_alloc_raw_bufs(nk_ctx *c, nk_dev *dv)
+{
+    if (dv->have_raw_bufs)
+        return NK_OK;
+    size_t cap = (size_t)dv->n_parts * 2u * ((size_t)c->raw_part_bytes + 16u) + 64;
+    for (int b = 0; b < NK_NBUF; b++)
+    {
+        nk_stepbuf *sb = &dv->sb[b];
+        sb->raw = nkd_alloc_pinned(cap);
+        sb->out = nkd_alloc_pinned(cap + (size_t)dv->n_parts * 4u * c->step_pairs); /* fq->fa may add "/1" per record */
+        sb->rsegs = calloc((size_t)dv->n_parts, sizeof *sb->rsegs);
+        sb->rres = calloc((size_t)dv->n_parts, sizeof *sb->rres);
+        sb->rseg_li = calloc((size_t)dv->n_parts, sizeof *sb->rseg_li);
+        sb->copies = calloc((size_t)dv->n_parts * 2u * ((size_t)c->raw_part_bytes / NK_COPY_PIECE + 2), sizeof *sb->copies);
+        if (!sb->raw || !sb->out || !sb->rsegs || !sb->rres || !sb->rseg_li || !sb->copies)
+            return NK_ENOMEM;
+    }
+    dv->have_raw_bufs = 1;
     return NK_OK;
 }
 
@@ -1555,6 +1743,7 @@ typedef struct
     int abort_rc;                  /* first error of any stage */
     int64_t first_invalid[NK_NBUF];
     int t_index, t_write;
+    int raw; /* 1: steps are raw record text parsed on the device; 0: parsed here */
 } nk_pipe;
 
 static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_invalid)
@@ -1610,6 +1799,254 @@ static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_inv
     return rc;
 }
 
+/* ------------------------------------------------------------------ raw-text steps
+ *
+ * The device reads the records itself (nkd_stage_raw): the host cuts each partition's byte range into steps of
+ * whole records with the line index, copies the bytes into the page-locked step buffer on all pool threads, and
+ * later write()s the text of the accepted records that comes back.  What the reference's worker does per record
+ * (C:1605-1674) happens on the GPU; the byte-exact host parser above remains for text the device declines. */
+
+/* file offset of the first byte of record j of a partition (j >= 1): one past its (per*j)-th line end */
+static size_t nk_record_start(const nk_lineidx *li, uint64_t line0, int per, uint64_t j)
+{
+    size_t nl = nk_lineidx_find(li, line0 + (uint64_t)per * j - 1);
+    return nl == SIZE_MAX ? SIZE_MAX : nl + 1;
+}
+
+/* whole records the raw-text pipeline may take from a byte range: those that start before `end` (the worker
+ * loop's test, C:1605) and whose every line is terminated inside the file */
+static uint64_t nk_raw_records_in(const nk_lineidx *li, size_t start, size_t end, int per, uint64_t line0)
+{
+    if (start >= end)
+        return 0;
+    uint64_t upto = nk_lineidx_before(li, end - 1) - line0; /* line ends in [start, end-1) */
+    uint64_t n = 1 + upto / (uint64_t)per;
+    uint64_t have = nk_lineidx_total(li) - line0; /* line ends from start to the end of the counted range */
+    if (n > have / (uint64_t)per)
+        n = have / (uint64_t)per;
+    return n;
+}
+
+static void nk_copy_task(int i, void *a)
+{
+    const nk_copy *cp = &((const nk_copy *)a)[i];
+    memcpy(cp->dst, cp->src, cp->n);
+}
+
+/* One step: for every partition of the engine the next (at most step_pairs) records of both files, as two windows
+ * of the step buffer.  Returns the number of records staged. */
+static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
+{
+    double t0 = nk_now();
+    const int per = c->cfg.in_fastq ? 4 : 2, paired = c->paired;
+    size_t at = 0, total = 0;
+    sb->n_rsegs = 0;
+    sb->n_copies = 0;
+    for (int li = 0; li < dv->n_parts; li++)
+    {
+        nk_part *p = &c->part[dv->parts[li]];
+        nk_pstep *ps = &sb->ps[li];
+        ps->raw_n = 0;
+        ps->fatal_record = -1;
+        uint64_t left = p->raw_total - p->raw_next;
+        if (!left)
+            continue;
+        uint64_t n = left < c->step_pairs ? left : c->step_pairs;
+        size_t f1 = 0, r1 = 0;
+        for (;;)
+        {
+            f1 = nk_record_start(&c->lif, p->line_f, per, p->raw_next + n);
+            r1 = paired ? nk_record_start(&c->lir, p->line_r, per, p->raw_next + n) : 0;
+            if (f1 == SIZE_MAX || r1 == SIZE_MAX)
+            { /* cannot happen for records counted by nk_raw_records_in; leave the rest to the host parser */
+                n = 0;
+                break;
+            }
+            size_t wf = f1 - p->raw_fp, wr = paired ? r1 - p->raw_rp : 0, big = wf > wr ? wf : wr;
+            size_t ops_bound = c->cfg.in_fastq ? (wf + wr) / 2 : wf + wr;
+            if ((big <= c->raw_part_bytes && ops_bound <= c->step_ops) || n == 1)
+            {
+                if (big > c->raw_part_bytes)
+                    n = 0; /* one record larger than the window: not regular text */
+                break;
+            }
+            double shrink = 0.95 * (double)c->raw_part_bytes / (double)big, s2 = 0.95 * (double)c->step_ops / (double)ops_bound;
+            if (s2 < shrink)
+                shrink = s2;
+            uint64_t m = (uint64_t)((double)n * shrink);
+            n = m >= n ? n - 1 : (m < 1 ? 1 : m);
+        }
+        if (n == 0)
+        {
+            p->raw_total = p->raw_next;
+            continue;
+        }
+        ps->raw_n = (uint32_t)n;
+        ps->f0 = p->raw_fp;
+        ps->f1 = f1;
+        ps->r0 = p->raw_rp;
+        ps->r1 = r1;
+        nkd_raw_segment *g = &sb->rsegs[sb->n_rsegs];
+        sb->rseg_li[sb->n_rsegs++] = li;
+        g->part = (uint32_t)p->lidx;
+        g->n_records = (uint32_t)n;
+        for (int m = 0; m < (paired ? 2 : 1); m++)
+        {
+            const nk_buf *src = m ? &c->rf : &c->ff;
+            size_t lo = m ? ps->r0 : ps->f0, hi = m ? ps->r1 : ps->f1;
+            if (m)
+            {
+                g->rev_off = (uint32_t)at;
+                g->rev_bytes = (uint32_t)(hi - lo);
+            }
+            else
+            {
+                g->fwd_off = (uint32_t)at;
+                g->fwd_bytes = (uint32_t)(hi - lo);
+            }
+            for (size_t o = lo; o < hi; o += NK_COPY_PIECE)
+            {
+                nk_copy *cp = &sb->copies[sb->n_copies++];
+                cp->dst = sb->raw + at + (o - lo);
+                cp->src = src->data + o;
+                cp->n = hi - o < NK_COPY_PIECE ? hi - o : NK_COPY_PIECE;
+            }
+            at += hi - lo;
+            size_t pad = (16 - (at & 15)) & 15;
+            memset(sb->raw + at, ' ', pad); /* neither a line end nor a NUL */
+            at += pad;
+        }
+        if (!paired)
+            g->rev_off = g->rev_bytes = 0;
+        p->raw_next += n;
+        p->raw_fp = f1;
+        p->raw_rp = r1;
+        total += n;
+    }
+    sb->raw_bytes = at;
+    sb->n_records = total;
+    if (sb->n_copies)
+        nk_parallel_for(sb->n_copies, threads, nk_copy_task, sb->copies);
+    dv->index_s += nk_now() - t0;
+    return total;
+}
+
+static int nk_emit_mode(const nk_ctx *c)
+{
+    if (c->cfg.in_fastq && !c->cfg.out_fastq)
+        return c->paired ? 1 : 2; /* single-end fq->fa prints nothing although it counts as printed, C:1995-1999 */
+    return 0;
+}
+
+static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_invalid)
+{
+    *first_invalid = -1;
+    double t0 = nk_now();
+    pthread_mutex_t *turn = c->serial_steps ? &c->dev[dv->lead].step_lock : NULL;
+    if (turn)
+        pthread_mutex_lock(turn);
+    int rc = nkd_stage_raw(dv->eng, sb->raw, sb->raw_bytes, sb->rsegs, sb->n_rsegs, c->paired, c->cfg.in_fastq ? 4 : 2);
+    if (!rc)
+        rc = nkd_run(dv->eng);
+    if (!rc)
+        rc = nkd_fetch_raw(dv->eng, nk_emit_mode(c), sb->out, (size_t)-1, sb->rres, first_invalid);
+    if (turn)
+        pthread_mutex_unlock(turn);
+    dv->device_s += nk_now() - t0;
+    if (rc)
+        snprintf(dv->err, sizeof dv->err, "%s", nkd_last_error(dv->eng));
+    else
+        for (int s = 0; s < sb->n_rsegs; s++)
+        { /* this step is done: the host parser, if it is ever needed, continues behind it */
+            nk_pstep *ps = &sb->ps[sb->rseg_li[s]];
+            nk_part *p = &c->part[dv->parts[sb->rseg_li[s]]];
+            p->commit_fp = ps->f1;
+            p->commit_rp = ps->r1;
+        }
+    return rc;
+}
+
+/* the reference's FATAL text for record `rec` of a raw-text step (C:1445-1454) */
+static int nk_report_invalid_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t rec)
+{
+    const int per = c->cfg.in_fastq ? 4 : 2;
+    size_t base = 0;
+    for (int s = 0; s < sb->n_rsegs; s++)
+    {
+        nk_pstep *ps = &sb->ps[sb->rseg_li[s]];
+        if ((size_t)rec >= base + ps->raw_n)
+        {
+            base += ps->raw_n;
+            continue;
+        }
+        size_t r = (size_t)rec - base;
+        for (int m = 0; m < (c->paired ? 2 : 1); m++)
+        {
+            const nk_buf *f = m ? &c->rf : &c->ff;
+            size_t lo = m ? ps->r0 : ps->f0, hi = m ? ps->r1 : ps->f1;
+            size_t q = r ? lo + nk_kth_newline(f->data + lo, hi - lo, (uint64_t)per * r) + 1 : lo;
+            q += nk_kth_newline(f->data + q, hi - q, 1) + 1; /* the sequence line follows the header */
+            size_t len = nk_kth_newline(f->data + q, hi - q, 1);
+            int bad = 0;
+            for (size_t b = 0; b < len; b++)
+                if (!strchr("ACGTN", f->data[q + b]) || f->data[q + b] == 0)
+                    bad = 1;
+            if (bad)
+            {
+                char *txt = malloc(len + 1);
+                nk_scrub_copy(txt, f->data + q, len);
+                snprintf(dv->err, sizeof dv->err, "FATAL: %s sequence does not appear to be a DNA sequence\n%s\n", m ? "REV" : "FWD", txt);
+                free(txt);
+                return NK_EDATA;
+            }
+        }
+        snprintf(dv->err, sizeof dv->err, "FATAL: sequence does not appear to be a DNA sequence");
+        return NK_EDATA;
+    }
+    return NK_EINTERNAL;
+}
+
+typedef struct
+{
+    nk_ctx *c;
+    nk_dev *dv;
+    nk_stepbuf *sb;
+    int io_error;
+} nk_rawwrite_job;
+
+/* one task per (segment, mate): the accepted records' text goes to the partition's file in one piece */
+static void nk_rawwrite_task(int idx, void *a)
+{
+    nk_rawwrite_job *j = a;
+    const int stride = j->c->paired ? 2 : 1, s = idx / stride, mate = idx % stride;
+    nk_part *p = &j->c->part[j->dv->parts[j->sb->rseg_li[s]]];
+    const nkd_raw_result *r = &j->sb->rres[s];
+    FILE *out = mate ? p->out_r : p->out_f;
+    uint64_t off = mate ? r->rev_off : r->fwd_off, n = mate ? r->rev_bytes : r->fwd_bytes;
+    if (n && out && fwrite(j->sb->out + off, 1, (size_t)n, out) != (size_t)n)
+        j->io_error = 1;
+    if (mate == 0)
+    {
+        p->processed += r->processed;
+        p->printed += r->printed;
+        p->skipped += r->processed - r->printed;
+    }
+}
+
+static int nk_write_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
+{
+    double t0 = nk_now();
+    nk_rawwrite_job job = {c, dv, sb, 0};
+    nk_parallel_for(sb->n_rsegs * (c->paired ? 2 : 1), threads, nk_rawwrite_task, &job);
+    dv->write_s += nk_now() - t0;
+    if (job.io_error)
+    {
+        snprintf(dv->err, sizeof dv->err, "error writing the output files: %s", strerror(errno));
+        return NK_EIO;
+    }
+    return NK_OK;
+}
+
 static void nk_pipe_fail(nk_pipe *pp, int rc)
 {
     pthread_mutex_lock(&pp->mu);
@@ -1631,12 +2068,15 @@ static void *nk_gpu_thread(void *a)
         pthread_mutex_unlock(&pp->mu);
         if (stop)
             break;
-        int rc = nk_gpu_step(pp->c, pp->dv, &pp->dv->sb[step % NK_NBUF], &pp->first_invalid[step % NK_NBUF]);
+        nk_stepbuf *sb = &pp->dv->sb[step % NK_NBUF];
+        int rc = pp->raw ? nk_gpu_step_raw(pp->c, pp->dv, sb, &pp->first_invalid[step % NK_NBUF])
+                         : nk_gpu_step(pp->c, pp->dv, sb, &pp->first_invalid[step % NK_NBUF]);
         if (rc)
         {
             nk_pipe_fail(pp, rc);
             break;
         }
+        __atomic_add_fetch(pp->raw ? &pp->c->raw_steps : &pp->c->parsed_steps, 1, __ATOMIC_RELAXED);
         pthread_mutex_lock(&pp->mu);
         pp->completed = step + 1;
         pthread_cond_broadcast(&pp->cv);
@@ -1730,8 +2170,16 @@ static void *nk_writer_thread(void *a)
         nk_stepbuf *sb = &dv->sb[step % NK_NBUF];
         int rc = NK_OK;
         if (pp->first_invalid[step % NK_NBUF] >= 0)
-            rc = nk_report_invalid(c, dv, sb, pp->first_invalid[step % NK_NBUF]);
-        nk_write_step(c, dv, sb, pp->t_write);
+            rc = pp->raw ? nk_report_invalid_raw(c, dv, sb, pp->first_invalid[step % NK_NBUF])
+                         : nk_report_invalid(c, dv, sb, pp->first_invalid[step % NK_NBUF]);
+        if (pp->raw)
+        {
+            int wrc = nk_write_step_raw(c, dv, sb, pp->t_write);
+            if (!rc)
+                rc = wrc;
+        }
+        else
+            nk_write_step(c, dv, sb, pp->t_write);
         if (rc)
         {
             nk_pipe_fail(pp, rc);
@@ -1765,7 +2213,19 @@ static void *nk_device_pipeline(void *a)
          * that is kept, so both stages get all of this pipeline's threads and the OS balances them (20 M pairs
          * at -p 64: 1.36 -> 0.98 s) */
         pp->t_index = pp->t_write = threads;
-    dv->rc = NK_OK;
+    if (pp->raw)
+    { /* copying in and writing out are plain byte moves: every pool thread this pipeline may use helps with both */
+        pp->t_index = threads;
+        pp->t_write = threads;
+    }
+    if (dv->rc)
+        return NULL;
+    if ((pp->raw ? nk_alloc_raw_bufs(c, dv) : nk_alloc_parsed_bufs(c, dv)) != NK_OK)
+    {
+        dv->rc = NK_ENOMEM;
+        snprintf(dv->err, sizeof dv->err, "Memory allocation failed (staging buffers)");
+        return NULL;
+    }
     pthread_mutex_init(&pp->mu, NULL);
     pthread_cond_init(&pp->cv, NULL);
     pp->built = pp->completed = pp->written = 0;
@@ -1787,7 +2247,8 @@ static void *nk_device_pipeline(void *a)
         pthread_mutex_unlock(&pp->mu);
         if (stop)
             break;
-        size_t n = nk_build_step(c, dv, &dv->sb[step % NK_NBUF], pp->t_index);
+        size_t n = pp->raw ? nk_build_step_raw(c, dv, &dv->sb[step % NK_NBUF], pp->t_index)
+                           : nk_build_step(c, dv, &dv->sb[step % NK_NBUF], pp->t_index);
         pthread_mutex_lock(&pp->mu);
         if (n == 0)
             pp->total = step;
@@ -1805,15 +2266,17 @@ static void *nk_device_pipeline(void *a)
     pthread_mutex_unlock(&pp->mu);
     pthread_join(gth, NULL);
     pthread_join(wth, NULL);
-    if (pp->abort_rc)
+    if (pp->abort_rc && pp->abort_rc != NK_EIRREGULAR) /* declined raw text is not an error: the host parser continues */
         dv->rc = pp->abort_rc;
     pthread_mutex_destroy(&pp->mu);
     pthread_cond_destroy(&pp->cv);
     return NULL;
 }
 
+/* lf / lr: line indexes of the whole files.  Already built ones (cum != NULL) are used; if the record-count
+ * partitioner needs them they are built here and left to the caller, who frees them. */
 static int nk_plan(const nk_buf *ff, const nk_buf *rf, int paired, int P, int fastq, int threads, uint64_t *fs,
-                   uint64_t *fe, uint64_t *rs, uint64_t *re, nk_diag *d)
+                   uint64_t *fe, uint64_t *rs, uint64_t *re, nk_diag *d, nk_lineidx *lf, nk_lineidx *lr)
 {
     if (!nk_mask64)
         nk_mask64 = nk_mask64_pick();
@@ -1836,14 +2299,13 @@ static int nk_plan(const nk_buf *ff, const nk_buf *rf, int paired, int P, int fa
     }
     else
     { /* C:1815-1828: the forward file's record count is applied to both files */
-        nk_lineidx lf, lr;
-        nk_lineidx_build_n(&lf, ff, threads);
-        nk_lineidx_build_n(&lr, rf, threads);
-        uint64_t recs = nk_records_from_lines(ff, lf.nchunks ? lf.cum[lf.nchunks] : 0, fastq);
-        nk_ranges_by_records(&lf, P, fastq, recs, fs, fe);
-        nk_ranges_by_records(&lr, P, fastq, recs, rs, re);
-        nk_lineidx_free(&lf);
-        nk_lineidx_free(&lr);
+        if (!lf->cum)
+            nk_lineidx_build_n(lf, ff, threads);
+        if (!lr->cum)
+            nk_lineidx_build_n(lr, rf, threads);
+        uint64_t recs = nk_records_from_lines(ff, nk_lineidx_total(lf), fastq);
+        nk_ranges_by_records(lf, P, fastq, recs, fs, fe);
+        nk_ranges_by_records(lr, P, fastq, recs, rs, re);
     }
     return NK_OK;
 }
@@ -1856,79 +2318,53 @@ int nk_plan_ranges(const char *fwd, size_t fwd_size, const char *rev, size_t rev
         return NK_EINVAL;
     nk_buf ff = {fwd, fwd_size}, rf = {rev, rev_size};
     nk_diag d = {{0}, 0};
+    nk_lineidx lf = {0}, lr = {0};
     int rc = nk_plan(&ff, &rf, rev != NULL, partitions, fastq, threads > 0 ? threads : nk_host_threads(), fwd_starts,
-                     fwd_ends, rev_starts, rev_ends, &d);
+                     fwd_ends, rev_starts, rev_ends, &d, &lf, &lr);
+    nk_lineidx_free(&lf);
+    nk_lineidx_free(&lr);
     if (rc && errbuf && errbuf_size)
         snprintf(errbuf, errbuf_size, "%s", d.msg);
     return rc;
 }
 
-static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev, size_t rsize, int paired,
-                      const uint64_t *plan[4])
+/* one pipeline per engine, raw-text or host-parsed steps; returns the first error */
+static int nk_run_pipelines(nk_ctx *c, int raw)
 {
-    if (!c->seeded)
-        return nk_fail(c, NK_EINVAL, "nk_process_* before nk_seed_finish");
-    if (fsize == 0 || (paired && rsize == 0))
-        return nk_fail(c, NK_EIO, "Error memory mapping input files");
-    double t0 = nk_now();
-    int P = c->cfg.partitions, fastq = c->cfg.in_fastq;
-    c->ff.data = fwd;
-    c->ff.size = fsize;
-    c->rf.data = rev;
-    c->rf.size = rsize;
-    c->paired = paired;
-    if (plan)
-    {
-        memcpy(c->fs, plan[0], sizeof(uint64_t) * (size_t)P);
-        memcpy(c->fe, plan[1], sizeof(uint64_t) * (size_t)P);
-        memset(c->rs, 0, sizeof(uint64_t) * (size_t)P);
-        memset(c->re, 0, sizeof(uint64_t) * (size_t)P);
-        if (paired)
-        {
-            memcpy(c->rs, plan[2], sizeof(uint64_t) * (size_t)P);
-            memcpy(c->re, plan[3], sizeof(uint64_t) * (size_t)P);
-        }
-        for (int t = 0; t < P; t++)
-            if (c->fe[t] >= fsize || c->fs[t] > fsize || (paired && (c->re[t] >= rsize || c->rs[t] > rsize)))
-                return nk_fail(c, NK_EINVAL, "nk_process_planned: range outside the file");
-    }
-    else
-    {
-        nk_diag d = {{0}, 0};
-        if (nk_plan(&c->ff, &c->rf, paired, P, fastq, c->threads, c->fs, c->fe, c->rs, c->re, &d))
-            return nk_fail(c, NK_EDATA, "%s", d.msg);
-    }
-    for (int i = 0; i < c->n_local; i++)
-    {
-        nk_part *p = &c->part[i];
-        p->cur.fp = c->fs[p->gid];
-        p->cur.fe = c->fe[p->gid];
-        p->cur.rp = c->rs[p->gid];
-        p->cur.re = c->re[p->gid];
-        p->cur.done = 0;
-        if (!nk_mask64)
-            nk_mask64 = nk_mask64_pick();
-        nk_nliter_seek(&p->cur.itf, c->ff.data, p->cur.fp, c->ff.size);
-        if (paired)
-            nk_nliter_seek(&p->cur.itr, c->rf.data, p->cur.rp, c->rf.size);
-        p->t_start = nk_now();
-        p->last_processed = p->processed;
-    }
-    c->tot.index_seconds += nk_now() - t0;
     nk_pipe *pipes = calloc((size_t)c->n_dev, sizeof *pipes);
-    pthread_t th[64];
+    pthread_t *th = calloc((size_t)c->n_dev, sizeof *th);
+    char *started = calloc((size_t)c->n_dev, 1);
+    if (!pipes || !th || !started)
+    {
+        free(pipes);
+        free(th);
+        free(started);
+        return nk_fail(c, NK_ENOMEM, "Memory allocation failed (pipelines)");
+    }
     for (int dd = 0; dd < c->n_dev; dd++)
     {
         pipes[dd].c = c;
         pipes[dd].dv = &c->dev[dd];
-        c->dev[dd].index_s = c->dev[dd].device_s = c->dev[dd].write_s = 0;
+        pipes[dd].raw = raw;
+        c->dev[dd].rc = NK_OK;
     }
     for (int dd = 1; dd < c->n_dev; dd++)
-        pthread_create(&th[dd], NULL, nk_device_pipeline, &pipes[dd]);
+    {
+        if (pthread_create(&th[dd], NULL, nk_device_pipeline, &pipes[dd]) == 0)
+            started[dd] = 1;
+        else
+        {
+            c->dev[dd].rc = NK_EINTERNAL;
+            snprintf(c->dev[dd].err, sizeof c->dev[dd].err, "cannot start the pipeline thread of engine %d", dd);
+        }
+    }
     nk_device_pipeline(&pipes[0]);
     for (int dd = 1; dd < c->n_dev; dd++)
-        pthread_join(th[dd], NULL);
+        if (started[dd])
+            pthread_join(th[dd], NULL);
     free(pipes);
+    free(th);
+    free(started);
     int rc = NK_OK;
     double mi = 0, md = 0, mw = 0;
     for (int dd = 0; dd < c->n_dev; dd++)
@@ -1942,10 +2378,129 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
             md = dv->device_s;
         if (dv->write_s > mw)
             mw = dv->write_s;
+        dv->index_s = dv->device_s = dv->write_s = 0;
     }
     c->tot.index_seconds += mi;
     c->tot.device_seconds += md;
     c->tot.write_seconds += mw;
+    return rc;
+}
+
+static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev, size_t rsize, int paired,
+                      const uint64_t *plan[4], const uint32_t *counts_f, const uint32_t *counts_r)
+{
+    if (!c->seeded)
+        return nk_fail(c, NK_EINVAL, "nk_process_* before nk_seed_finish");
+    if (fsize == 0 || (paired && rsize == 0))
+        return nk_fail(c, NK_EIO, "Error memory mapping input files");
+    double t0 = nk_now();
+    int P = c->cfg.partitions, fastq = c->cfg.in_fastq, per = fastq ? 4 : 2;
+    c->ff.data = fwd;
+    c->ff.size = fsize;
+    c->rf.data = rev;
+    c->rf.size = rsize;
+    c->paired = paired;
+    if (!nk_mask64)
+        nk_mask64 = nk_mask64_pick();
+    memset(&c->lif, 0, sizeof c->lif);
+    memset(&c->lir, 0, sizeof c->lir);
+    if (counts_f)
+        nk_lineidx_from_counts(&c->lif, &c->ff, counts_f);
+    if (counts_r && paired)
+        nk_lineidx_from_counts(&c->lir, &c->rf, counts_r);
+    int rc = NK_OK;
+    if (plan)
+    {
+        memcpy(c->fs, plan[0], sizeof(uint64_t) * (size_t)P);
+        memcpy(c->fe, plan[1], sizeof(uint64_t) * (size_t)P);
+        memset(c->rs, 0, sizeof(uint64_t) * (size_t)P);
+        memset(c->re, 0, sizeof(uint64_t) * (size_t)P);
+        if (paired)
+        {
+            memcpy(c->rs, plan[2], sizeof(uint64_t) * (size_t)P);
+            memcpy(c->re, plan[3], sizeof(uint64_t) * (size_t)P);
+        }
+        for (int t = 0; t < P; t++)
+            if (c->fe[t] >= fsize || c->fs[t] > fsize || (paired && (c->re[t] >= rsize || c->rs[t] > rsize)))
+                rc = nk_fail(c, NK_EINVAL, "nk_process_planned: range outside the file");
+    }
+    else
+    {
+        nk_diag d = {{0}, 0};
+        if (nk_plan(&c->ff, &c->rf, paired, P, fastq, c->threads, c->fs, c->fe, c->rs, c->re, &d, &c->lif, &c->lir))
+            rc = nk_fail(c, NK_EDATA, "%s", d.msg);
+    }
+    int raw_work = 0;
+    if (!rc && c->raw_mode)
+    {
+        /* line indexes over the byte ranges of this context's partitions (kept from planning when it made them) */
+        size_t flo = SIZE_MAX, fhi = 0, rlo = SIZE_MAX, rhi = 0;
+        for (int i = 0; i < c->n_local; i++)
+        {
+            int g = c->part[i].gid;
+            if (c->fs[g] < c->fe[g] && (!paired || c->rs[g] < c->re[g]))
+            {
+                flo = c->fs[g] < flo ? c->fs[g] : flo;
+                fhi = c->fe[g] > fhi ? c->fe[g] : fhi;
+                rlo = c->rs[g] < rlo ? c->rs[g] : rlo;
+                rhi = c->re[g] > rhi ? c->re[g] : rhi;
+            }
+        }
+        const size_t slack = 8u * NK_MAX_LINE + 2; /* the record that starts before a range's end runs past it */
+        if (!c->lif.cum && flo != SIZE_MAX)
+            nk_lineidx_build_range(&c->lif, &c->ff, c->threads, flo, fhi + slack);
+        if (paired && !c->lir.cum && rlo != SIZE_MAX)
+            nk_lineidx_build_range(&c->lir, &c->rf, c->threads, rlo, rhi + slack);
+    }
+    for (int i = 0; i < c->n_local && !rc; i++)
+    {
+        nk_part *p = &c->part[i];
+        p->cur.fp = c->fs[p->gid];
+        p->cur.fe = c->fe[p->gid];
+        p->cur.rp = c->rs[p->gid];
+        p->cur.re = c->re[p->gid];
+        p->cur.done = 0;
+        p->commit_fp = p->raw_fp = p->cur.fp;
+        p->commit_rp = p->raw_rp = p->cur.rp;
+        p->raw_total = p->raw_next = 0;
+        if (c->raw_mode && c->lif.cum && (!paired || c->lir.cum))
+        {
+            p->line_f = nk_lineidx_before(&c->lif, p->cur.fp);
+            uint64_t n = nk_raw_records_in(&c->lif, p->cur.fp, p->cur.fe, per, p->line_f);
+            if (paired)
+            {
+                p->line_r = nk_lineidx_before(&c->lir, p->cur.rp);
+                uint64_t nr = nk_raw_records_in(&c->lir, p->cur.rp, p->cur.re, per, p->line_r);
+                n = nr < n ? nr : n;
+            }
+            p->raw_total = n;
+            raw_work |= n > 0;
+        }
+        p->t_start = nk_now();
+        p->last_processed = p->processed;
+    }
+    c->tot.index_seconds += nk_now() - t0;
+    if (!rc && raw_work)
+        rc = nk_run_pipelines(c, 1);
+    /* whatever the raw-text pipeline did not take -- text the device declined (NUL bytes, lines of 1024+ chars),
+     * a last record cut short by the end of the file -- goes through the byte-exact host parser from where each
+     * partition stands */
+    int parsed_work = 0;
+    for (int i = 0; i < c->n_local && !rc; i++)
+    {
+        nk_part *p = &c->part[i];
+        p->cur.fp = p->commit_fp;
+        p->cur.rp = p->commit_rp;
+        nk_nliter_seek(&p->cur.itf, c->ff.data, p->cur.fp, c->ff.size);
+        if (paired)
+            nk_nliter_seek(&p->cur.itr, c->rf.data, p->cur.rp, c->rf.size);
+        if (p->cur.fp < p->cur.fe && (!paired || p->cur.rp < p->cur.re))
+            parsed_work = 1;
+    }
+    if (!rc && parsed_work)
+        rc = nk_run_pipelines(c, 0);
+    nk_lineidx_free(&c->lif);
+    nk_lineidx_free(&c->lir);
     /* reporting totals are sums of the partitions' cumulative counters, C:1897-1909 */
     uint64_t pr = 0, pt = 0, sk = 0, mu = 0;
     for (int i = 0; i < c->n_local; i++)
@@ -1970,9 +2525,40 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
 
 int nk_process_paired(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size)
 {
-    return nk_process(c, fwd, fwd_size, rev, rev_size, 1, NULL);
+    return nk_process(c, fwd, fwd_size, rev, rev_size, 1, NULL, NULL, NULL);
 }
-int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size) { return nk_process(c, fwd, fwd_size, NULL, 0, 0, NULL); }
+int nk_process_single(nk_ctx *c, const char *fwd, size_t fwd_size)
+{
+    return nk_process(c, fwd, fwd_size, NULL, 0, 0, NULL, NULL, NULL);
+}
+/* The per-chunk line-end counts every planning step starts from (count_records_seqfile's scan, C:1302-1320, cut
+ * into NK_LINE_CHUNK-byte chunks).  The ranks of a multi-process launch count a share of the chunks each,
+ * exchange the counts, and hand all of them to nk_process_indexed, so that the files are scanned once per node
+ * instead of once per rank. */
+size_t nk_line_chunk_bytes(void) { return NK_LI_CHUNK; }
+int nk_count_chunk_lines(const char *data, size_t size, size_t chunk_first, size_t n_chunks, uint32_t *counts, int threads)
+{
+    nk_buf f = {data, size};
+    size_t total = (size + NK_LI_CHUNK - 1) / NK_LI_CHUNK;
+    if (!data || chunk_first > total || n_chunks > total - chunk_first)
+        return NK_EINVAL;
+    if (n_chunks == 0)
+        return NK_OK;
+    nk_lineidx li = {0};
+    nk_lineidx_build_range(&li, &f, threads > 0 ? threads : nk_host_threads(), chunk_first * NK_LI_CHUNK,
+                           (chunk_first + n_chunks) * NK_LI_CHUNK);
+    for (size_t i = 0; i < n_chunks; i++)
+        counts[i] = (uint32_t)(li.cum[chunk_first + i + 1] - li.cum[chunk_first + i]);
+    nk_lineidx_free(&li);
+    return NK_OK;
+}
+int nk_process_indexed(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size,
+                       const uint32_t *fwd_counts, const uint32_t *rev_counts)
+{
+    if (!fwd_counts || (rev && !rev_counts))
+        return nk_fail(c, NK_EINVAL, "nk_process_indexed: missing line counts");
+    return nk_process(c, fwd, fwd_size, rev, rev ? rev_size : 0, rev != NULL, NULL, fwd_counts, rev_counts);
+}
 int nk_process_planned(nk_ctx *c, const char *fwd, size_t fwd_size, const char *rev, size_t rev_size,
                        const uint64_t *fwd_starts, const uint64_t *fwd_ends, const uint64_t *rev_starts,
                        const uint64_t *rev_ends)
@@ -1980,7 +2566,7 @@ int nk_process_planned(nk_ctx *c, const char *fwd, size_t fwd_size, const char *
     const uint64_t *plan[4] = {fwd_starts, fwd_ends, rev_starts, rev_ends};
     if (!fwd_starts || !fwd_ends || (rev && (!rev_starts || !rev_ends)))
         return nk_fail(c, NK_EINVAL, "nk_process_planned: missing range arrays");
-    return nk_process(c, fwd, fwd_size, rev, rev ? rev_size : 0, rev != NULL, plan);
+    return nk_process(c, fwd, fwd_size, rev, rev ? rev_size : 0, rev != NULL, plan, NULL, NULL);
 }
 
 static int nk_span_cmp(const void *a, const void *b)
@@ -2063,6 +2649,8 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
             out->class_ms[k] += rs.class_ms[k];
     }
     out->engines = (uint64_t)c->n_dev;
+    out->raw_steps = c->raw_steps;
+    out->parsed_steps = c->parsed_steps;
     if (c->seeded)
         for (int i = 0; i < c->n_local; i++)
         {
@@ -2582,8 +3170,12 @@ int nk_main(int argc, char **argv)
     else
         printf("No data processed\n");
     if (cfg->verbose)
+    {
         printf("B200: seed %.3f s, process %.3f s (index %.3f, device %.3f, write %.3f) on %d GPU(s), %d host threads\n",
                c->tot.seed_seconds, c->tot.process_seconds, c->tot.index_seconds, c->tot.device_seconds, c->tot.write_seconds, gpus, c->threads);
+        printf("B200: %llu device steps on raw record text, %llu on host-parsed records\n", (unsigned long long)c->raw_steps,
+               (unsigned long long)c->parsed_steps);
+    }
     nk_destroy(c);
     return 0;
 }

@@ -99,6 +99,17 @@ class NkEngine
     uint64_t merge_cap = 0, merge_n = 0, merged_n = 0;
     bool merged_ready = false;
 
+    /* raw record text path (nkd_stage_raw / nkd_fetch_raw) */
+    unsigned char *d_raw = nullptr, *d_out = nullptr;
+    unsigned *d_tile = nullptr, *d_nlpos = nullptr, *d_nops = nullptr, *d_opscan = nullptr, *d_tout = nullptr;
+    unsigned *d_rflags = nullptr, *d_outlen = nullptr, *d_outoff = nullptr;
+    unsigned long long *d_summary = nullptr;
+    NkRawWin *d_wins = nullptr;
+    std::vector<NkRawWin> h_wins;
+    uint64_t raw_cap = 0, raw_reads_cap = 0, raw_lines_cap = 0;
+    NkRaw raw{}; /* the staged raw step */
+    bool raw_staged = false;
+
     bool debug = getenv("NKB200_DEBUG") != nullptr;
 
     int fail(int code, const std::string &m)
@@ -191,6 +202,18 @@ class NkEngine
         be.release(d_ctr);
         be.release(d_parts);
         be.release(d_bloom);
+        be.release(d_raw);
+        be.release(d_out);
+        be.release(d_tile);
+        be.release(d_nlpos);
+        be.release(d_nops);
+        be.release(d_opscan);
+        be.release(d_tout);
+        be.release(d_rflags);
+        be.release(d_outlen);
+        be.release(d_outoff);
+        be.release(d_summary);
+        be.release(d_wins);
         merge_release();
         be.shutdown();
     }
@@ -643,8 +666,243 @@ class NkEngine
         paired = is_paired;
         n_records = nr / stride;
         staged = true;
+        raw_staged = false;
         ran = false;
         return NK_OK;
+    }
+
+    /* ------------------------------------------------------------ steps handed over as raw record text */
+
+    /* scratch of the raw path, allocated on first use: a context that only ever stages parsed reads does not pay */
+    int raw_prepare()
+    {
+        if (d_raw)
+            return NK_OK;
+        if (!cfg.max_raw_bytes)
+            return fail(NK_EINVAL, "nkd_stage_raw: the engine was created with max_raw_bytes = 0");
+        raw_cap = (cfg.max_raw_bytes + 15) & ~15ull;
+        raw_reads_cap = cfg.max_step_reads + 2;
+        raw_lines_cap = raw_reads_cap * 4 + 16;
+        if (raw_cap >= 0xFFFFFFF0ull)
+            return fail(NK_EINVAL, "nkd_stage_raw: a step's raw text must stay below 4 GiB");
+        bool ok = true;
+        ok &= dalloc(d_raw, raw_cap + 64);
+        ok &= dalloc(d_out, raw_cap + 2 * raw_reads_cap + 64);
+        ok &= dalloc(d_tile, raw_cap / NK_RAW_TILE + 4);
+        ok &= dalloc(d_nlpos, raw_lines_cap);
+        ok &= dalloc(d_nops, raw_reads_cap + 1);
+        ok &= dalloc(d_opscan, raw_reads_cap + 1);
+        ok &= dalloc(d_outlen, raw_reads_cap + 1);
+        ok &= dalloc(d_outoff, raw_reads_cap + 1);
+        ok &= dalloc(d_tout, NK_MAX_PARTITIONS);
+        ok &= dalloc(d_rflags, 4);
+        ok &= dalloc(d_summary, 6 * NK_MAX_PARTITIONS);
+        ok &= dalloc(d_wins, NK_MAX_PARTITIONS);
+        if (!ok || !be.prepare_scan((size_t)std::max<uint64_t>(raw_reads_cap + 1, raw_cap / NK_RAW_TILE + 4), err))
+            return fail(NK_ENOMEM, "nkd_stage_raw: cannot allocate the raw-text scratch");
+        return NK_OK;
+    }
+
+    int stage_raw(const uint8_t *host_raw, size_t raw_bytes, const nkd_raw_segment *segs, int n_segs, int is_paired, int per)
+    {
+        if (!seeded)
+            return fail(NK_EINVAL, "nkd_stage_raw before nkd_seed_finish");
+        int rc = raw_prepare();
+        if (rc)
+            return rc;
+        if ((per != 2 && per != 4) || n_segs < 1 || n_segs > (int)parts.size())
+            return fail(NK_EINVAL, "nkd_stage_raw: bad segment count or lines per record");
+        const unsigned stride = is_paired ? 2u : 1u;
+        if (raw_bytes & 15u)
+            return fail(NK_EINVAL, "nkd_stage_raw: raw_bytes must be a multiple of 16 (pad with spaces)");
+        size_t bytes16 = raw_bytes;
+        if (bytes16 > raw_cap)
+            return fail(NK_EINVAL, "nkd_stage_raw: step exceeds max_raw_bytes");
+        h_wins.assign((size_t)n_segs, NkRawWin{});
+        std::fill(T.begin(), T.end(), 0u);
+        std::vector<char> seen(parts.size(), 0);
+        uint64_t recs = 0, lines = 0, outs = 0, prev_end = 0;
+        for (int s = 0; s < n_segs; s++)
+        {
+            const nkd_raw_segment &g = segs[s];
+            NkRawWin &w = h_wins[s];
+            if (g.part >= parts.size() || seen[g.part])
+                return fail(NK_EINVAL, "nkd_stage_raw: one segment per resident partition");
+            seen[g.part] = 1;
+            /* windows follow each other at the next 16-byte boundary, so that the copies below cover every byte
+             * the line scan reads */
+            if (g.n_records == 0 || g.fwd_off != ((prev_end + 15) & ~15ull) || (uint64_t)g.fwd_off + g.fwd_bytes > raw_bytes ||
+                g.fwd_bytes == 0)
+                return fail(NK_EINVAL, "nkd_stage_raw: forward window misplaced");
+            prev_end = (uint64_t)g.fwd_off + g.fwd_bytes;
+            if (is_paired)
+            {
+                if (g.rev_off != ((prev_end + 15) & ~15ull) || (uint64_t)g.rev_off + g.rev_bytes > raw_bytes || g.rev_bytes == 0)
+                    return fail(NK_EINVAL, "nkd_stage_raw: reverse window misplaced");
+                prev_end = (uint64_t)g.rev_off + g.rev_bytes;
+            }
+            w.f_off = g.fwd_off;
+            w.f_bytes = g.fwd_bytes;
+            w.r_off = is_paired ? g.rev_off : 0;
+            w.r_bytes = is_paired ? g.rev_bytes : 0;
+            w.n_records = g.n_records;
+            w.part = g.part;
+            w.f_line0 = (unsigned)lines;
+            lines += (uint64_t)per * g.n_records;
+            w.r_line0 = (unsigned)lines;
+            if (is_paired)
+                lines += (uint64_t)per * g.n_records;
+            w.rec0 = (unsigned)recs;
+            w.out0 = (unsigned)outs;
+            recs += g.n_records;
+            outs += (uint64_t)stride * g.n_records;
+        }
+        if (recs * stride > cfg.max_step_reads || lines > raw_lines_cap)
+            return fail(NK_EINVAL, "nkd_stage_raw: step exceeds the read limit given to nkd_create");
+        if (((prev_end + 15) & ~15ull) != raw_bytes)
+            return fail(NK_EINVAL, "nkd_stage_raw: raw_bytes must end the last window (rounded up to 16)");
+        /* windows go over as they are; the gaps keep whatever the host put there (neither '\n' nor NUL) */
+        for (int s = 0; s < n_segs; s++)
+        {
+            const NkRawWin &w = h_wins[s];
+            unsigned lo = w.f_off, hi = (w.f_off + w.f_bytes + 15u) & ~15u;
+            be.h2d(d_raw + lo, host_raw + lo, hi - lo);
+            h2d_bytes += hi - lo;
+            if (is_paired)
+            {
+                lo = w.r_off;
+                hi = (w.r_off + w.r_bytes + 15u) & ~15u;
+                be.h2d(d_raw + lo, host_raw + lo, hi - lo);
+                h2d_bytes += hi - lo;
+            }
+        }
+        be.h2d(d_wins, h_wins.data(), (size_t)n_segs * sizeof(NkRawWin));
+        be.zero(d_rflags, 4 * sizeof(unsigned));
+        be.zero(d_nlpos, (size_t)(lines + 1) * sizeof(unsigned));
+        raw = NkRaw{};
+        raw.raw = d_raw;
+        raw.raw_bytes = (unsigned)bytes16;
+        raw.wins = d_wins;
+        raw.n_wins = (unsigned)n_segs;
+        raw.n_records = (unsigned)recs;
+        raw.stride = stride;
+        raw.per = (unsigned)per;
+        raw.k = cfg.k;
+        raw.tile = d_tile;
+        raw.nlpos = d_nlpos;
+        raw.nlpos_cap = (unsigned)lines;
+        raw.reads = d_reads;
+        raw.nops = d_nops;
+        raw.opscan = d_opscan;
+        raw.t_out = d_tout;
+        raw.flags = d_rflags;
+        raw.accept = d_accept;
+        raw.outlen = d_outlen;
+        raw.outoff = d_outoff;
+        raw.out = d_out;
+        raw.summary = d_summary;
+        raw.inv_rec = NK_TMAX;
+        be.begin_timer(0); /* the step's device span starts with its parsing */
+        be.raw_index(raw);
+        unsigned h_flags[4] = {0, 0, 0, 0};
+        std::vector<unsigned> h_t((size_t)n_segs);
+        be.d2h(h_flags, d_rflags, sizeof h_flags);
+        be.d2h(h_t.data(), d_tout, (size_t)n_segs * sizeof(unsigned));
+        be.sync();
+        /* h_flags[1] = line ends found in the whole buffer */
+        if (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG))
+        {
+            be.end_timer(0);
+            be.reset_timer(0);
+            return fail(NK_EIRREGULAR, "raw text needs the host parser (NUL byte or a line of 1024+ chars)");
+        }
+        if ((h_flags[0] & NK_RAW_SHAPE) || h_flags[1] != lines)
+        {
+            be.end_timer(0);
+            be.reset_timer(0);
+            return fail(NK_EINVAL, "nkd_stage_raw: a window does not hold the announced number of complete records");
+        }
+        uint64_t tot = 0;
+        for (int s = 0; s < n_segs; s++)
+        {
+            T[h_wins[s].part] = h_t[s];
+            if (h_t[s] >= (1u << NK_T_BITS))
+                return fail(NK_EINVAL, "a partition has 2^28 or more operations in one step");
+            tot += h_t[s];
+        }
+        if (tot > cfg.max_step_ops)
+            return fail(NK_EINVAL, "step has more operations than max_step_ops");
+        seq_view = d_raw;
+        n_reads = (size_t)recs * stride;
+        n_records = (size_t)recs;
+        paired = is_paired;
+        staged = true;
+        raw_staged = true;
+        ran = false;
+        return NK_OK;
+    }
+
+    int fetch_raw(int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid)
+    {
+        if (!ran || !raw_staged)
+            return fail(NK_EINVAL, "nkd_fetch_raw without nkd_stage_raw + nkd_run");
+        if (emit_mode < 0 || emit_mode > 2)
+            return fail(NK_EINVAL, "nkd_fetch_raw: bad emit mode");
+        be.d2h(&h_ctr, d_ctr, 32);
+        be.sync();
+        int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
+        raw.emit_mode = emit_mode;
+        raw.inv_rec = inv >= 0 ? (unsigned)inv : NK_TMAX;
+        be.begin_timer(7);
+        be.zero(d_summary, 6 * (size_t)raw.n_wins * sizeof(unsigned long long));
+        be.raw_emit(raw);
+        be.end_timer(7);
+        std::vector<unsigned long long> sm(6 * (size_t)raw.n_wins);
+        be.d2h(sm.data(), d_summary, sm.size() * sizeof(unsigned long long));
+        be.sync();
+        uint64_t total = 0;
+        for (unsigned w = 0; w < raw.n_wins; w++)
+            total = std::max<uint64_t>(total, std::max(sm[6 * w] + sm[6 * w + 1], sm[6 * w + 2] + sm[6 * w + 3]));
+        if (total > out_cap)
+            return fail(NK_EINVAL, "nkd_fetch_raw: output buffer too small");
+        if (total)
+            be.d2h(out, d_out, (size_t)total);
+        be.end_timer(0);
+        be.sync();
+        d2h_bytes += total + sm.size() * 8 + 32;
+        finish_timers();
+        for (unsigned w = 0; w < raw.n_wins; w++)
+        {
+            nkd_raw_result &r = results[w];
+            r.fwd_off = sm[6 * w];
+            r.fwd_bytes = sm[6 * w + 1];
+            r.rev_off = sm[6 * w + 2];
+            r.rev_bytes = sm[6 * w + 3];
+            r.processed = sm[6 * w + 4];
+            r.printed = sm[6 * w + 5];
+            nkd_part_stats &st = parts[h_wins[w].part].st;
+            st.processed += r.processed;
+            st.printed += r.printed;
+            st.skipped += r.processed - r.printed;
+        }
+        if (first_invalid)
+            *first_invalid = inv;
+        staged = false;
+        raw_staged = false;
+        ran = false;
+        return NK_OK;
+    }
+
+    void finish_timers()
+    {
+        be.timer_spans(0, spans);
+        last_total_ms = be.timer_ms(0);
+        last_probe_ms = be.timer_ms(1);
+        rs.run_ms += last_total_ms;
+        rs.probe_ms += last_probe_ms;
+        rs.class_ms[0] += last_probe_ms;
+        for (int t = 2; t <= 8; t++)
+            rs.class_ms[t - 1] += be.timer_ms(t);
     }
 
     int seed_step(const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t nr, int64_t *first_invalid)
@@ -735,7 +993,8 @@ class NkEngine
             return fail(NK_EINVAL, "nkd_run before nkd_seed_finish");
         if (!staged)
             return fail(NK_EINVAL, "nkd_run without nkd_stage");
-        be.begin_timer(0);
+        if (!raw_staged)
+            be.begin_timer(0); /* a raw step's span started in stage_raw and ends in fetch_raw */
         for (int t = 1; t <= 8; t++)
             be.reset_timer(t);
         be.zero(d_high, (n_reads + 1) * sizeof(unsigned));
@@ -751,29 +1010,23 @@ class NkEngine
         be.begin_timer(7);
         be.decide(make_run(NK_MODE_SCORE, 0, 0), (unsigned)n_records, paired, cfg.coverage, d_accept);
         be.end_timer(7);
-        be.end_timer(0);
+        if (!raw_staged)
+            be.end_timer(0);
         ran = true;
         return NK_OK;
     }
 
     int fetch(uint8_t *accept, size_t nrec, int64_t *first_invalid)
     {
-        if (!ran)
-            return fail(NK_EINVAL, "nkd_fetch without nkd_run");
+        if (!ran || raw_staged)
+            return fail(NK_EINVAL, "nkd_fetch without nkd_stage + nkd_run");
         if (nrec != n_records)
             return fail(NK_EINVAL, "nkd_fetch: record count differs from the staged step");
         be.d2h(accept, d_accept, nrec);
         be.d2h(&h_ctr, d_ctr, 32);
         d2h_bytes += nrec + 32;
         be.sync();
-        be.timer_spans(0, spans);
-        last_total_ms = be.timer_ms(0);
-        last_probe_ms = be.timer_ms(1);
-        rs.run_ms += last_total_ms;
-        rs.probe_ms += last_probe_ms;
-        rs.class_ms[0] += last_probe_ms;
-        for (int t = 2; t <= 8; t++)
-            rs.class_ms[t - 1] += be.timer_ms(t);
+        finish_timers();
         int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         if (first_invalid)
             *first_invalid = (inv >= 0 && (size_t)inv < nrec) ? inv : -1;

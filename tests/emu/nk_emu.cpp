@@ -194,6 +194,73 @@ struct EmuBackend
         for (unsigned r : order(n_records))
             nk_decide_op(P, r, paired, coverage, accept);
     }
+    /* raw record text: the same per-record / per-entry functions as the kernels, entries visited in shuffled order */
+    bool prepare_scan(size_t, std::string &) { return true; }
+    void raw_index(const NkRaw &R)
+    {
+        unsigned n = 0;
+        for (unsigned p = 0; p < R.raw_bytes; p++)
+        {
+            if (R.raw[p] == 0)
+                *R.flags |= NK_RAW_NUL;
+            if (R.raw[p] == '\n')
+            {
+                if (n < R.nlpos_cap)
+                    R.nlpos[n] = p;
+                n++;
+            }
+        }
+        R.flags[1] = n;
+        for (unsigned i : order(R.n_records))
+            nk_raw_record_op(R, i);
+        const unsigned n_reads = R.n_records * R.stride;
+        unsigned run = 0;
+        for (unsigned j = 0; j < n_reads; j++)
+        {
+            R.opscan[j] = run;
+            run += R.nops[j];
+        }
+        R.opscan[n_reads] = run;
+        for (unsigned j : order(n_reads))
+            nk_raw_opbase_op(R, j);
+    }
+    void raw_emit(const NkRaw &R)
+    {
+        const unsigned n_out = R.n_records * R.stride;
+        for (unsigned e : order(n_out))
+        {
+            unsigned wi, mate, rec;
+            int counted, printed;
+            R.outlen[e] = nk_emit_len_op(R, e, wi, mate, rec, counted, printed);
+            if (!mate)
+            {
+                R.summary[6u * wi + 4u] += (unsigned)counted;
+                R.summary[6u * wi + 5u] += (unsigned)printed;
+            }
+        }
+        unsigned run = 0;
+        for (unsigned e = 0; e < n_out; e++)
+        {
+            R.outoff[e] = run;
+            run += R.outlen[e];
+        }
+        R.outoff[n_out] = run;
+        for (unsigned e : order(n_out))
+        {
+            const unsigned o = R.outoff[e], len = R.outoff[e + 1] - o;
+            if (!len)
+                continue;
+            unsigned wi, mate, rec;
+            int counted, printed;
+            nk_emit_len_op(R, e, wi, mate, rec, counted, printed);
+            const NkRawWin w = R.wins[wi];
+            const NkRawRec x = nk_raw_record(R, w, rec - w.rec0, (int)mate);
+            for (unsigned b = 0; b < len; b++)
+                R.out[o + b] = nk_emit_byte(R, x, mate, b, len);
+        }
+        for (unsigned w : order(R.n_wins))
+            nk_emit_summary_op(R, w);
+    }
     /* table dump and merged table: the same tile sizes / offsets / per-entry formatter as the kernels */
     bool dump_scan(const NkDumpSrc &src, unsigned long long lo, unsigned long long n, int k, int text,
                    unsigned long long *tile)
