@@ -43,7 +43,7 @@ sys.path.insert(0, str(ROOT))
 
 K, DEPTH, COVERAGE, PARTS, READ_LEN, TRANSCRIPTS, SEED = 25, 100, 0.9, 8, 150, 20000, 1
 SEED_RECORDS = 1 + 3_000_000  # 1 + 3e6 / forward_file_count, C:2242
-CLASSES = ["probe", "open", "apply", "classify", "sort_rank", "commit", "decide", "growth_undo"]
+CLASSES = ["probe", "open", "apply", "classify", "sort_rank", "commit", "decide", "growth_undo", "parse", "emit"]
 
 
 def shm_dir():

@@ -160,6 +160,13 @@ int nkd_stage_raw(nkd_engine *e, const uint8_t *raw, size_t raw_bytes, const nkd
  * 2 = nothing (single-end fq->fa, C:1995-1999).  out = page-locked buffer of out_cap bytes. */
 int nkd_fetch_raw(nkd_engine *e, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results,
                   int64_t *first_invalid);
+/* nkd_fetch_raw returns once the results are known; the text itself is still on its way to `out` on a copy
+ * stream (so that the engine's next step does not wait for it).  Call this before reading `out`.  slot = the
+ * value passed to nkd_fetch_raw_slot (nkd_fetch_raw uses slot 0); an engine keeps NKD_FETCH_SLOTS transfers apart. */
+#define NKD_FETCH_SLOTS 4
+int nkd_fetch_raw_slot(nkd_engine *e, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results,
+                       int64_t *first_invalid, int slot);
+int nkd_fetch_wait(nkd_engine *e, int slot);
 /* page-locked host memory for the staging buffers (cudaMallocHost / cudaFreeHost) */
 void *nkd_alloc_pinned(size_t bytes);
 void nkd_free_pinned(void *p);
@@ -178,8 +185,9 @@ typedef struct
     uint64_t probe_touches;  /* slots visited inside k_probe (the rest are visited by k_open) */
     uint64_t h2d_bytes, d2h_bytes;
     /* CUDA-event time per kernel class in scoring steps: 0 probe, 1 open, 2 apply, 3 classify,
-     * 4 sort+rank, 5 commit, 6 decide, 7 growth/undo */
-    double class_ms[8];
+     * 4 sort+rank, 5 commit, 6 decide, 7 growth/undo, 8 raw text -> reads (line ends, records, operation
+     * numbering), 9 accepted records' text (measure, scan, copy) */
+    double class_ms[10];
     uint64_t pend_events, open_ops, slow_events; /* list entries incl. chunk holes */
 } nkd_run_stats;
 int nkd_run_stats_get(nkd_engine *e, nkd_run_stats *out);
@@ -305,7 +313,7 @@ typedef struct
     double run_ms, probe_ms;
     uint64_t launches, probe_launches;
     uint64_t ops, touches, probe_touches, slow_events, expansions;
-    double class_ms[8]; /* see nkd_run_stats */
+    double class_ms[10]; /* see nkd_run_stats */
     uint64_t pend_events, open_ops;
     uint64_t engines; /* engines (stream + scratch + pipeline thread) of this context, over all its GPUs */
     /* device steps by kind: raw record text parsed on the device (the default) / records parsed by the host

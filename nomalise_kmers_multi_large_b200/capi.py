@@ -52,7 +52,7 @@ class RunStats(C.Structure):
     """nkd_run_stats"""
     _fields_ = [("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("run_ms", C.c_double),
                 ("probe_ms", C.c_double), ("probe_touches", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("class_ms", C.c_double * 8), ("pend_events", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("class_ms", C.c_double * 10), ("pend_events", C.c_uint64),
                 ("open_ops", C.c_uint64), ("slow_events", C.c_uint64)]
 
     def as_dict(self):
@@ -95,7 +95,7 @@ class Totals(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("run_ms", C.c_double), ("probe_ms", C.c_double),
                 ("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("ops", C.c_uint64),
                 ("touches", C.c_uint64), ("probe_touches", C.c_uint64), ("slow_events", C.c_uint64),
-                ("expansions", C.c_uint64), ("class_ms", C.c_double * 8), ("pend_events", C.c_uint64),
+                ("expansions", C.c_uint64), ("class_ms", C.c_double * 10), ("pend_events", C.c_uint64),
                 ("open_ops", C.c_uint64), ("engines", C.c_uint64), ("raw_steps", C.c_uint64),
                 ("parsed_steps", C.c_uint64)]
 
@@ -108,7 +108,7 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
                   "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from",
-                  "nkd_stage_raw", "nkd_fetch_raw"]
+                  "nkd_stage_raw", "nkd_fetch_raw", "nkd_fetch_raw_slot", "nkd_fetch_wait"]
 PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
@@ -148,6 +148,8 @@ def _declare_engine(lib):
     lib.nkd_device_count.restype = C.c_int
     lib.nkd_stage_raw.argtypes = [vp, u8p, sz, C.POINTER(RawSegment), C.c_int, C.c_int, C.c_int]
     lib.nkd_fetch_raw.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64)]
+    lib.nkd_fetch_raw_slot.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64), C.c_int]
+    lib.nkd_fetch_wait.argtypes = [vp, C.c_int]
     return lib
 
 
@@ -327,6 +329,7 @@ class Engine:
         res = (RawResult * len(windows))()
         inv = C.c_int64(-1)
         self._check(self.lib.nkd_fetch_raw(self.h, emit_mode, out.ctypes.data, out.size, res, C.byref(inv)))
+        self._check(self.lib.nkd_fetch_wait(self.h, 0))
         got = []
         for r in res:
             got.append((out[r.fwd_off:r.fwd_off + r.fwd_bytes].tobytes(), out[r.rev_off:r.rev_off + r.rev_bytes].tobytes(),

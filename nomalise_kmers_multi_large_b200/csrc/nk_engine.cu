@@ -666,7 +666,10 @@ struct CudaBackend
     {
         std::vector<cudaEvent_t> ev; /* start/stop pairs */
         size_t used = 0;
-    } timers[9];
+    } timers[11];
+    /* the accepted records' text leaves on its own stream, so the engine's next step starts without waiting for it */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done[NKD_FETCH_SLOTS] = {}, emit_ready = nullptr, last_copy = nullptr;
 
     bool ok(cudaError_t e, const char *what)
     {
@@ -716,6 +719,10 @@ struct CudaBackend
             cudaGetLastError();
             sync_ev = nullptr;
         }
+        ok(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < NKD_FETCH_SLOTS; i++)
+            ok(cudaEventCreateWithFlags(&copy_done[i], cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate");
+        ok(cudaEventCreateWithFlags(&emit_ready, cudaEventDisableTiming), "cudaEventCreate");
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         epoch(dev);
         cudaMemPool_t pool;
@@ -744,6 +751,17 @@ struct CudaBackend
             cudaFreeAsync(sort_tmp, stream);
         if (scan_tmp)
             cudaFreeAsync(scan_tmp, stream);
+        if (copy_stream)
+        {
+            cudaStreamSynchronize(copy_stream);
+            cudaStreamDestroy(copy_stream);
+        }
+        copy_stream = nullptr;
+        for (int i = 0; i < NKD_FETCH_SLOTS; i++)
+            if (copy_done[i])
+                cudaEventDestroy(copy_done[i]);
+        if (emit_ready)
+            cudaEventDestroy(emit_ready);
         if (stream)
         {
             cudaStreamSynchronize(stream);
@@ -984,6 +1002,22 @@ struct CudaBackend
         if (n_records)
             k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept), launches++;
     }
+
+    /* the engine's stream waits until the last text transfer has left the device buffer */
+    void copy_fence()
+    {
+        if (last_copy)
+            ok(cudaStreamWaitEvent(stream, last_copy, 0), "stream wait");
+    }
+    /* the caller has synchronised the engine's stream: the text is complete in d_out */
+    void copy_out(void *h, const void *d, size_t n, int slot)
+    {
+        if (n)
+            ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, copy_stream), "D2H copy");
+        ok(cudaEventRecord(copy_done[slot], copy_stream), "event record");
+        last_copy = copy_done[slot];
+    }
+    void copy_wait(int slot) { ok(cudaEventSynchronize(copy_done[slot]), "event synchronize"); }
 
     /* raw record text: line ends -> records -> operation numbering */
     void *scan_tmp = nullptr;

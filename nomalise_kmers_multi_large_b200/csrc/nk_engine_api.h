@@ -108,10 +108,25 @@ int nkd_stage_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes, const nkd
     h->e.be.enter();
     return nkd_done(h, h->e.stage_raw(raw, raw_bytes, segs, n_segs, paired, lines_per_record));
 }
-int nkd_fetch_raw(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid)
+int nkd_fetch_raw_slot(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results,
+                       int64_t *first_invalid, int slot)
 {
     h->e.be.enter();
-    return nkd_done(h, h->e.fetch_raw(emit_mode, out, out_cap, results, first_invalid));
+    if (slot < 0 || slot >= NKD_FETCH_SLOTS)
+        return h->e.fail(NK_EINVAL, "nkd_fetch_raw_slot: bad slot");
+    return nkd_done(h, h->e.fetch_raw(emit_mode, out, out_cap, results, first_invalid, slot));
+}
+int nkd_fetch_raw(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid)
+{
+    return nkd_fetch_raw_slot(h, emit_mode, out, out_cap, results, first_invalid, 0);
+}
+int nkd_fetch_wait(nkd_engine *h, int slot)
+{
+    h->e.be.enter();
+    if (slot < 0 || slot >= NKD_FETCH_SLOTS)
+        return h->e.fail(NK_EINVAL, "nkd_fetch_wait: bad slot");
+    h->e.be.copy_wait(slot);
+    return nkd_done(h, NK_OK);
 }
 int nkd_last_run_ms(nkd_engine *h, float *total_ms, float *probe_ms)
 {

@@ -166,6 +166,35 @@ static void nk_parallel_for(int n, int nthreads, nk_task_fn fn, void *arg)
     pthread_mutex_unlock(&nk_pool.mu);
 }
 
+/* NKB200_TRACE=file: one line per pipeline stage and step (engine, step, stage, start, end in seconds), for the
+ * timeline plots under profiles/ */
+static struct
+{
+    int on;
+    FILE *f;
+    pthread_mutex_t mu;
+    double t0;
+} nk_tr = {-1, NULL, PTHREAD_MUTEX_INITIALIZER, 0};
+
+static void nk_trace(int engine, int step, const char *stage, double a, double b)
+{
+    if (nk_tr.on == 0)
+        return;
+    pthread_mutex_lock(&nk_tr.mu);
+    if (nk_tr.on < 0)
+    {
+        const char *path = getenv("NKB200_TRACE");
+        nk_tr.f = path && *path ? fopen(path, "a") : NULL;
+        nk_tr.on = nk_tr.f != NULL;
+    }
+    if (nk_tr.on)
+    {
+        fprintf(nk_tr.f, "%d %d %s %.6f %.6f\n", engine, step, stage, a, b);
+        fflush(nk_tr.f);
+    }
+    pthread_mutex_unlock(&nk_tr.mu);
+}
+
 /* boolean environment switches: unset, empty and "0" mean off */
 static int nk_env_on(const char *name)
 {
@@ -714,6 +743,7 @@ typedef struct
     int have_parsed_bufs, have_raw_bufs; /* staging is allocated when a pipeline of that kind first runs */
     size_t max_step_bytes;
     double index_s, device_s, write_s;
+    double t_stage, t_run, t_fetch; /* NKB200_TIMES=1: where the raw-text device steps spend their host time */
     uint64_t h2d, d2h;
     int rc;
     char err[512];
@@ -807,6 +837,10 @@ void nk_destroy(nk_ctx *c)
 {
     if (!c)
         return;
+    if (nk_env_on("NKB200_TIMES"))
+        for (int d = 0; d < c->n_dev; d++)
+            fprintf(stderr, "[nk] engine %d: raw steps stage %.3f s, run %.3f s, fetch %.3f s\n", d, c->dev[d].t_stage,
+                    c->dev[d].t_run, c->dev[d].t_fetch);
     for (int d = 0; d < c->n_dev; d++)
     {
         nk_dev *dv = &c->dev[d];
@@ -838,6 +872,14 @@ void nk_destroy(nk_ctx *c)
     free(c->part);
     free(c->dev);
     free(c);
+}
+
+static int nk_alloc_raw_bufs(nk_ctx *c, nk_dev *dv);
+
+static void nk_alloc_raw_task(int d, void *a)
+{
+    nk_ctx *c = a;
+    c->dev[d].rc = nk_alloc_raw_bufs(c, &c->dev[d]);
 }
 
 int nk_create(const nk_config *cfg, nk_ctx **out)
@@ -997,6 +1039,19 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
                 return NK_ENOMEM;
             }
         }
+    }
+    /* the raw-text staging is pinned now, outside any timed region and on all engines at once (page-locking a GB
+     * takes ~0.4 s); the host parser's staging only if it is ever needed */
+    if (c->raw_mode)
+    {
+        nk_parallel_for(c->n_dev, c->n_dev, nk_alloc_raw_task, c);
+        for (int d = 0; d < c->n_dev; d++)
+            if (c->dev[d].rc)
+            {
+                nk_fail(NULL, NK_ENOMEM, "Memory allocation failed (staging buffers)");
+                nk_destroy(c);
+                return NK_ENOMEM;
+            }
     }
     /* seed staging: as large as the smallest engine's step */
     int min_dev_parts = max_dev_parts;
@@ -1925,9 +1980,12 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
     }
     sb->raw_bytes = at;
     sb->n_records = total;
+    double t1 = nk_now();
     if (sb->n_copies)
         nk_parallel_for(sb->n_copies, threads, nk_copy_task, sb->copies);
     dv->index_s += nk_now() - t0;
+    nk_trace((int)(dv - c->dev), -1, "cut", t0, t1);
+    nk_trace((int)(dv - c->dev), -1, "copy", t1, nk_now());
     return total;
 }
 
@@ -1946,10 +2004,19 @@ static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first
     if (turn)
         pthread_mutex_lock(turn);
     int rc = nkd_stage_raw(dv->eng, sb->raw, sb->raw_bytes, sb->rsegs, sb->n_rsegs, c->paired, c->cfg.in_fastq ? 4 : 2);
+    double t1 = nk_now();
     if (!rc)
         rc = nkd_run(dv->eng);
+    double t2 = nk_now();
     if (!rc)
-        rc = nkd_fetch_raw(dv->eng, nk_emit_mode(c), sb->out, (size_t)-1, sb->rres, first_invalid);
+        rc = nkd_fetch_raw_slot(dv->eng, nk_emit_mode(c), sb->out, (size_t)-1, sb->rres, first_invalid, (int)(sb - dv->sb));
+    double t3 = nk_now();
+    dv->t_stage += t1 - t0;
+    dv->t_run += t2 - t1;
+    dv->t_fetch += t3 - t2;
+    nk_trace((int)(dv - c->dev), (int)c->raw_steps, "stage", t0, t1);
+    nk_trace((int)(dv - c->dev), (int)c->raw_steps, "run", t1, t2);
+    nk_trace((int)(dv - c->dev), (int)c->raw_steps, "fetch", t2, t3);
     if (turn)
         pthread_mutex_unlock(turn);
     dv->device_s += nk_now() - t0;
@@ -2036,9 +2103,17 @@ static void nk_rawwrite_task(int idx, void *a)
 static int nk_write_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
 {
     double t0 = nk_now();
+    if (nkd_fetch_wait(dv->eng, (int)(sb - dv->sb)) != NK_OK) /* the text is still arriving on the engine's copy stream */
+    {
+        snprintf(dv->err, sizeof dv->err, "%s", nkd_last_error(dv->eng));
+        return NK_ENODEVICE;
+    }
+    double t1 = nk_now();
     nk_rawwrite_job job = {c, dv, sb, 0};
     nk_parallel_for(sb->n_rsegs * (c->paired ? 2 : 1), threads, nk_rawwrite_task, &job);
     dv->write_s += nk_now() - t0;
+    nk_trace((int)(dv - c->dev), -1, "d2h_wait", t0, t1);
+    nk_trace((int)(dv - c->dev), -1, "write", t1, nk_now());
     if (job.io_error)
     {
         snprintf(dv->err, sizeof dv->err, "error writing the output files: %s", strerror(errno));
@@ -2480,8 +2555,10 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
         p->last_processed = p->processed;
     }
     c->tot.index_seconds += nk_now() - t0;
+    nk_trace(-1, -1, "plan", t0, nk_now());
     if (!rc && raw_work)
         rc = nk_run_pipelines(c, 1);
+    nk_trace(-1, -1, "pipelines", t0, nk_now());
     /* whatever the raw-text pipeline did not take -- text the device declined (NUL bytes, lines of 1024+ chars),
      * a last record cut short by the end of the file -- goes through the byte-exact host parser from where each
      * partition stands */
@@ -2645,7 +2722,7 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
         out->d2h_bytes += rs.d2h_bytes;
         out->pend_events += rs.pend_events;
         out->open_ops += rs.open_ops;
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < 10; k++)
             out->class_ms[k] += rs.class_ms[k];
     }
     out->engines = (uint64_t)c->n_dev;

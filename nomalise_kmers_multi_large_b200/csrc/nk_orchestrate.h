@@ -757,7 +757,7 @@ class NkEngine
             recs += g.n_records;
             outs += (uint64_t)stride * g.n_records;
         }
-        if (recs * stride > cfg.max_step_reads || lines > raw_lines_cap)
+        if (recs * stride > cfg.max_step_reads || lines + 1 > raw_lines_cap)
             return fail(NK_EINVAL, "nkd_stage_raw: step exceeds the read limit given to nkd_create");
         if (((prev_end + 15) & ~15ull) != raw_bytes)
             return fail(NK_EINVAL, "nkd_stage_raw: raw_bytes must end the last window (rounded up to 16)");
@@ -803,23 +803,22 @@ class NkEngine
         raw.summary = d_summary;
         raw.inv_rec = NK_TMAX;
         be.begin_timer(0); /* the step's device span starts with its parsing */
+        be.reset_timer(9);
+        be.begin_timer(9);
         be.raw_index(raw);
+        be.end_timer(9);
         unsigned h_flags[4] = {0, 0, 0, 0};
         std::vector<unsigned> h_t((size_t)n_segs);
         be.d2h(h_flags, d_rflags, sizeof h_flags);
         be.d2h(h_t.data(), d_tout, (size_t)n_segs * sizeof(unsigned));
         be.sync();
         /* h_flags[1] = line ends found in the whole buffer */
-        if (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG))
+        if (h_flags[1] != lines || (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG | NK_RAW_SHAPE)))
         {
             be.end_timer(0);
             be.reset_timer(0);
-            return fail(NK_EIRREGULAR, "raw text needs the host parser (NUL byte or a line of 1024+ chars)");
-        }
-        if ((h_flags[0] & NK_RAW_SHAPE) || h_flags[1] != lines)
-        {
-            be.end_timer(0);
-            be.reset_timer(0);
+            if (h_flags[1] == lines && (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG)))
+                return fail(NK_EIRREGULAR, "raw text needs the host parser (NUL byte or a line of 1024+ chars)");
             return fail(NK_EINVAL, "nkd_stage_raw: a window does not hold the announced number of complete records");
         }
         uint64_t tot = 0;
@@ -842,7 +841,7 @@ class NkEngine
         return NK_OK;
     }
 
-    int fetch_raw(int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid)
+    int fetch_raw(int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid, int slot)
     {
         if (!ran || !raw_staged)
             return fail(NK_EINVAL, "nkd_fetch_raw without nkd_stage_raw + nkd_run");
@@ -853,10 +852,13 @@ class NkEngine
         int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         raw.emit_mode = emit_mode;
         raw.inv_rec = inv >= 0 ? (unsigned)inv : NK_TMAX;
-        be.begin_timer(7);
+        be.reset_timer(10);
+        be.begin_timer(10);
         be.zero(d_summary, 6 * (size_t)raw.n_wins * sizeof(unsigned long long));
+        be.copy_fence(); /* the previous step's text must have left d_out */
         be.raw_emit(raw);
-        be.end_timer(7);
+        be.end_timer(10);
+        be.end_timer(0);
         std::vector<unsigned long long> sm(6 * (size_t)raw.n_wins);
         be.d2h(sm.data(), d_summary, sm.size() * sizeof(unsigned long long));
         be.sync();
@@ -865,10 +867,7 @@ class NkEngine
             total = std::max<uint64_t>(total, std::max(sm[6 * w] + sm[6 * w + 1], sm[6 * w + 2] + sm[6 * w + 3]));
         if (total > out_cap)
             return fail(NK_EINVAL, "nkd_fetch_raw: output buffer too small");
-        if (total)
-            be.d2h(out, d_out, (size_t)total);
-        be.end_timer(0);
-        be.sync();
+        be.copy_out(out, d_out, (size_t)total, slot); /* on the copy stream: nkd_fetch_wait(slot) before `out` is read */
         d2h_bytes += total + sm.size() * 8 + 32;
         finish_timers();
         for (unsigned w = 0; w < raw.n_wins; w++)
@@ -901,7 +900,7 @@ class NkEngine
         rs.run_ms += last_total_ms;
         rs.probe_ms += last_probe_ms;
         rs.class_ms[0] += last_probe_ms;
-        for (int t = 2; t <= 8; t++)
+        for (int t = 2; t <= 10; t++)
             rs.class_ms[t - 1] += be.timer_ms(t);
     }
 

@@ -196,6 +196,9 @@ struct EmuBackend
     }
     /* raw record text: the same per-record / per-entry functions as the kernels, entries visited in shuffled order */
     bool prepare_scan(size_t, std::string &) { return true; }
+    void copy_fence() {}
+    void copy_out(void *h, const void *d, size_t n, int) { memcpy(h, d, n); }
+    void copy_wait(int) {}
     void raw_index(const NkRaw &R)
     {
         unsigned n = 0;

@@ -209,3 +209,85 @@ def random_case(rnd):
                 n_seed_reads=rnd.choice([0, 20, 200]), steps=rnd.choice([1, 2, 4]), records_per_step=rnd.choice([5, 40, 150]),
                 paired=rnd.random() < 0.7, read_len=rnd.choice([(k, k + 3), (40, 120), (100, 160), (k, 300)]),
                 err=rnd.choice([0.0, 0.01, 0.05]))
+
+
+def fasta_of(header: bytes, seq: bytes, tag: bytes) -> bytes:
+    """fastq_to_fasta (C:852-876) on the already N->A scrubbed sequence"""
+    h = b">" + header[1:]
+    if len(h) < 2 or not h.endswith(b"/" + tag):
+        h += b"/" + tag
+    return h + b"\n" + seq + b"\n"
+
+
+def run_raw_case(lib, *, seed=1, k=15, canonical=False, depth=3, coverage=0.9, n_parts=2, cap0=4099, genome_len=3000,
+                 steps=3, records_per_step=120, paired=True, fastq=True, emit_mode=0, read_len=(10, 120), err=0.01):
+    """Steps handed over as raw record text (nkd_stage_raw / nkd_fetch_raw): the device finds the lines, applies
+    the length gate, scores and assembles the accepted records' text.  Compared with the oracle's sequential
+    table driven by the worker loop's rules (C:1605-1674): text of every partition and mate, processed / printed,
+    and every slot of every table after every step."""
+    rng = np.random.default_rng(seed)
+    genome = make_genome(rng, genome_len)
+    lo, hi = read_len
+    per_rec = 2 * (hi + 40) + 8
+    eng = capi.Engine(k=k, canonical=canonical, depth_per_part=depth, coverage=coverage, n_parts=n_parts, capacity0=cap0,
+                      max_step_reads=2 * records_per_step * n_parts + 64, max_step_bytes=1 << 16,
+                      max_step_ops=2 * records_per_step * n_parts * (hi + 1) + 4096,
+                      max_raw_bytes=2 * records_per_step * n_parts * per_rec + 4096, lib=lib)
+    try:
+        eng.seed_finish()
+        otabs = [ol.OracleTable(cap0) for _ in range(n_parts)]
+        serial = 0
+        totals = {"processed": 0, "printed": 0, "dropped": 0}
+        for step in range(steps):
+            windows, want = [], []
+            for p in range(n_parts):
+                n = int(rng.integers(1, records_per_step + 1))
+                texts, recs = [[], []], []
+                for _ in range(n):
+                    mates = []
+                    for m in range(2 if paired else 1):
+                        s = sample_read(rng, genome, lo, hi, err, n_rate=0.05)
+                        if m:
+                            s = revcomp(s)
+                        serial += 1
+                        name = b"r%d %s" % (serial, b"x" * int(rng.integers(0, 9)))
+                        if rng.random() < 0.5:
+                            name += b"/%d" % (m + 1)   # fastq_to_fasta keeps an existing /1 or /2
+                        lead = b"@" if fastq else b">"
+                        rec = lead + name + b"\n" + s + b"\n" + ((b"+\n" + b"I" * len(s) + b"\n") if fastq else b"")
+                        texts[m].append(rec)
+                        mates.append((lead + name, s))
+                    recs.append(mates)
+                windows.append((p, n, b"".join(texts[0]), b"".join(texts[1]) if paired else None))
+                out = [[], []]
+                processed = printed = 0
+                for mates in recs:
+                    if any(len(s) < k for _, s in mates):
+                        totals["dropped"] += 1
+                        continue  # the pair vanishes: no counter, no table access (C:1430-1443)
+                    scores = [otabs[p].score(s, k, canonical, depth) for _, s in mates]
+                    processed += 1
+                    if all(ol.keep_mate(h, t, coverage) for h, t in scores):
+                        printed += 1
+                        for m, (hdr, s) in enumerate(mates):
+                            s2 = s.replace(b"N", b"A")
+                            if emit_mode == 0:
+                                out[m].append(hdr + b"\n" + s2 + b"\n" + ((b"+\n" + b"I" * len(s) + b"\n") if fastq else b""))
+                            elif emit_mode == 1:
+                                out[m].append(fasta_of(hdr, s2, b"%d" % (m + 1)))
+                want.append((b"".join(out[0]), b"".join(out[1]), processed, printed))
+                totals["processed"] += processed
+                totals["printed"] += printed
+            got, inv = eng.step_raw(windows, paired, lines_per_record=4 if fastq else 2, emit_mode=emit_mode)
+            assert inv == -1
+            for p in range(n_parts):
+                assert got[p][2:] == want[p][2:], (step, p, "processed/printed", got[p][2:], want[p][2:])
+                assert got[p][0] == want[p][0], (step, p, "forward text differs")
+                assert got[p][1] == want[p][1], (step, p, "reverse text differs")
+                ek, ec = eng.export(p)
+                okk, okc = otabs[p].export()
+                assert np.array_equal(ek, okk), f"keys differ step {step} part {p}"
+                assert np.array_equal(ec, okc), f"counts differ step {step} part {p}"
+        return totals
+    finally:
+        eng.close()

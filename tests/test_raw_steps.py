@@ -1,0 +1,71 @@
+"""Steps as raw record text (nkd_stage_raw / nkd_fetch_raw, include/nk_b200.h): the worker loop's record reader,
+length gate, scoring and printing (C:1605-1674, C:852-876) done on the device, against the oracle.  The same
+scenarios run on the CPU emulation of the engine (host-side logic, per-record functions of nk_core.h) and, marked
+gpu, on the sm_100a kernels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nomalise_kmers_multi_large_b200 import capi
+from tests import engine_cases as ec
+
+CASES = {
+    "fq_paired": dict(k=15, depth=3, n_parts=2),
+    "fq_paired_canonical_growth": dict(k=25, canonical=True, depth=2, cap0=257, n_parts=3, read_len=(20, 150)),
+    "fq_to_fa": dict(k=21, depth=4, n_parts=2, emit_mode=1, read_len=(15, 100)),
+    "single_end": dict(k=17, depth=3, n_parts=2, paired=False),
+    "single_end_fq_to_fa_prints_nothing": dict(k=17, depth=3, n_parts=1, paired=False, emit_mode=2),
+    "fasta_in_out": dict(k=15, depth=5, n_parts=2, fastq=False, coverage=0.5),
+    "k5_long_reads": dict(k=5, depth=40, n_parts=1, read_len=(5, 1000), records_per_step=30, genome_len=6000),
+    "k31_one_record_steps": dict(k=31, depth=2, n_parts=4, records_per_step=1, steps=6, read_len=(25, 60)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_raw_steps_match_oracle_emu(emu_lib, name):
+    t = ec.run_raw_case(emu_lib, seed=11, **CASES[name])
+    assert t["processed"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_raw_steps_match_oracle_gpu(cuda_lib, name):
+    for seed in (11, 12):
+        t = ec.run_raw_case(cuda_lib, seed=seed, **CASES[name])
+        assert t["processed"] > 0
+
+
+def _declined(lib, text_f, text_r, n):
+    eng = capi.Engine(k=15, depth_per_part=3, n_parts=1, capacity0=257, max_step_reads=64, max_step_bytes=1 << 12,
+                      max_step_ops=1 << 14, max_raw_bytes=1 << 16, lib=lib)
+    try:
+        eng.seed_finish()
+        with pytest.raises(capi.NkError) as e:
+            eng.step_raw([(0, n, text_f, text_r)], True)
+        return e.value.code
+    finally:
+        eng.close()
+
+
+REC = b"@a\nACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIII\n"
+
+
+def check_declined(lib):
+    """text the record reader of the reference splits differently goes back to the host parser (NK_EIRREGULAR = -7);
+    windows that do not hold the announced records are the caller's bug (NK_EINVAL)"""
+    nul = REC.replace(b"GTAC", b"GT\0C", 1)
+    long_line = b"@a\n" + b"ACGT" * 300 + b"\n+\n" + b"I" * 1200 + b"\n"
+    assert _declined(lib, REC + nul, REC + REC, 2) == -7
+    assert _declined(lib, REC + long_line, REC + REC, 2) == -7
+    assert _declined(lib, REC + REC, REC + REC, 3) == -1            # fewer line ends than announced
+    assert _declined(lib, REC + REC + b"@b\n", REC + REC, 2) == -1   # window does not end on its last record
+
+
+def test_raw_text_the_device_declines_emu(emu_lib):
+    check_declined(emu_lib)
+
+
+@pytest.mark.gpu
+def test_raw_text_the_device_declines_gpu(cuda_lib):
+    check_declined(cuda_lib)
