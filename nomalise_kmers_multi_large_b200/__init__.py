@@ -5,6 +5,6 @@ command-line program ``csrc/normalise_kmers_multi_large_b200``; this package onl
 """
 from . import capi
 from .capi import Engine, NkError, load_library
-from .pipeline import Pipeline, plan_ranges, run_cli
+from .pipeline import Pipeline, count_chunk_lines, plan_ranges, run_cli
 
-__all__ = ["capi", "Engine", "Pipeline", "NkError", "load_library", "plan_ranges", "run_cli"]
+__all__ = ["capi", "Engine", "Pipeline", "NkError", "load_library", "plan_ranges", "count_chunk_lines", "run_cli"]

@@ -63,6 +63,16 @@ class Pipeline:
         self._check(self.lib.nk_process_planned(self.h, pf, nf, pr, nr, plan[0].ctypes.data, plan[1].ctypes.data,
                                                 plan[2].ctypes.data, plan[3].ctypes.data))
 
+    def process_indexed(self, fwd, rev, fwd_counts, rev_counts):
+        """nk_process_indexed: like process_paired / process_single, with the per-chunk line-end counts of the files
+        (count_chunk_lines, gathered from all ranks) so that the files are not scanned again for planning"""
+        pf, nf = self._ptr(fwd)
+        pr, nr = self._ptr(rev) if rev is not None else (None, 0)
+        fc = np.ascontiguousarray(fwd_counts, dtype=np.uint32)
+        rc_ = np.ascontiguousarray(rev_counts, dtype=np.uint32) if rev is not None else None
+        self._check(self.lib.nk_process_indexed(self.h, pf, nf, pr, nr, fc.ctypes.data,
+                                                rc_.ctypes.data if rc_ is not None else None))
+
     def process_single(self, fwd):
         pf, nf = self._ptr(fwd)
         self._check(self.lib.nk_process_single(self.h, pf, nf))
@@ -106,6 +116,23 @@ def plan_ranges(fwd, rev, partitions, fastq=True, threads=0, lib=None):
     if rc != capi.NK_OK:
         raise capi.NkError(rc, err.value.decode())
     return plan
+
+
+def count_chunk_lines(buf, rank=0, world=1, threads=0, lib=None):
+    """nk_count_chunk_lines for this rank's share of a file's chunks: returns (counts of the share as uint32,
+    number of chunks of the whole file, chunks per share).  Shares are equal blocks, the last one may be shorter."""
+    lib = lib if lib is not None else capi.load_library()
+    p, n = Pipeline._ptr(buf)
+    chunk = lib.nk_line_chunk_bytes()
+    n_chunks = (n + chunk - 1) // chunk
+    share = (n_chunks + world - 1) // world
+    first = min(n_chunks, rank * share)
+    mine = max(0, min(share, n_chunks - first))
+    counts = np.zeros(max(mine, 1), dtype=np.uint32)
+    rc = lib.nk_count_chunk_lines(p, n, first, mine, counts.ctypes.data, threads)
+    if rc != capi.NK_OK:
+        raise capi.NkError(rc, "nk_count_chunk_lines")
+    return counts[:mine], n_chunks, share
 
 
 def run_cli(args, cwd=None, env=None, **kw):

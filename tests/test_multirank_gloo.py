@@ -22,10 +22,14 @@ def free_port():
     return p
 
 
-def test_two_ranks_equal_one_process(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["planned", "indexed"])
+def test_two_ranks_equal_one_process(tmp_path, mode):
     subprocess.run(["make", "-C", str(ROOT / "tests" / "emu")], check=True, capture_output=True)
     ol.build_oracle()
-    f, r = cc.synth(tmp_path, "s", 1500, seed=11)
+    f, r = cc.synth(tmp_path, "s", 4000, seed=11)   # a few 256-KB chunks per file, so that both ranks count some
     parts, k, depth = 4, 21, 16
     want = cc.run_cli(ol.ORACLE_CLI, ["-f", f, "-r", r, "-k", k, "-c", "-p", parts, "-d", depth, "-m", 1], tmp_path / "oracle")
     out = tmp_path / "ranks"
@@ -36,7 +40,7 @@ def test_two_ranks_equal_one_process(tmp_path):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    LOCAL_RANK=str(rank))
         procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "_rank_worker.py"), str(f), str(r), str(out),
-                                       str(parts), str(k), str(depth), str(EMU_LIB)], env=env,
+                                       str(parts), str(k), str(depth), str(EMU_LIB), mode], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     for p in procs:
         o, e = p.communicate(timeout=600)
