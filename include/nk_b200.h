@@ -153,6 +153,10 @@ typedef struct
     uint64_t fwd_off, fwd_bytes, rev_off, rev_bytes;
     uint64_t processed, printed;
 } nkd_raw_result;
+/* Optional: start copying the NEXT step's buffer to the device while the current step runs (its own stream, a
+ * second device buffer); nkd_stage_raw of that very buffer then finds the bytes in place.  The buffer must stay
+ * untouched until that step's nkd_stage_raw has returned. */
+int nkd_upload_raw(nkd_engine *e, const uint8_t *raw, size_t raw_bytes);
 /* returns NK_EIRREGULAR (and stages nothing) when the text needs the byte-exact host parser */
 int nkd_stage_raw(nkd_engine *e, const uint8_t *raw, size_t raw_bytes, const nkd_raw_segment *segs, int n_segs,
                   int paired, int lines_per_record);

@@ -108,7 +108,8 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_export", "nkd_extract_keys", "nkd_stage_segments", "nkd_alloc_pinned", "nkd_free_pinned",
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
                   "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from",
-                  "nkd_stage_raw", "nkd_fetch_raw", "nkd_fetch_raw_slot", "nkd_fetch_wait"]
+                  "nkd_stage_raw", "nkd_fetch_raw", "nkd_fetch_raw_slot", "nkd_fetch_wait",
+                  "nkd_upload_raw"]
 PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
@@ -150,6 +151,7 @@ def _declare_engine(lib):
     lib.nkd_fetch_raw.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64)]
     lib.nkd_fetch_raw_slot.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64), C.c_int]
     lib.nkd_fetch_wait.argtypes = [vp, C.c_int]
+    lib.nkd_upload_raw.argtypes = [vp, u8p, sz]
     return lib
 
 

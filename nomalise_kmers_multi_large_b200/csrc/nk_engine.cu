@@ -668,7 +668,8 @@ struct CudaBackend
         size_t used = 0;
     } timers[11];
     /* the accepted records' text leaves on its own stream, so the engine's next step starts without waiting for it */
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, up_stream = nullptr;
+    cudaEvent_t up_done = nullptr;
     cudaEvent_t copy_done[NKD_FETCH_SLOTS] = {}, emit_ready = nullptr, last_copy = nullptr;
 
     bool ok(cudaError_t e, const char *what)
@@ -723,6 +724,8 @@ struct CudaBackend
         for (int i = 0; i < NKD_FETCH_SLOTS; i++)
             ok(cudaEventCreateWithFlags(&copy_done[i], cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate");
         ok(cudaEventCreateWithFlags(&emit_ready, cudaEventDisableTiming), "cudaEventCreate");
+        ok(cudaStreamCreateWithFlags(&up_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        ok(cudaEventCreateWithFlags(&up_done, cudaEventDisableTiming), "cudaEventCreate");
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         epoch(dev);
         cudaMemPool_t pool;
@@ -762,6 +765,14 @@ struct CudaBackend
                 cudaEventDestroy(copy_done[i]);
         if (emit_ready)
             cudaEventDestroy(emit_ready);
+        if (up_stream)
+        {
+            cudaStreamSynchronize(up_stream);
+            cudaStreamDestroy(up_stream);
+        }
+        up_stream = nullptr;
+        if (up_done)
+            cudaEventDestroy(up_done);
         if (stream)
         {
             cudaStreamSynchronize(stream);
@@ -1003,6 +1014,14 @@ struct CudaBackend
             k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept), launches++;
     }
 
+    /* the next step's text goes to the device on its own stream ... */
+    void upload(void *d, const void *h, size_t n)
+    {
+        ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, up_stream), "H2D copy");
+        ok(cudaEventRecord(up_done, up_stream), "event record");
+    }
+    /* ... and the engine's stream picks it up when it has landed */
+    void upload_fence() { ok(cudaStreamWaitEvent(stream, up_done, 0), "stream wait"); }
     /* the engine's stream waits until the last text transfer has left the device buffer */
     void copy_fence()
     {

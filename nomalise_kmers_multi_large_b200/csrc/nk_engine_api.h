@@ -108,6 +108,11 @@ int nkd_stage_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes, const nkd
     h->e.be.enter();
     return nkd_done(h, h->e.stage_raw(raw, raw_bytes, segs, n_segs, paired, lines_per_record));
 }
+int nkd_upload_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes)
+{
+    h->e.be.enter();
+    return nkd_done(h, h->e.upload_raw(raw, raw_bytes));
+}
 int nkd_fetch_raw_slot(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results,
                        int64_t *first_invalid, int slot)
 {

@@ -1996,7 +1996,7 @@ static int nk_emit_mode(const nk_ctx *c)
     return 0;
 }
 
-static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_invalid)
+static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, nk_stepbuf *next, int64_t *first_invalid)
 {
     *first_invalid = -1;
     double t0 = nk_now();
@@ -2004,6 +2004,8 @@ static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first
     if (turn)
         pthread_mutex_lock(turn);
     int rc = nkd_stage_raw(dv->eng, sb->raw, sb->raw_bytes, sb->rsegs, sb->n_rsegs, c->paired, c->cfg.in_fastq ? 4 : 2);
+    if (!rc && next && next->raw_bytes) /* the following step is built already: its bytes travel while this one runs */
+        nkd_upload_raw(dv->eng, next->raw, next->raw_bytes);
     double t1 = nk_now();
     if (!rc)
         rc = nkd_run(dv->eng);
@@ -2144,7 +2146,15 @@ static void *nk_gpu_thread(void *a)
         if (stop)
             break;
         nk_stepbuf *sb = &pp->dv->sb[step % NK_NBUF];
-        int rc = pp->raw ? nk_gpu_step_raw(pp->c, pp->dv, sb, &pp->first_invalid[step % NK_NBUF])
+        nk_stepbuf *next = NULL;
+        if (pp->raw && !nk_env_on("NKB200_NO_PREFETCH"))
+        {
+            pthread_mutex_lock(&pp->mu);
+            if (pp->built > step + 1)
+                next = &pp->dv->sb[(step + 1) % NK_NBUF];
+            pthread_mutex_unlock(&pp->mu);
+        }
+        int rc = pp->raw ? nk_gpu_step_raw(pp->c, pp->dv, sb, next, &pp->first_invalid[step % NK_NBUF])
                          : nk_gpu_step(pp->c, pp->dv, sb, &pp->first_invalid[step % NK_NBUF]);
         if (rc)
         {

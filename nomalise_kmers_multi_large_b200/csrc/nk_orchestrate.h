@@ -101,6 +101,9 @@ class NkEngine
 
     /* raw record text path (nkd_stage_raw / nkd_fetch_raw) */
     unsigned char *d_raw = nullptr, *d_out = nullptr;
+    unsigned char *d_raw_next = nullptr; /* second text buffer: the next step's bytes arrive while this one runs */
+    const uint8_t *uploaded = nullptr;   /* host buffer whose bytes d_raw_next holds (or is receiving) */
+    size_t uploaded_bytes = 0;
     unsigned *d_tile = nullptr, *d_nlpos = nullptr, *d_nops = nullptr, *d_opscan = nullptr, *d_tout = nullptr;
     unsigned *d_rflags = nullptr, *d_outlen = nullptr, *d_outoff = nullptr;
     unsigned long long *d_summary = nullptr;
@@ -203,6 +206,7 @@ class NkEngine
         be.release(d_parts);
         be.release(d_bloom);
         be.release(d_raw);
+        be.release(d_raw_next);
         be.release(d_out);
         be.release(d_tile);
         be.release(d_nlpos);
@@ -687,6 +691,7 @@ class NkEngine
             return fail(NK_EINVAL, "nkd_stage_raw: a step's raw text must stay below 4 GiB");
         bool ok = true;
         ok &= dalloc(d_raw, raw_cap + 64);
+        ok &= dalloc(d_raw_next, raw_cap + 64);
         ok &= dalloc(d_out, raw_cap + 2 * raw_reads_cap + 64);
         ok &= dalloc(d_tile, raw_cap / NK_RAW_TILE + 4);
         ok &= dalloc(d_nlpos, raw_lines_cap);
@@ -700,6 +705,20 @@ class NkEngine
         ok &= dalloc(d_wins, NK_MAX_PARTITIONS);
         if (!ok || !be.prepare_scan((size_t)std::max<uint64_t>(raw_reads_cap + 1, raw_cap / NK_RAW_TILE + 4), err))
             return fail(NK_ENOMEM, "nkd_stage_raw: cannot allocate the raw-text scratch");
+        return NK_OK;
+    }
+
+    int upload_raw(const uint8_t *host_raw, size_t raw_bytes)
+    {
+        int rc = raw_prepare();
+        if (rc)
+            return rc;
+        if ((raw_bytes & 15u) || raw_bytes > raw_cap)
+            return fail(NK_EINVAL, "nkd_upload_raw: bad size");
+        be.upload(d_raw_next, host_raw, raw_bytes);
+        uploaded = host_raw;
+        uploaded_bytes = raw_bytes;
+        h2d_bytes += raw_bytes;
         return NK_OK;
     }
 
@@ -762,7 +781,14 @@ class NkEngine
         if (((prev_end + 15) & ~15ull) != raw_bytes)
             return fail(NK_EINVAL, "nkd_stage_raw: raw_bytes must end the last window (rounded up to 16)");
         /* windows go over as they are; the gaps keep whatever the host put there (neither '\n' nor NUL) */
-        for (int s = 0; s < n_segs; s++)
+        const bool prefetched = uploaded == host_raw && uploaded_bytes == raw_bytes;
+        uploaded = nullptr;
+        if (prefetched)
+        { /* the bytes were sent ahead (nkd_upload_raw): take that buffer once its copy has landed */
+            std::swap(d_raw, d_raw_next);
+            be.upload_fence();
+        }
+        for (int s = 0; s < n_segs && !prefetched; s++)
         {
             const NkRawWin &w = h_wins[s];
             unsigned lo = w.f_off, hi = (w.f_off + w.f_bytes + 15u) & ~15u;

@@ -196,6 +196,8 @@ struct EmuBackend
     }
     /* raw record text: the same per-record / per-entry functions as the kernels, entries visited in shuffled order */
     bool prepare_scan(size_t, std::string &) { return true; }
+    void upload(void *d, const void *h, size_t n) { memcpy(d, h, n); }
+    void upload_fence() {}
     void copy_fence() {}
     void copy_out(void *h, const void *d, size_t n, int) { memcpy(h, d, n); }
     void copy_wait(int) {}
