@@ -334,6 +334,7 @@ def run_ours(args):
         if sampler:
             sampler.active = timed
         t0 = time.perf_counter()
+        t_plan = 0.0
         if world > 1:
             # every rank counts the line ends of its share of the files' chunks; the counts (4 bytes per 256 KB of
             # input) are all-gathered, and each rank plans its own partitions from all of them (nk_process_indexed)
@@ -345,6 +346,7 @@ def run_ours(args):
                 allc = torch.empty(share * world, dtype=torch.int32, device=pad.device)
                 dist.all_gather_into_tensor(allc, pad)
                 counts.append(allc.cpu().numpy().view(np.uint32)[:n_chunks].copy())
+            t_plan = time.perf_counter() - t0
             ctx.process_indexed(fwd, rev, counts[0], counts[1])
         else:
             ctx.process_paired(fwd, rev)
@@ -360,7 +362,7 @@ def run_ours(args):
             agg["ms_" + name] = tot["class_ms"][i]
         agg["h2d_bytes"] -= before["h2d_bytes"]       # seeding traffic is outside the timed region
         agg["d2h_bytes"] -= before["d2h_bytes"]
-        agg["wall_s"], agg["seed_s"] = wall, seed_s
+        agg["wall_s"], agg["seed_s"], agg["count_s"] = wall, seed_s, t_plan
         ctx.close()
         ok = True
         if verify and golden is not None:
@@ -409,7 +411,7 @@ def run_ours(args):
     wall_s = sum(all_max(dist, local, s["wall_s"]) for s in steps)
     keys = ["processed", "printed", "skipped", "launches", "probe_launches", "ops", "touches", "probe_touches",
             "slow_events", "expansions", "h2d_bytes", "d2h_bytes", "probe_ms", "index_seconds", "device_seconds",
-            "write_seconds", "seed_s", "pend_events", "open_ops", "engines", "raw_steps", "parsed_steps"] + ["ms_" + c for c in CLASSES]
+            "write_seconds", "seed_s", "count_s", "pend_events", "open_ops", "engines", "raw_steps", "parsed_steps"] + ["ms_" + c for c in CLASSES]
     sums = dict(zip(keys, all_sum(dist, local, [sum(s[k] for s in steps) for k in keys])))
     ikeys = ["probe_ms", "probe_launches", "probe_touches", "processed", "run_ms"] + ["ms_" + c for c in CLASSES]
     iso = dict(zip(ikeys, all_sum(dist, local, [isolated[k] for k in ikeys]))) if isolated else None
@@ -442,8 +444,11 @@ def run_ours(args):
                                if golden is not None else "no reference output recorded for this workload size")},
         "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": sums["h2d_bytes"] / n,
                 "d2h_bytes_per_step": sums["d2h_bytes"] / n, "ms_per_step": e2e_s * 1e3,
-                "host_s_per_step": {"stage_copy": sums["index_seconds"] / n, "device_calls": sums["device_seconds"] / n,
-                                    "write": sums["write_seconds"] / n}},
+                # per rank: busy time of the slowest engine's pipeline stages (they overlap), averaged over the ranks
+                "host_s_per_step": {"count_lines_allgather": sums["count_s"] / n / world,
+                                    "stage_copy": sums["index_seconds"] / n / world,
+                                    "device_calls": sums["device_seconds"] / n / world,
+                                    "write": sums["write_seconds"] / n / world}},
         # H2D ingest against what PCIe and the host can do (north_star; SURVEY 8(d) "ingest bound")
         "ingest": {"h2d_gbs": sums["h2d_bytes"] / n / e2e_s / 1e9, "h2d_gbs_per_gpu": sums["h2d_bytes"] / n / e2e_s / 1e9 / world,
                    "pcie_peak_gbs": PCIE_H2D_GBS, "frac_of_pcie_per_gpu": sums["h2d_bytes"] / n / e2e_s / 1e9 / world / PCIE_H2D_GBS,

@@ -145,7 +145,7 @@ int nkd_run_stats_get(nkd_engine *h, nkd_run_stats *out)
 {
     *out = h->e.rs;
     out->launches = h->e.be.launches;
-    out->h2d_bytes = h->e.h2d_bytes;
+    out->h2d_bytes = h->e.h2d_bytes + h->e.upload_total;
     out->d2h_bytes = h->e.d2h_bytes;
     return NK_OK;
 }

@@ -184,7 +184,10 @@ static void nk_trace(int engine, int step, const char *stage, double a, double b
     if (nk_tr.on < 0)
     {
         const char *path = getenv("NKB200_TRACE");
-        nk_tr.f = path && *path ? fopen(path, "a") : NULL;
+        char name[1024];
+        if (path && *path)
+            snprintf(name, sizeof name, "%s.%d", path, (int)getpid()); /* one file per process (rank) */
+        nk_tr.f = path && *path ? fopen(name, "a") : NULL;
         nk_tr.on = nk_tr.f != NULL;
     }
     if (nk_tr.on)
@@ -1799,7 +1802,29 @@ typedef struct
     int64_t first_invalid[NK_NBUF];
     int t_index, t_write;
     int raw; /* 1: steps are raw record text parsed on the device; 0: parsed here */
+    /* raw text is sent ahead of its step (nkd_upload_raw) by whichever of the two threads sees the chance first:
+     * the GPU stage right after it has staged the step before, or the builder when it finishes a step later than
+     * that.  staged = steps whose nkd_stage_raw has returned; uploaded = steps whose upload has been claimed */
+    int staged, uploaded, prefetch;
 } nk_pipe;
+
+/* step `u` is built and the step before it has been staged (its device buffer is the free one): send it ahead */
+static void nk_try_upload(nk_pipe *pp, int u)
+{
+    if (!pp->raw || !pp->prefetch)
+        return;
+    pthread_mutex_lock(&pp->mu);
+    int go = pp->built > u && pp->staged == u && pp->uploaded < u && !pp->abort_rc;
+    if (go)
+        pp->uploaded = u;
+    pthread_mutex_unlock(&pp->mu);
+    if (go)
+    {
+        nk_stepbuf *sb = &pp->dv->sb[u % NK_NBUF];
+        if (sb->raw_bytes)
+            nkd_upload_raw(pp->dv->eng, sb->raw, sb->raw_bytes);
+    }
+}
 
 static int nk_gpu_step(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int64_t *first_invalid)
 {
@@ -1882,10 +1907,41 @@ static uint64_t nk_raw_records_in(const nk_lineidx *li, size_t start, size_t end
     return n;
 }
 
+/* The staging buffer is written once and next read by the GPU's copy engine: streaming stores keep it out of the
+ * caches and spare the read-for-ownership of every destination line (the host side of this path is bound by
+ * memory bandwidth, profiles/r02_host_traffic.md). */
+__attribute__((target("avx2"))) static void nk_copy_stream_avx2(uint8_t *dst, const char *src, size_t n)
+{
+    size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+    if (head > n)
+        head = n;
+    memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    n -= head;
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128)
+    {
+        __m256i a = _mm256_loadu_si256((const __m256i *)(src + i)), b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+        __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64)), d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+        _mm256_stream_si256((__m256i *)(dst + i), a);
+        _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+        _mm256_stream_si256((__m256i *)(dst + i + 64), c);
+        _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+    }
+    _mm_sfence();
+    memcpy(dst + i, src + i, n - i);
+}
+
+static int nk_have_avx2 = -1;
+
 static void nk_copy_task(int i, void *a)
 {
     const nk_copy *cp = &((const nk_copy *)a)[i];
-    memcpy(cp->dst, cp->src, cp->n);
+    if (nk_have_avx2 > 0)
+        nk_copy_stream_avx2(cp->dst, cp->src, cp->n);
+    else
+        memcpy(cp->dst, cp->src, cp->n);
 }
 
 /* One step: for every partition of the engine the next (at most step_pairs) records of both files, as two windows
@@ -1981,6 +2037,11 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
     sb->raw_bytes = at;
     sb->n_records = total;
     double t1 = nk_now();
+    if (nk_have_avx2 < 0)
+    {
+        __builtin_cpu_init();
+        nk_have_avx2 = __builtin_cpu_supports("avx2") && !nk_env_on("NKB200_PLAIN_MEMCPY");
+    }
     if (sb->n_copies)
         nk_parallel_for(sb->n_copies, threads, nk_copy_task, sb->copies);
     dv->index_s += nk_now() - t0;
@@ -1996,7 +2057,7 @@ static int nk_emit_mode(const nk_ctx *c)
     return 0;
 }
 
-static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, nk_stepbuf *next, int64_t *first_invalid)
+static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, nk_pipe *pp, int step, int64_t *first_invalid)
 {
     *first_invalid = -1;
     double t0 = nk_now();
@@ -2004,8 +2065,13 @@ static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, nk_stepbuf *ne
     if (turn)
         pthread_mutex_lock(turn);
     int rc = nkd_stage_raw(dv->eng, sb->raw, sb->raw_bytes, sb->rsegs, sb->n_rsegs, c->paired, c->cfg.in_fastq ? 4 : 2);
-    if (!rc && next && next->raw_bytes) /* the following step is built already: its bytes travel while this one runs */
-        nkd_upload_raw(dv->eng, next->raw, next->raw_bytes);
+    if (!rc && pp)
+    { /* the following step's bytes travel while this one runs */
+        pthread_mutex_lock(&pp->mu);
+        pp->staged = step + 1;
+        pthread_mutex_unlock(&pp->mu);
+        nk_try_upload(pp, step + 1);
+    }
     double t1 = nk_now();
     if (!rc)
         rc = nkd_run(dv->eng);
@@ -2146,15 +2212,7 @@ static void *nk_gpu_thread(void *a)
         if (stop)
             break;
         nk_stepbuf *sb = &pp->dv->sb[step % NK_NBUF];
-        nk_stepbuf *next = NULL;
-        if (pp->raw && !nk_env_on("NKB200_NO_PREFETCH"))
-        {
-            pthread_mutex_lock(&pp->mu);
-            if (pp->built > step + 1)
-                next = &pp->dv->sb[(step + 1) % NK_NBUF];
-            pthread_mutex_unlock(&pp->mu);
-        }
-        int rc = pp->raw ? nk_gpu_step_raw(pp->c, pp->dv, sb, next, &pp->first_invalid[step % NK_NBUF])
+        int rc = pp->raw ? nk_gpu_step_raw(pp->c, pp->dv, sb, pp, step, &pp->first_invalid[step % NK_NBUF])
                          : nk_gpu_step(pp->c, pp->dv, sb, &pp->first_invalid[step % NK_NBUF]);
         if (rc)
         {
@@ -2314,6 +2372,9 @@ static void *nk_device_pipeline(void *a)
     pthread_mutex_init(&pp->mu, NULL);
     pthread_cond_init(&pp->cv, NULL);
     pp->built = pp->completed = pp->written = 0;
+    pp->staged = 0;
+    pp->uploaded = 0; /* step 0 is copied by its own nkd_stage_raw */
+    pp->prefetch = !nk_env_on("NKB200_NO_PREFETCH");
     pp->total = -1;
     pp->abort_rc = 0;
     pthread_t gth, wth;
@@ -2343,6 +2404,7 @@ static void *nk_device_pipeline(void *a)
         pthread_mutex_unlock(&pp->mu);
         if (n == 0)
             break;
+        nk_try_upload(pp, step);
     }
     pthread_mutex_lock(&pp->mu);
     if (pp->total < 0)

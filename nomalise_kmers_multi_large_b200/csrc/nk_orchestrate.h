@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -88,6 +89,7 @@ class NkEngine
     int paired = 0;
     std::vector<unsigned> T;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    uint64_t upload_total = 0; /* bytes sent ahead by nkd_upload_raw (kept apart: another thread adds to it) */
     nkd_run_stats rs{};
     std::vector<float> spans; /* (start, end) ms of every scoring step on the device clock */
     bool staged = false, ran = false;
@@ -104,6 +106,7 @@ class NkEngine
     unsigned char *d_raw_next = nullptr; /* second text buffer: the next step's bytes arrive while this one runs */
     const uint8_t *uploaded = nullptr;   /* host buffer whose bytes d_raw_next holds (or is receiving) */
     size_t uploaded_bytes = 0;
+    std::mutex up_mu; /* nkd_upload_raw may come from another host thread than the one that runs the steps */
     unsigned *d_tile = nullptr, *d_nlpos = nullptr, *d_nops = nullptr, *d_opscan = nullptr, *d_tout = nullptr;
     unsigned *d_rflags = nullptr, *d_outlen = nullptr, *d_outoff = nullptr;
     unsigned long long *d_summary = nullptr;
@@ -715,10 +718,11 @@ class NkEngine
             return rc;
         if ((raw_bytes & 15u) || raw_bytes > raw_cap)
             return fail(NK_EINVAL, "nkd_upload_raw: bad size");
+        std::lock_guard<std::mutex> lock(up_mu);
         be.upload(d_raw_next, host_raw, raw_bytes);
         uploaded = host_raw;
         uploaded_bytes = raw_bytes;
-        h2d_bytes += raw_bytes;
+        upload_total += raw_bytes;
         return NK_OK;
     }
 
@@ -781,12 +785,16 @@ class NkEngine
         if (((prev_end + 15) & ~15ull) != raw_bytes)
             return fail(NK_EINVAL, "nkd_stage_raw: raw_bytes must end the last window (rounded up to 16)");
         /* windows go over as they are; the gaps keep whatever the host put there (neither '\n' nor NUL) */
-        const bool prefetched = uploaded == host_raw && uploaded_bytes == raw_bytes;
-        uploaded = nullptr;
-        if (prefetched)
-        { /* the bytes were sent ahead (nkd_upload_raw): take that buffer once its copy has landed */
-            std::swap(d_raw, d_raw_next);
-            be.upload_fence();
+        bool prefetched;
+        {
+            std::lock_guard<std::mutex> lock(up_mu);
+            prefetched = uploaded == host_raw && uploaded_bytes == raw_bytes;
+            uploaded = nullptr;
+            if (prefetched)
+            { /* the bytes were sent ahead (nkd_upload_raw): take that buffer once its copy has landed */
+                std::swap(d_raw, d_raw_next);
+                be.upload_fence();
+            }
         }
         for (int s = 0; s < n_segs && !prefetched; s++)
         {
