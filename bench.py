@@ -101,8 +101,24 @@ def generate(n_pairs, transcripts, tag):
     pf, pr = d / f"{stem}_1.fastq", d / f"{stem}_2.fastq"
     done = d / f"{stem}.done"
     if not done.exists():
-        subprocess.run([str(ROOT / "tools" / "nk_synth"), "-n", str(n_pairs), "-s", str(SEED), "-t", str(transcripts),
-                        "-L", str(READ_LEN), "-o", str(d / stem)], check=True, capture_output=True)
+        synth = str(ROOT / "tools" / "nk_synth")
+        if n_pairs <= 20_000_000:
+            subprocess.run([synth, "-n", str(n_pairs), "-s", str(SEED), "-t", str(transcripts), "-L", str(READ_LEN),
+                            "-o", str(d / stem)], check=True, capture_output=True)
+        else:
+            # large workloads: 10 M-pair blocks generated side by side (block b uses seed SEED + b over the same
+            # transcript count) and concatenated in block order; still a pure function of (n_pairs, transcripts)
+            blocks = [(b, min(10_000_000, n_pairs - b * 10_000_000)) for b in range((n_pairs + 9_999_999) // 10_000_000)]
+            procs = [subprocess.Popen([synth, "-n", str(n), "-s", str(SEED + b), "-t", str(transcripts), "-L", str(READ_LEN),
+                                       "-o", str(d / f"{stem}.b{b}")], stdout=subprocess.DEVNULL) for b, n in blocks]
+            assert all(p.wait() == 0 for p in procs), "nk_synth failed"
+            for mate, dst in (("1", pf), ("2", pr)):
+                with open(dst, "wb") as out:
+                    for b, _ in blocks:
+                        part = d / f"{stem}.b{b}_{mate}.fastq"
+                        with open(part, "rb") as src:
+                            shutil.copyfileobj(src, out, 1 << 24)
+                        part.unlink()
         done.write_text("ok")
     return pf, pr
 

@@ -98,6 +98,15 @@ int nkd_create(const nkd_config *cfg, nkd_engine **out);
 void nkd_destroy(nkd_engine *e);
 const char *nkd_last_error(const nkd_engine *e);
 
+/* Table budget (bytes of HBM for this engine's partition tables, 0 = unlimited; set before nkd_seed_finish).
+ * The reference's threads each own a table and share nothing (C:1841-1880, README:68), so partitions can be worked
+ * on in any order: with a budget, a table comes into being (copy_hash_table, C:908) when its partition is first
+ * staged, and the least recently used tables of partitions that are not part of the current step wait in host
+ * memory.  Results do not depend on the budget. */
+int nkd_set_table_budget(nkd_engine *e, uint64_t bytes);
+int nkd_residency_stats(nkd_engine *e, uint64_t *resident_parts, uint64_t *evictions, uint64_t *loads);
+int nkd_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
+
 /* sequence_to_hash_zero over a batch of seed reads (C:1501-1537, C:1352); reads[i].part is ignored.
  * n_ops = op_base + windows of the last read. */
 int nkd_seed_step(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,

@@ -109,7 +109,7 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
                   "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from",
                   "nkd_stage_raw", "nkd_fetch_raw", "nkd_fetch_raw_slot", "nkd_fetch_wait",
-                  "nkd_upload_raw"]
+                  "nkd_upload_raw", "nkd_set_table_budget", "nkd_residency_stats", "nkd_device_memory"]
 PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
@@ -152,6 +152,9 @@ def _declare_engine(lib):
     lib.nkd_fetch_raw_slot.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64), C.c_int]
     lib.nkd_fetch_wait.argtypes = [vp, C.c_int]
     lib.nkd_upload_raw.argtypes = [vp, u8p, sz]
+    lib.nkd_set_table_budget.argtypes = [vp, C.c_uint64]
+    lib.nkd_residency_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.nkd_device_memory.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -258,6 +261,14 @@ class Engine:
 
     def __exit__(self, *a):
         self.close()
+
+    def set_table_budget(self, nbytes):
+        self._check(self.lib.nkd_set_table_budget(self.h, nbytes))
+
+    def residency(self):
+        r, e, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.nkd_residency_stats(self.h, C.byref(r), C.byref(e), C.byref(l))
+        return {"resident": r.value, "evictions": e.value, "loads": l.value}
 
     def seed_step(self, buf: np.ndarray, descs: np.ndarray):
         inv = C.c_int64(-1)

@@ -1014,6 +1014,29 @@ struct CudaBackend
             k_decide<<<grid_for(n_records, 256), 256, 0, stream>>>(P, n_records, paired, coverage, accept), launches++;
     }
 
+    static bool device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes)
+    {
+        size_t f = 0, t = 0;
+        if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        /* what the stream-ordered pool holds but has handed back counts as free as well */
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+        {
+            unsigned long long reserved = 0, used = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+                f += (size_t)(reserved - used);
+        }
+        if (free_bytes)
+            *free_bytes = f;
+        if (total_bytes)
+            *total_bytes = t;
+        return true;
+    }
     /* the next step's text goes to the device on its own stream ... */
     void upload(void *d, const void *h, size_t n)
     {

@@ -102,6 +102,30 @@ int nkd_fetch(nkd_engine *h, uint8_t *accept, size_t n_records, int64_t *first_i
     h->e.be.enter();
     return nkd_done(h, h->e.fetch(accept, n_records, first_invalid));
 }
+int nkd_set_table_budget(nkd_engine *h, uint64_t bytes)
+{
+    if (h->e.seeded)
+        return h->e.fail(NK_EINVAL, "nkd_set_table_budget after nkd_seed_finish");
+    h->e.table_budget = bytes;
+    return NK_OK;
+}
+int nkd_residency_stats(nkd_engine *h, uint64_t *resident_parts, uint64_t *evictions, uint64_t *loads)
+{
+    uint64_t r = 0;
+    for (auto &p : h->e.parts)
+        r += p.tab != nullptr;
+    if (resident_parts)
+        *resident_parts = r;
+    if (evictions)
+        *evictions = h->e.evictions;
+    if (loads)
+        *loads = h->e.loads;
+    return NK_OK;
+}
+int nkd_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+    return NK_BACKEND::device_memory(device, free_bytes, total_bytes) ? NK_OK : NK_ENODEVICE;
+}
 int nkd_stage_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes, const nkd_raw_segment *segs, int n_segs, int paired,
                   int lines_per_record)
 {
@@ -172,6 +196,9 @@ int nkd_export(nkd_engine *h, int part, uint64_t *keys, int32_t *counts, uint64_
     h->e.be.enter();
     if (part < 0 || part >= (int)h->e.parts.size())
         return h->e.fail(NK_EINVAL, "no such partition");
+    int rc = h->e.make_resident(std::vector<int>{part});
+    if (rc)
+        return nkd_done(h, rc);
     return nkd_done(h, h->e.export_table(h->e.parts[part], keys, counts, capacity));
 }
 int nkd_dump_text(nkd_engine *h, int part, uint64_t first, uint64_t n, char *text, size_t text_cap, size_t *bytes)

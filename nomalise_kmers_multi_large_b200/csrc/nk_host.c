@@ -730,6 +730,7 @@ typedef struct
      * commit_* past every step it has finished, which is where the host parser takes over if it has to */
     uint64_t raw_total, raw_next, line_f, line_r;
     size_t raw_fp, raw_rp, commit_fp, commit_rp;
+    int active; /* part of the wave that is being processed (all partitions, unless the tables do not fit the GPU) */
 } nk_part;
 
 #define NK_NBUF 3 /* index step i+1, run step i on the GPU and write step i-1 at the same time */
@@ -744,6 +745,7 @@ typedef struct
     int *parts; /* indices into ctx->part */
     nk_stepbuf sb[NK_NBUF];
     int have_parsed_bufs, have_raw_bufs; /* staging is allocated when a pipeline of that kind first runs */
+    uint64_t table_budget;               /* bytes of HBM for this engine's tables, 0 = all of them fit */
     size_t max_step_bytes;
     double index_s, device_s, write_s;
     double t_stage, t_run, t_fetch; /* NKB200_TIMES=1: where the raw-text device steps spend their host time */
@@ -770,6 +772,7 @@ struct nk_ctx
     uint32_t raw_part_bytes; /* raw text per partition, mate and step */
     nk_lineidx lif, lir;     /* line indexes of the files being processed */
     uint64_t raw_steps, parsed_steps;
+    uint64_t waves; /* passes over disjoint sets of partitions in nk_process_* so far (1 per file when all tables fit) */
     /* seeding */
     uint8_t *seed_seq[2]; /* two staging buffers: one is parsed into while the GPUs seed from the other */
     nkd_read *seed_reads[2];
@@ -1481,6 +1484,51 @@ static int nk_concat_outputs(nk_ctx *c, const char *base)
     return rc;
 }
 
+/* Do the tables of all partitions fit their GPU, with room to grow?  If not, every engine of that GPU gets a budget
+ * and nk_process_* works on its partitions in waves (SURVEY 8.B row e; partitions are independent, C:1841-1880).
+ * NKB200_TABLE_BUDGET_MB forces a budget per engine (tests). */
+static int nk_set_table_budgets(nk_ctx *c)
+{
+    const char *forced = getenv("NKB200_TABLE_BUDGET_MB");
+    for (int d = 0; d < c->n_dev; d++)
+    {
+        nk_dev *dv = &c->dev[d];
+        if (dv->lead != d)
+            continue;
+        nkd_part_stats st;
+        nkd_seed_stats(dv->eng, &st);
+        uint64_t table = st.capacity * 16, free_b = 0, total_b = 0, parts_on_gpu = 0, engines = 0;
+        for (int o = 0; o < c->n_dev; o++)
+            if (c->dev[o].lead == d)
+            {
+                parts_on_gpu += (uint64_t)c->dev[o].n_parts;
+                engines++;
+            }
+        uint64_t budget = 0;
+        if (forced && atoll(forced) > 0)
+            budget = (uint64_t)atoll(forced) << 20;
+        else if (nkd_device_memory(dv->ordinal, &free_b, &total_b) == NK_OK)
+        {
+            /* resident for good needs every table plus room for each to grow once (x1.5) and a re-hash in flight */
+            uint64_t want = parts_on_gpu * table * 3 / 2 + engines * table * 3 / 2;
+            if (want > free_b - free_b / 10)
+                budget = (free_b - free_b / 10) / engines;
+        }
+        for (int o = 0; o < c->n_dev; o++)
+            if (c->dev[o].lead == d)
+            {
+                c->dev[o].table_budget = budget;
+                int rc = nkd_set_table_budget(c->dev[o].eng, budget);
+                if (rc)
+                    return nk_fail(c, rc, "%s", nkd_last_error(c->dev[o].eng));
+            }
+        if (budget && c->cfg.verbose)
+            printf("B200: GPU %d holds %llu partitions of %.2f GB tables in %.1f GB: working in waves, %.1f GB per engine\n", dv->ordinal,
+                   (unsigned long long)parts_on_gpu, (double)table / 1e9, (double)free_b / 1e9, (double)budget / 1e9);
+    }
+    return NK_OK;
+}
+
 static void nk_seed_finish_task(int d, void *a)
 {
     nk_ctx *c = a;
@@ -1506,6 +1554,9 @@ int nk_seed_finish(nk_ctx *c)
         if (rc)
             return rc;
     }
+    int brc = nk_set_table_budgets(c);
+    if (brc)
+        return brc;
     nk_parallel_for(c->n_dev, c->n_dev, nk_seed_adopt_task, c); /* while the lead engines still hold the seed table */
     for (int d = 0; d < c->n_dev; d++)
         if (c->dev[d].rc)
@@ -1547,7 +1598,7 @@ static void nk_index_task(int li, void *a)
     ps->ops = 0;
     ps->seq_hi = ps->seq_lo;
     size_t pos = ps->seq_lo;
-    while (!cur->done && cur->fp < cur->fe && (!paired || cur->rp < cur->re))
+    while (p->active && !cur->done && cur->fp < cur->fe && (!paired || cur->rp < cur->re))
     {
         if (ps->n_records >= c->step_pairs || pos + 2 * NK_MAX_LINE > ps->seq_end || ps->ops + 2 * NK_MAX_LINE > c->step_ops)
             break;
@@ -1959,7 +2010,7 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
         nk_pstep *ps = &sb->ps[li];
         ps->raw_n = 0;
         ps->fatal_record = -1;
-        uint64_t left = p->raw_total - p->raw_next;
+        uint64_t left = p->active ? p->raw_total - p->raw_next : 0;
         if (!left)
             continue;
         uint64_t n = left < c->step_pairs ? left : c->step_pairs;
@@ -2628,26 +2679,68 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     }
     c->tot.index_seconds += nk_now() - t0;
     nk_trace(-1, -1, "plan", t0, nk_now());
-    if (!rc && raw_work)
-        rc = nk_run_pipelines(c, 1);
-    nk_trace(-1, -1, "pipelines", t0, nk_now());
-    /* whatever the raw-text pipeline did not take -- text the device declined (NUL bytes, lines of 1024+ chars),
-     * a last record cut short by the end of the file -- goes through the byte-exact host parser from where each
-     * partition stands */
-    int parsed_work = 0;
-    for (int i = 0; i < c->n_local && !rc; i++)
+    /* Waves: an engine whose tables do not fit its share of the GPU works on `per_wave` of its partitions at a time,
+     * to the end of their byte ranges; the tables of the others wait in host memory (the engine parks and fetches
+     * them as the steps name other partitions).  One wave when everything fits. */
+    int n_waves = 1;
+    int per_wave[256];
+    for (int d = 0; d < c->n_dev && d < 256; d++)
     {
-        nk_part *p = &c->part[i];
-        p->cur.fp = p->commit_fp;
-        p->cur.rp = p->commit_rp;
-        nk_nliter_seek(&p->cur.itf, c->ff.data, p->cur.fp, c->ff.size);
-        if (paired)
-            nk_nliter_seek(&p->cur.itr, c->rf.data, p->cur.rp, c->rf.size);
-        if (p->cur.fp < p->cur.fe && (!paired || p->cur.rp < p->cur.re))
-            parsed_work = 1;
+        nk_dev *dv = &c->dev[d];
+        per_wave[d] = dv->n_parts;
+        if (!dv->table_budget)
+            continue;
+        uint64_t table = 0;
+        for (int i = 0; i < dv->n_parts; i++)
+        {
+            nkd_part_stats st;
+            if (nkd_part_stats_get(dv->eng, i, &st) == NK_OK && st.capacity * 16 > table)
+                table = st.capacity * 16;
+        }
+        /* a wave's tables, each with room to grow once, plus one re-hash in flight */
+        uint64_t fit = table ? dv->table_budget / table : (uint64_t)dv->n_parts;
+        int r = fit > 3 ? (int)((fit - 2) * 2 / 3) : 1;
+        if (r < 1)
+            r = 1;
+        int waves = (dv->n_parts + r - 1) / r;
+        per_wave[d] = (dv->n_parts + waves - 1) / waves; /* even waves */
+        if (waves > n_waves)
+            n_waves = waves;
     }
-    if (!rc && parsed_work)
-        rc = nk_run_pipelines(c, 0);
+    for (int w = 0; w < n_waves && !rc; w++)
+    {
+        raw_work = 0;
+        for (int i = 0; i < c->n_local; i++)
+        {
+            nk_part *p = &c->part[i];
+            int d = p->dev < 256 ? p->dev : 255;
+            p->active = p->lidx / per_wave[d] == w;
+            raw_work |= p->active && p->raw_total > p->raw_next;
+        }
+        c->waves++;
+        if (raw_work)
+            rc = nk_run_pipelines(c, 1);
+        /* whatever the raw-text pipeline did not take -- text the device declined (NUL bytes, lines of 1024+ chars),
+         * a last record cut short by the end of the file -- goes through the byte-exact host parser from where each
+         * partition stands */
+        int parsed_work = 0;
+        for (int i = 0; i < c->n_local && !rc; i++)
+        {
+            nk_part *p = &c->part[i];
+            if (!p->active)
+                continue;
+            p->cur.fp = p->commit_fp;
+            p->cur.rp = p->commit_rp;
+            nk_nliter_seek(&p->cur.itf, c->ff.data, p->cur.fp, c->ff.size);
+            if (paired)
+                nk_nliter_seek(&p->cur.itr, c->rf.data, p->cur.rp, c->rf.size);
+            if (p->cur.fp < p->cur.fe && (!paired || p->cur.rp < p->cur.re))
+                parsed_work = 1;
+        }
+        if (!rc && parsed_work)
+            rc = nk_run_pipelines(c, 0);
+    }
+    nk_trace(-1, -1, "pipelines", t0, nk_now());
     nk_lineidx_free(&c->lif);
     nk_lineidx_free(&c->lir);
     /* reporting totals are sums of the partitions' cumulative counters, C:1897-1909 */
@@ -3324,6 +3417,16 @@ int nk_main(int argc, char **argv)
                c->tot.seed_seconds, c->tot.process_seconds, c->tot.index_seconds, c->tot.device_seconds, c->tot.write_seconds, gpus, c->threads);
         printf("B200: %llu device steps on raw record text, %llu on host-parsed records\n", (unsigned long long)c->raw_steps,
                (unsigned long long)c->parsed_steps);
+        uint64_t ev = 0, ld = 0;
+        for (int d = 0; d < c->n_dev; d++)
+        {
+            uint64_t e1 = 0, l1 = 0;
+            nkd_residency_stats(c->dev[d].eng, NULL, &e1, &l1);
+            ev += e1;
+            ld += l1;
+        }
+        printf("B200: %llu wave(s) of partitions, %llu tables parked in host memory, %llu brought in\n", (unsigned long long)c->waves,
+               (unsigned long long)ev, (unsigned long long)ld);
     }
     nk_destroy(c);
     return 0;

@@ -29,6 +29,11 @@ struct NkTable
     NkSlot *tab = nullptr;
     uint64_t cap = 0, used = 0, thr = 0, magic = 0;
     nkd_part_stats st{};
+    /* table residency (engines with a table budget): a partition's table is in HBM (tab), parked in host memory
+     * (host), or still identical to the seed table (fresh) */
+    void *host = nullptr;
+    bool fresh = false;
+    uint64_t last_use = 0;
 };
 
 /* smallest used for which the reference's `used >= capacity * 0.8` (double) holds, C:933 */
@@ -62,6 +67,10 @@ class NkEngine
     NkTable seed;
     std::vector<NkTable> parts;
     bool seeded = false;
+    /* Partitions are independent (C:1841-1880): when their tables do not fit the GPU together, the host works on them in
+     * waves and the tables of the others wait in host memory.  0 = no budget, every table stays in HBM. */
+    uint64_t table_budget = 0, use_clock = 0, evictions = 0, loads = 0;
+    unsigned fresh_left = 0;
 
     /* step buffers */
     const unsigned char *seq_view = nullptr; /* where the kernels read the step's sequence bytes from */
@@ -188,7 +197,11 @@ class NkEngine
         be.sync();
         be.release(seed.tab);
         for (auto &p : parts)
+        {
             be.release(p.tab);
+            free(p.host);
+            p.host = nullptr;
+        }
         be.release(d_seq);
         be.release(d_reads);
         be.release(d_high);
@@ -244,6 +257,107 @@ class NkEngine
         t.magic = nk_magic(cap);
         t.st.capacity = cap;
         return true;
+    }
+
+    /* ------------------------------------------------------------ table residency */
+
+    int evict_part(int p)
+    {
+        NkTable &t = parts[p];
+        if (!t.tab)
+            return NK_OK;
+        size_t bytes = (size_t)t.cap * sizeof(NkSlot);
+        t.host = malloc(bytes);
+        if (!t.host)
+            return fail(NK_ENOMEM, "cannot park a partition table in host memory");
+        be.d2h(t.host, t.tab, bytes);
+        be.sync();
+        be.release(t.tab);
+        t.tab = nullptr;
+        d2h_bytes += bytes;
+        evictions++;
+        if (debug)
+            fprintf(stderr, "[nkd] partition %d parked in host memory (%zu MB)\n", p, bytes >> 20);
+        return NK_OK;
+    }
+
+    int load_part(int p)
+    {
+        NkTable &t = parts[p];
+        if (t.tab)
+            return NK_OK;
+        size_t bytes = (size_t)t.cap * sizeof(NkSlot);
+        t.tab = (NkSlot *)be.alloc(bytes);
+        if (!t.tab)
+            return fail(NK_ENOMEM, "Memory allocation failed (partition table)");
+        if (t.host)
+        {
+            be.h2d(t.tab, t.host, bytes);
+            be.sync();
+            free(t.host);
+            t.host = nullptr;
+            h2d_bytes += bytes;
+        }
+        else if (t.fresh)
+        { /* copy_hash_table, C:908-927: first use of this partition */
+            be.d2d(t.tab, seed.tab, bytes);
+            t.fresh = false;
+            if (--fresh_left == 0)
+            {
+                be.sync();
+                be.release(seed.tab);
+                seed.tab = nullptr;
+            }
+        }
+        else
+            return fail(NK_EINTERNAL, "partition table lost");
+        loads++;
+        return NK_OK;
+    }
+
+    /* the partitions in `need` get their tables into HBM; least recently used others make room */
+    int make_resident(const std::vector<int> &need)
+    {
+        if (!table_budget)
+            return NK_OK;
+        std::vector<char> wanted(parts.size(), 0);
+        uint64_t resident = seed.tab ? seed.cap * sizeof(NkSlot) : 0, incoming = 0, largest = 0;
+        for (int p : need)
+            wanted[p] = 1;
+        for (size_t p = 0; p < parts.size(); p++)
+        {
+            uint64_t b = parts[p].cap * sizeof(NkSlot);
+            if (parts[p].tab)
+                resident += b;
+            else if (wanted[p])
+                incoming += b;
+            if (wanted[p] && b > largest)
+                largest = b;
+        }
+        /* room for one table growing while the others stay (old and new table coexist during a re-hash, C:1070) */
+        uint64_t headroom = largest + largest / 2;
+        while (resident + incoming + headroom > table_budget)
+        {
+            int victim = -1;
+            for (size_t p = 0; p < parts.size(); p++)
+                if (parts[p].tab && !wanted[p] && (victim < 0 || parts[p].last_use < parts[victim].last_use))
+                    victim = (int)p;
+            if (victim < 0)
+                break; /* everything resident is needed: the allocation below decides */
+            resident -= parts[victim].cap * sizeof(NkSlot);
+            int rc = evict_part(victim);
+            if (rc)
+                return rc;
+        }
+        use_clock++;
+        for (int p : need)
+        {
+            int rc = load_part(p);
+            if (rc)
+                return rc;
+            parts[p].last_use = use_clock;
+        }
+        return NK_OK;
     }
 
     /* expand_local_hash_table, C:1055-1108 */
@@ -331,7 +445,8 @@ class NkEngine
             d.gbase = g;
             d.lo = lo[p];
             d.hi = hi[p];
-            g += tabs[p]->cap;
+            if (tabs[p]->tab) /* tables parked in host memory take no part in this step */
+                g += tabs[p]->cap;
         }
         be.h2d(d_parts, h_parts.data(), tabs.size() * sizeof(NkPart));
     }
@@ -355,7 +470,7 @@ class NkEngine
             hi[p] = T[p];
         uint64_t gsum = 0;
         for (auto *t : tabs)
-            gsum += t->cap;
+            gsum += t->tab ? t->cap : 0;
         for (;;)
         {
             bool live = false;
@@ -383,7 +498,7 @@ class NkEngine
                     }
                 gsum = 0;
                 for (auto *t : tabs)
-                    gsum += t->cap;
+                    gsum += t->tab ? t->cap : 0;
             }
             if (gsum >= (1ull << 34))
                 return fail(NK_ENOMEM, "tables of one device exceed 2^34 slots");
@@ -661,14 +776,23 @@ class NkEngine
             at += g.n_reads;
         }
         uint64_t tot = 0;
+        std::vector<int> need;
         for (int p = 0; p < n_tabs; p++)
         {
             if (T[p] >= (1u << NK_T_BITS))
                 return fail(NK_EINVAL, "a partition has 2^28 or more operations in one step");
             tot += T[p];
+            if (T[p])
+                need.push_back(p);
         }
         if (tot > cfg.max_step_ops)
             return fail(NK_EINVAL, "step has more operations than max_step_ops");
+        if (seeded && !ignore_part)
+        {
+            int rc = make_resident(need);
+            if (rc)
+                return rc;
+        }
         n_reads = nr;
         paired = is_paired;
         n_records = nr / stride;
@@ -784,6 +908,14 @@ class NkEngine
             return fail(NK_EINVAL, "nkd_stage_raw: step exceeds the read limit given to nkd_create");
         if (((prev_end + 15) & ~15ull) != raw_bytes)
             return fail(NK_EINVAL, "nkd_stage_raw: raw_bytes must end the last window (rounded up to 16)");
+        {
+            std::vector<int> need;
+            for (int s = 0; s < n_segs; s++)
+                need.push_back((int)segs[s].part);
+            int rc2 = make_resident(need);
+            if (rc2)
+                return rc2;
+        }
         /* windows go over as they are; the gaps keep whatever the host put there (neither '\n' nor NUL) */
         bool prefetched;
         {
@@ -975,6 +1107,15 @@ class NkEngine
         be.release(seed.tab);
         seed = src.seed;
         seed.tab = nullptr;
+        if (table_budget)
+        { /* tables come into being when their partition is first used: this engine keeps its own seed table till then */
+            seed.tab = (NkSlot *)be.alloc(seed.cap * sizeof(NkSlot));
+            if (!seed.tab)
+                return fail(NK_ENOMEM, "Memory allocation failed (seed table copy)");
+            be.d2d(seed.tab, src.seed.tab, seed.cap * sizeof(NkSlot));
+            be.sync();
+            return seed_finish_lazy();
+        }
         parts.resize(cfg.n_parts);
         for (int p = 0; p < cfg.n_parts; p++)
         {
@@ -993,10 +1134,31 @@ class NkEngine
         return NK_OK;
     }
 
+    int seed_finish_lazy()
+    {
+        parts.assign(cfg.n_parts, NkTable{});
+        for (int p = 0; p < cfg.n_parts; p++)
+        {
+            NkTable &t = parts[p];
+            t = seed;
+            t.tab = nullptr;
+            t.st = nkd_part_stats{};
+            t.st.capacity = seed.cap;
+            t.st.used = seed.used;
+            t.fresh = true;
+        }
+        fresh_left = (unsigned)cfg.n_parts;
+        be.sync();
+        seeded = true;
+        return NK_OK;
+    }
+
     int seed_finish()
     {
         if (seeded)
             return fail(NK_EINVAL, "nkd_seed_finish called twice");
+        if (table_budget)
+            return seed_finish_lazy();
         parts.resize(cfg.n_parts);
         for (int p = 0; p < cfg.n_parts; p++)
         {
@@ -1132,6 +1294,12 @@ class NkEngine
         const NkTable *t = part == NKD_PART_SEED ? &seed : (part >= 0 && part < (int)parts.size() ? &parts[part] : nullptr);
         if (!t)
             return fail(NK_EINVAL, "no such partition");
+        if (part >= 0 && !t->tab)
+        {
+            int rc = make_resident(std::vector<int>{part});
+            if (rc)
+                return rc;
+        }
         if (!t->tab)
             return fail(NK_EINVAL, "table not resident");
         src.tab = t->tab;

@@ -196,6 +196,16 @@ struct EmuBackend
     }
     /* raw record text: the same per-record / per-entry functions as the kernels, entries visited in shuffled order */
     bool prepare_scan(size_t, std::string &) { return true; }
+    static bool device_memory(int, uint64_t *free_bytes, uint64_t *total_bytes)
+    { /* NK_EMU_HBM_MB lets the CPU tests drive the host pipeline's wave scheduling */
+        const char *s = getenv("NK_EMU_HBM_MB");
+        uint64_t b = (s && atoll(s) > 0 ? (uint64_t)atoll(s) : 1024ull * 180) << 20;
+        if (free_bytes)
+            *free_bytes = b;
+        if (total_bytes)
+            *total_bytes = b;
+        return true;
+    }
     void upload(void *d, const void *h, size_t n) { memcpy(d, h, n); }
     void upload_fence() {}
     void copy_fence() {}

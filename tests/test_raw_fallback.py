@@ -88,3 +88,35 @@ def test_host_parse_switch_emu(inputs):
 @pytest.mark.parametrize("name,mixed", CASES)
 def test_mix_of_raw_and_parsed_steps_gpu(inputs, name, mixed):
     run(capi.CLI_PATH, {"NKB200_STEP_PAIRS": "128"}, inputs, name, mixed, True)
+
+
+WAVES_RE = re.compile(r"B200: (\d+) wave\(s\) of partitions, (\d+) tables parked in host memory, (\d+) brought in")
+
+
+def check_waves(binary, inputs, env, tag):
+    """Tables that do not fit the GPU together: partitions are worked on in waves and the tables of the others wait in
+    host memory (SURVEY 8.B row e, H6).  A small artificial budget forces that here; two input file pairs make every
+    table go out and come back, and -P dumps them all at the end.  Nothing may change in any file."""
+    tmp, files = inputs
+    f, r = files["regular"]
+    f2, r2 = files["reverse_has_fewer_records"]
+    args = ["-f", f, f2, "-r", r, r2, "-k", 21, "-d", 16, "-m", 1, "-p", 8, "-c", "-P"]
+    want = cc.run_cli(ol.ORACLE_CLI, args, tmp / tag / "oracle")
+    got = cc.run_cli(binary, args + ["-e"], tmp / tag / "got", env=dict(env, NKB200_TABLE_BUDGET_MB="450"))
+    cc.assert_same(got, want, "waves")
+    m = WAVES_RE.search(got["stdout"])
+    assert m, got["stdout"][-600:]
+    waves, parked, loaded = (int(x) for x in m.groups())
+    assert waves >= 4 and parked > 0 and loaded >= 8 + parked, (waves, parked, loaded)   # 2 files x >= 2 waves
+    free = cc.run_cli(binary, args + ["-e"], tmp / tag / "free", env=env)
+    assert WAVES_RE.search(free["stdout"]).groups() == ("2", "0", "0")   # everything fits: one wave per file, as before
+    cc.assert_same(free, want, "no budget")
+
+
+def test_waves_when_tables_do_not_fit_emu(inputs):
+    check_waves(EMU_CLI, inputs, {"NKB200_STEP_PAIRS": "256"}, "waves_emu")
+
+
+@pytest.mark.gpu
+def test_waves_when_tables_do_not_fit_gpu(inputs):
+    check_waves(capi.CLI_PATH, inputs, {"NKB200_STEP_PAIRS": "256"}, "waves_gpu")
