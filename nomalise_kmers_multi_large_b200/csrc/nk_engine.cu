@@ -734,9 +734,6 @@ struct CudaBackend
             unsigned long long keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        /* the table is probed with random 16-byte gathers: fetch single 32-byte sectors from HBM */
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-        cudaGetLastError();
         return NK_OK;
     }
     void shutdown()
@@ -841,6 +838,9 @@ struct CudaBackend
         return e && atoi(e) >= 32 ? (unsigned)atoi(e) : dflt;
     }
     unsigned min_list_entries() const { return (unsigned)sms * 8u * 8u * 2u * 32u * 3u; }
+    /* entries the classification kernels may leave as holes: every warp of k_classify and k_classify_claimed can
+     * abandon the tail of one NK_SLOW_CHUNK reservation */
+    unsigned slow_hole_margin() const { return 2u * (unsigned)sms * 8u * 8u * NK_SLOW_CHUNK; }
     void chunk_sizes(unsigned *c, unsigned pend_cap, unsigned open_cap, unsigned claim_cap, unsigned slow_cap,
                      unsigned spec_cap)
     {

@@ -147,7 +147,10 @@ int nkd_fetch_raw_slot(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_ca
 }
 int nkd_fetch_raw(nkd_engine *h, int emit_mode, uint8_t *out, size_t out_cap, nkd_raw_result *results, int64_t *first_invalid)
 {
-    return nkd_fetch_raw_slot(h, emit_mode, out, out_cap, results, first_invalid, 0);
+    /* not through nkd_fetch_raw_slot: an exported name may resolve into another library that exports it too (the tests
+     * load the CUDA library and the CPU emulation of the engine side by side) */
+    h->e.be.enter();
+    return nkd_done(h, h->e.fetch_raw(emit_mode, out, out_cap, results, first_invalid, 0));
 }
 int nkd_fetch_wait(nkd_engine *h, int slot)
 {

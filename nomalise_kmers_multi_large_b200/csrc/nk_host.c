@@ -667,7 +667,7 @@ typedef struct
     uint32_t nbytes;   /* bytes consumed by its lines */
     uint16_t seq_rel;  /* offset of the sequence line */
     uint16_t seq_len;
-    uint32_t plain;    /* all lines are "text\n": the record can be copied verbatim */
+    uint32_t plain;    /* bit 0: all lines are "text\n", the record can be copied verbatim; bits 8..: lines that were read */
 } nk_span;
 
 typedef struct
@@ -932,8 +932,11 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
      * dealt to (by default) up to four engines, each with its own stream, scratch lists and pipeline thread, so that
      * one engine's list passes (classify, sort, rank, commit) and host round trips overlap the other's table
      * probing on the same GPU. */
-    int epg = getenv("NKB200_ENGINES_PER_GPU") ? atoi(getenv("NKB200_ENGINES_PER_GPU")) : 4;
-    if (epg < 1 || epg > 8)
+    /* default: up to four engines, each with at least two partitions (measured at 8, 4, 2 and 1 partitions per GPU,
+     * profiles/r02_ab_engines.txt: an engine with a single partition needs steps so large that the ordered slow path
+     * grows faster than the overlap between engines pays) */
+    int epg = getenv("NKB200_ENGINES_PER_GPU") ? atoi(getenv("NKB200_ENGINES_PER_GPU")) : 0;
+    if (epg < 0 || epg > 8)
         epg = 1;
     int n_gpus = cfg->n_devices > 0 ? cfg->n_devices : 1;
     if (n_gpus > c->n_local)
@@ -942,7 +945,8 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
     for (int g = 0; g < n_gpus; g++)
     {
         int cnt = (c->n_local - g + n_gpus - 1) / n_gpus; /* partitions i with i mod n_gpus == g */
-        n_eng[g] = cnt < epg ? cnt : epg;
+        int want = epg ? epg : (cnt / 2 > 4 ? 4 : (cnt / 2 < 1 ? 1 : cnt / 2));
+        n_eng[g] = cnt < want ? cnt : want;
         first_eng[g + 1] = first_eng[g] + n_eng[g];
     }
     c->n_dev = first_eng[n_gpus];
@@ -1604,7 +1608,7 @@ static void nk_index_task(int li, void *a)
             break;
         nk_span sf = {cur->fp, 0, 0, 0, 1}, sr = {cur->rp, 0, 0, 0, 1};
         size_t fp = cur->fp, rp = cur->rp;
-        int more = 1, complete = 1, plain_f = 1, plain_r = 1;
+        int more = 1, complete = 1, plain_f = 1, plain_r = 1, lines_read = per;
         /* fast path: every line of the record ends in '\n' within 1023 chars and no NUL is near, so
          * read_line (C:394-409) consumes exactly "text\n" each time; positions come from the SIMD iterator */
         int fast = 1;
@@ -1675,9 +1679,15 @@ static void nk_index_task(int li, void *a)
                     sr.seq_len = (uint16_t)lr;
                 }
                 if (!mf || !mr)
-                {
+                { /* read_line gave up (a NUL byte, the end of the file): with both sequence lines in, the reference
+                   * still scores and counts the record before it stops (C:1629, C:1733) */
                     more = 0;
-                    complete = (i == per - 1);
+                    complete = (i >= 1);
+                    if (i < per - 1)
+                    { /* printed line by line, as far as it was read (both mates stop at the same line) */
+                        plain_f = plain_r = 0;
+                        lines_read = i + 1;
+                    }
                     break;
                 }
             }
@@ -1686,14 +1696,14 @@ static void nk_index_task(int li, void *a)
                 nk_nliter_seek(&cur->itr, rf->data, rp, rf->size);
         }
         if (!complete)
-        { /* a record whose lines cannot all be read is not scored (reference: undefined, C:1616-1629) */
+        { /* cut before its sequence lines: not scored (the reference scores stale stack bytes here, C:1616-1629) */
             cur->done = 1;
             break;
         }
         sf.nbytes = (uint32_t)(fp - cur->fp);
         sr.nbytes = (uint32_t)(rp - cur->rp);
-        sf.plain = (uint32_t)plain_f;
-        sr.plain = (uint32_t)plain_r;
+        sf.plain = (uint32_t)plain_f | ((uint32_t)lines_read << 8);
+        sr.plain = (uint32_t)plain_r | ((uint32_t)lines_read << 8);
         cur->fp = fp;
         cur->rp = rp;
         if (!more)
@@ -1727,7 +1737,7 @@ static void nk_index_task(int li, void *a)
 
 static void nk_emit_lines(FILE *o, const nk_buf *f, const nk_span *s, int per, char *tmp)
 {
-    if (s->plain)
+    if (s->plain & 1u)
     { /* verbatim bytes, N -> A inside the sequence line (C:1426-1427 mutates the buffer that is printed) */
         const char *src = f->data + s->start;
         const char *seq = src + s->seq_rel;
@@ -1744,6 +1754,8 @@ static void nk_emit_lines(FILE *o, const nk_buf *f, const nk_span *s, int per, c
         return;
     }
     size_t pos = s->start; /* cut, unterminated or NUL-holding lines: print each as the reference's "%s\n" */
+    if ((int)(s->plain >> 8) < per)
+        per = (int)(s->plain >> 8); /* the record reader stopped early: only the lines it read are printed */
     for (int i = 0; i < per; i++)
     {
         uint32_t len;
@@ -2004,6 +2016,19 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
     size_t at = 0, total = 0;
     sb->n_rsegs = 0;
     sb->n_copies = 0;
+    /* the step's room (records, bytes, operations) is shared by the partitions that still have records: when only a
+     * wave of them is being worked on, or most have run dry, each takes a larger share and the launches stay large */
+    int busy = 0;
+    for (int li = 0; li < dv->n_parts; li++)
+    {
+        nk_part *p = &c->part[dv->parts[li]];
+        busy += p->active && p->raw_total > p->raw_next;
+    }
+    uint64_t share = busy ? (uint64_t)dv->n_parts / (uint64_t)busy : 1;
+    if (share * c->step_pairs > 262144)
+        share = 262144 / c->step_pairs ? 262144 / c->step_pairs : 1; /* operations per partition and step stay below 2^28 */
+    const uint64_t quota = (uint64_t)c->step_pairs * share, byte_room = (uint64_t)c->raw_part_bytes * share,
+                   op_room = (uint64_t)c->step_ops * share;
     for (int li = 0; li < dv->n_parts; li++)
     {
         nk_part *p = &c->part[dv->parts[li]];
@@ -2013,7 +2038,7 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
         uint64_t left = p->active ? p->raw_total - p->raw_next : 0;
         if (!left)
             continue;
-        uint64_t n = left < c->step_pairs ? left : c->step_pairs;
+        uint64_t n = left < quota ? left : quota;
         size_t f1 = 0, r1 = 0;
         for (;;)
         {
@@ -2026,13 +2051,13 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
             }
             size_t wf = f1 - p->raw_fp, wr = paired ? r1 - p->raw_rp : 0, big = wf > wr ? wf : wr;
             size_t ops_bound = c->cfg.in_fastq ? (wf + wr) / 2 : wf + wr;
-            if ((big <= c->raw_part_bytes && ops_bound <= c->step_ops) || n == 1)
+            if ((big <= byte_room && ops_bound <= op_room) || n == 1)
             {
-                if (big > c->raw_part_bytes)
+                if (big > byte_room)
                     n = 0; /* one record larger than the window: not regular text */
                 break;
             }
-            double shrink = 0.95 * (double)c->raw_part_bytes / (double)big, s2 = 0.95 * (double)c->step_ops / (double)ops_bound;
+            double shrink = 0.95 * (double)byte_room / (double)big, s2 = 0.95 * (double)op_room / (double)ops_bound;
             if (s2 < shrink)
                 shrink = s2;
             uint64_t m = (uint64_t)((double)n * shrink);

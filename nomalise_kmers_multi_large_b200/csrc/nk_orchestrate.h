@@ -159,7 +159,7 @@ class NkEngine
         claim_cap = open_cap;
         spec_cap = open_cap;
         /* every listed event can turn into one slow record; chunked reservation wastes at most a chunk per warp */
-        slow_cap = (unsigned)std::min<double>(4e9, 1.25 * ((double)pend_cap + (double)spec_cap) + (1 << 20));
+        slow_cap = (unsigned)std::min<double>(4e9, 1.25 * ((double)pend_cap + (double)spec_cap) + (1 << 20) + be.slow_hole_margin());
         bool ok = true;
         ok &= dalloc(d_seq, c.max_step_bytes + 64);
         ok &= dalloc(d_reads, c.max_step_reads + 1);

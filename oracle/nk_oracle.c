@@ -19,8 +19,12 @@
  * Deliberate, documented deviations (reference behaviour is undefined there):
  *   D1 bytes past EOF read as '\0' (reference relies on the zero page tail and
  *      faults when size is a multiple of the page size, C:397)
- *   D2 a record whose lines cannot all be read is not scored, the partition
- *      stops (reference scores stale stack bytes, C:1616-1629)
+ *   D2 a record that read_line cuts short (a NUL byte, or the end of the file inside
+ *      the record) is scored, counted and ends the partition as in the reference
+ *      (C:1616-1631, C:1733) when both sequence lines were read; if it is accepted,
+ *      only the lines that were read are printed (the reference prints whatever its
+ *      stack holds for the others).  Cut before the sequence lines, it is not
+ *      scored (reference: stale stack bytes are scored)
  *   D3 a final record dropped by the length gate ends the partition (reference
  *      dereferences NULL, C:1622-1631)
  *   D4 pure single-end with -p > 1 runs (reference tests an uninitialised FILE*,
@@ -619,7 +623,12 @@ static void run_range(const nko_cfg *c, nko_part *p, const nko_file *ff, size_t 
             if (!mf || !mr)
             {
                 more = 0;
-                complete = (i == per - 1);
+                complete = (i >= 1); /* both sequence lines are in: the reference scores the record, C:1629 */
+                for (int j = i + 1; j < per; j++)
+                {
+                    fl[j][0] = rl[j][0] = '\0';
+                    fn[j] = rn[j] = -1; /* not read: not printed (D2) */
+                }
                 break;
             }
         }
@@ -662,7 +671,7 @@ static void run_range(const nko_cfg *c, nko_part *p, const nko_file *ff, size_t 
             }
             else
             {
-                for (int i = 0; i < per; i++)
+                for (int i = 0; i < per && fn[i] >= 0; i++)
                 {
                     fprintf(p->out_f, "%s\n", fl[i]);
                     if (paired)

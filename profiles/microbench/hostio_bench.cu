@@ -5,6 +5,7 @@
  *   nlcount     AVX2 newline count over the mmap, T threads
  *   write       write() of T private files on tmpfs, 4 MB per call, from a pinned buffer
  *   pwrite1     pwrite() by T threads into ONE tmpfs file at disjoint offsets
+ *   mmapw1      T threads memcpy into a MAP_SHARED mapping of ONE fresh tmpfs file (ftruncate'd) at disjoint offsets
  *   register    cudaHostRegister(ReadOnly) of the tmpfs mmap (would allow DMA straight from the page cache)
  *   h2d / d2h   cudaMemcpyAsync pinned <-> device
  *   zc_read     kernel reading mapped pinned memory (16-byte loads); zc_write: kernel storing to it
@@ -92,6 +93,9 @@ static void *worker(void *a)
                 perror("pwrite");
         }
         break;
+    case 4:
+        memcpy((char *)j->src + lo, j->dst + lo, n); /* src = the writable mapping of the output file here */
+        break;
     }
     return NULL;
 }
@@ -154,9 +158,9 @@ int main(int argc, char **argv)
     printf("cudaHostAlloc %zu MB: %.3f s\n", bytes >> 20, now() - t0);
     memset(pinned, 1, bytes);
     int Ts[] = {1, 2, 4, 8, 16, 32, 64};
-    for (int mode = 0; mode < 4; mode++)
+    for (int mode = 0; mode < 5; mode++)
     {
-        const char *nm[] = {"memcpy mmap->pinned", "nlcount mmap", "write T files", "pwrite one file"};
+        const char *nm[] = {"memcpy mmap->pinned", "nlcount mmap", "write T files", "pwrite one file", "memcpy into mmap of 1 file"};
         int ofd = -1;
         char oname[256];
         snprintf(oname, sizeof oname, "%s/hostio_one.bin", dir);
@@ -168,6 +172,20 @@ int main(int argc, char **argv)
             if (mode == 3)
                 ofd = open(oname, O_WRONLY | O_CREAT | O_TRUNC, 0644);
             double best = 1e9;
+            if (mode == 4)
+            { /* what a writer would do per step: grow the file, map the new range, fill it on T threads, unmap */
+                ofd = open(oname, O_RDWR | O_CREAT | O_TRUNC, 0644);
+                double t0 = now();
+                if (ftruncate(ofd, (off_t)bytes))
+                    perror("ftruncate");
+                char *m = (char *)mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, ofd, 0);
+                run(4, T, m, pinned, bytes, dir, ofd);
+                munmap(m, bytes);
+                best = now() - t0;
+                close(ofd);
+                unlink(oname);
+            }
+            else
             for (int rep = 0; rep < (mode >= 2 ? 1 : 2); rep++)
             {
                 double s = run(mode, T, src, pinned, bytes, dir, ofd);

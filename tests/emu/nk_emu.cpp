@@ -40,6 +40,7 @@ struct EmuBackend
     void sync() {}
     bool prepare_sort(size_t, std::string &) { return true; }
     unsigned min_list_entries() const { return 0; }
+    unsigned slow_hole_margin() const { return 0; }
     void chunk_sizes(unsigned *c, unsigned, unsigned, unsigned, unsigned, unsigned) { c[0] = c[1] = c[2] = c[3] = c[4] = 0; }
     void begin_timer(int) {}
     void end_timer(int) {}

@@ -92,3 +92,26 @@ def test_n_is_printed_as_a(inputs):
     assert res["rc"] == 0
     text = (out / "output_forward.k21_norm1000000_thread0.fastq").read_bytes()
     assert b"@withN/1\nACGTTGCAAACGTTGCA" in text and b"N" not in text.split(b"@withN/1\n")[1].split(b"\n")[0]
+
+
+def test_record_cut_short_by_a_nul_is_still_scored(inputs):
+    """C:1622-1631, C:1733: when read_line gives up inside a record (a NUL byte here), the reference still scores and
+    counts what it has read and only then leaves the loop.  Counters and the -P table must agree with the reference
+    binary; the record's own printed lines are undefined there (stale stack bytes), so read files are compared between
+    the oracle and the product only."""
+    tmp, files = inputs
+    f, r = files["trailing_blank_line"]
+    lines = f.read_bytes().split(b"\n")
+    lines[4 * 250 + 1] = lines[4 * 250 + 1][:40] + b"\0" + lines[4 * 250 + 1][41:]   # NUL inside a forward sequence line
+    cut = tmp / "nul_1.fastq"
+    cut.write_bytes(b"\n".join(lines))
+    args = ["-f", cut, "-r", r, "-k", 21, "-d", 4, "-m", 1, "-P"]
+    want = cc.run_cli(ol.ORACLE_CLI, args, tmp / "nul" / "oracle")
+    got = cc.run_cli(EMU_CLI, args, tmp / "nul" / "emu", env={"NKB200_STEP_PAIRS": "16"})
+    cc.assert_same(got, want, "NUL in a sequence line")
+    assert want["counters"][-1][0] == 251   # 250 whole records and the cut one
+    if ol.REF_BIN.exists():
+        ref = cc.run_cli(ol.REF_BIN, args, tmp / "nul" / "ref")
+        assert ref["rc"] == want["rc"] and ref["counters"] == want["counters"] and ref["final"] == want["final"]
+        dumps = [n for n in want["files"] if n.startswith("output_kmer.")]
+        assert dumps and all(ref["files"][n] == want["files"][n] for n in dumps)

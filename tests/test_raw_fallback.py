@@ -62,7 +62,9 @@ def run(binary, env, inputs, name, mixed, gpu):
     m = STEPS_RE.search(got["stdout"])
     assert m, got["stdout"][-400:]
     raw_steps, parsed_steps = int(m.group(1)), int(m.group(2))
-    assert raw_steps > 0
+    # an engine whose step holds text the device declines hands all of its partitions to the host parser from there on,
+    # so a run on one engine may see no raw-text step at all
+    assert raw_steps > 0 or mixed
     assert (parsed_steps > 0) == mixed, (name, raw_steps, parsed_steps)
     return got
 
