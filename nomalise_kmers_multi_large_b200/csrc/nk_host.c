@@ -881,6 +881,7 @@ void nk_destroy(nk_ctx *c)
 }
 
 static int nk_alloc_raw_bufs(nk_ctx *c, nk_dev *dv);
+static int nk_have_avx2 = -1; /* streaming-store staging copies (nk_copy_stream_avx2); chosen once in nk_create */
 
 static void nk_alloc_raw_task(int d, void *a)
 {
@@ -922,6 +923,14 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         return nk_fail(NULL, NK_EINVAL, "merged table / merged output need a context that owns all %d partitions", cfg->partitions);
     }
     c->threads = nk_host_threads();
+    /* process-wide choices of CPU features, made here while a single thread runs */
+    if (!nk_mask64)
+        nk_mask64 = nk_mask64_pick();
+    if (nk_have_avx2 < 0)
+    {
+        __builtin_cpu_init();
+        nk_have_avx2 = __builtin_cpu_supports("avx2") && !nk_env_on("NKB200_PLAIN_MEMCPY");
+    }
     int ndev_avail = nkd_device_count();
     if (ndev_avail <= 0)
     {
@@ -1996,8 +2005,6 @@ __attribute__((target("avx2"))) static void nk_copy_stream_avx2(uint8_t *dst, co
     memcpy(dst + i, src + i, n - i);
 }
 
-static int nk_have_avx2 = -1;
-
 static void nk_copy_task(int i, void *a)
 {
     const nk_copy *cp = &((const nk_copy *)a)[i];
@@ -2113,11 +2120,6 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
     sb->raw_bytes = at;
     sb->n_records = total;
     double t1 = nk_now();
-    if (nk_have_avx2 < 0)
-    {
-        __builtin_cpu_init();
-        nk_have_avx2 = __builtin_cpu_supports("avx2") && !nk_env_on("NKB200_PLAIN_MEMCPY");
-    }
     if (sb->n_copies)
         nk_parallel_for(sb->n_copies, threads, nk_copy_task, sb->copies);
     dv->index_s += nk_now() - t0;
@@ -3373,9 +3375,17 @@ int nk_main(int argc, char **argv)
             fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a.rev[i], ((const char *)mr.map)[0]);
             return 1;
         }
-        uint64_t before[NK_MAX_PARTITIONS];
+        /* what the reference's worker keeps from the start of a file for the percentages of its report line, C:1592-1594 */
+        uint64_t before[NK_MAX_PARTITIONS], before_printed[NK_MAX_PARTITIONS], before_skipped[NK_MAX_PARTITIONS],
+            before_used[NK_MAX_PARTITIONS];
         for (int t = 0; t < c->n_local; t++)
+        {
+            nkd_part_stats st0;
             before[t] = c->part[t].processed;
+            before_printed[t] = c->part[t].printed;
+            before_skipped[t] = c->part[t].skipped;
+            before_used[t] = nk_partition_stats(c, c->part[t].gid, &st0) == NK_OK ? st0.used : 0;
+        }
         double tf = nk_now();
         rc = paired ? nk_process_paired(c, mf.map, mf.size, mr.map, mr.size) : nk_process_single(c, mf.map, mf.size);
         double dt = nk_now() - tf;
@@ -3404,9 +3414,14 @@ int nk_main(int argc, char **argv)
             nk_part *p = &c->part[t];
             nkd_part_stats st;
             nk_partition_stats(c, p->gid, &st);
+            /* growth since the start of this file, as the reference reports it when no 60 s progress report
+             * intervened (C:1746-1749); the rate's own percentage compares with such a report and stays 0 */
+            float gp = before_printed[t] ? (float)(p->printed - before_printed[t]) / (int)before_printed[t] : 0;
+            float gs = before_skipped[t] ? (float)(p->skipped - before_skipped[t]) / (int)before_skipped[t] : 0;
+            float gk = before_used[t] ? (float)(st.used - before_used[t]) / before_used[t] : 0;
             printf("Thread %d - Processing rate: %'.0f (%+.2f%%) sequences/s, processed %'zu pairs, printed: %'zu (%+.2f%%), skipped: %'zu (%+.2f%%), Unique kmers (all sequences; this thread): %'zu (%+.2f%%)\n",
-                   p->gid, dt > 0 ? (double)(p->processed - before[t]) / dt : 0.0, 0.0, (size_t)p->processed, (size_t)p->printed, 0.0,
-                   (size_t)p->skipped, 0.0, (size_t)st.used, 0.0);
+                   p->gid, dt > 0 ? (double)(p->processed - before[t]) / dt : 0.0, 0.0, (size_t)p->processed, (size_t)p->printed, gp * 100,
+                   (size_t)p->skipped, gs * 100, (size_t)st.used, gk * 100);
         }
         printf("Cumulative file statistics: Processed %'zu, Printed %'zu, Skipped %'zu, Cumulative Max Unique Kmers in a thread: %'zu\n",
                (size_t)c->tot.processed, (size_t)c->tot.printed, (size_t)c->tot.skipped, (size_t)c->file_max_used);

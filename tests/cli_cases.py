@@ -73,6 +73,29 @@ def run_cli(binary, args, cwd: Path, env=None, timeout=1800):
             "stderr": p.stderr}
 
 
+def stdout_contract(res):
+    """The program's stdout with the parts that depend on timing masked (rates, run times) and the per-thread lines in
+    thread order (the reference prints them in completion order): every other line is part of the observable contract
+    (SURVEY 8.B row b: 'Initial hash table size ...', 'Processing file pair ...', per-thread counts, cumulative file
+    statistics, final report)."""
+    lines = []
+    for l in res["stdout"].splitlines():
+        if l.startswith("B200:"):
+            continue   # the product's own extra lines under -e
+        l = re.sub(r"Processing rate: (?:[\d,]+|inf|-?nan) \([+-]?(?:[\d.]+|inf|-?nan)%\)", "Processing rate: R", l)
+        l = re.sub(r"Total runtime: [\d.]+ seconds", "Total runtime: T seconds", l)
+        l = re.sub(r"Overall processing rate: [\d,]+ ", "Overall processing rate: R ", l)
+        lines.append(l)
+    threads = sorted((l for l in lines if l.startswith("Thread ")), key=lambda l: int(l.split()[1]))
+    it = iter(threads)
+    return [next(it) if l.startswith("Thread ") else l for l in lines]
+
+
+def assert_same_stdout(a, b, what=""):
+    sa, sb = stdout_contract(a), stdout_contract(b)
+    assert sa == sb, (what, "stdout differs", [(x, y) for x, y in zip(sa, sb) if x != y][:4], len(sa), len(sb))
+
+
 def assert_same(a, b, what=""):
     assert a["rc"] == b["rc"], (what, "exit status", a["rc"], b["rc"], a["stderr"][-500:], b["stderr"][-500:])
     assert a["counters"] == b["counters"], (what, "counters", a["counters"], b["counters"])

@@ -82,3 +82,17 @@ def test_cli_fatal_on_non_dna(cases):
     for binary in (ol.ORACLE_CLI, EMU_CLI):
         res = cc.run_cli(binary, ["-f", bad, "-r", r, "-k", 15, "-m", 1], tmp / "fatal" / Path(binary).name)
         assert res["rc"] == 1 and "FATAL: FWD sequence does not appear to be a DNA sequence" in res["stderr"]
+
+
+@pytest.mark.parametrize("name", ["dump_p4_k15", "equal_sizes_F6", "multi_file", "single_end_fq2fa_empty", "fasta_in_out_mixed"])
+def test_cli_stdout_matches_reference_binary(cases, name):
+    """the stdout lines of SURVEY 8.B row (b), compared line by line with the reference binary's (timing fields masked)"""
+    if not ol.REF_BIN.exists():
+        pytest.skip("oracle/_ref not built (no reference checkout on this box)")
+    tmp, table = cases
+    args = table[name]
+    binary = ol.REF_BIN_TLS if "-c" in args else ol.REF_BIN
+    want = cc.run_cli(binary, args, tmp / name / "reference_stdout")
+    got = cc.run_cli(EMU_CLI, args, tmp / name / "emu_stdout", env={"NKB200_STEP_PAIRS": "64"})
+    cc.assert_same(got, want, name)
+    cc.assert_same_stdout(got, want, name)

@@ -53,6 +53,7 @@ def test_cli_matches_reference_binary(cases, name, ref):
     want = cc.run_cli(ref, args, tmp / name / "reference")   # sleeps 1 s per partition (C:1879)
     got = cc.run_cli(capi.CLI_PATH, args, tmp / name / "b200_vs_ref")
     cc.assert_same(got, want, name)
+    cc.assert_same_stdout(got, want, name)   # every stdout line of the reference, timing fields masked
 
 
 @pytest.mark.parametrize("name", ["canonical_p8", "p64_canonical_config3_shape"])
