@@ -111,6 +111,12 @@ int nkd_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
  * n_ops = op_base + windows of the last read. */
 int nkd_seed_step(nkd_engine *e, const uint8_t *seq, size_t seq_bytes, const nkd_read *reads, size_t n_reads,
                   int64_t *first_invalid);
+/* seed_kmer_hash (C:1322-1373) on a piece of a file as raw record text: `raw` holds n_records complete records
+ * (text_bytes bytes, padded with spaces to a multiple of 16 in a page-locked buffer); the device finds the lines
+ * and inserts, with count 0, the first `limit` records whose sequence line is longer than k.  *taken = how many
+ * of them this piece had.  NK_EIRREGULAR when the text needs the host parser (nkd_seed_step). */
+int nkd_seed_raw(nkd_engine *e, const uint8_t *raw, size_t text_bytes, uint32_t n_records, int lines_per_record,
+                 uint32_t limit, uint32_t *taken, int64_t *first_invalid);
 /* copy_hash_table for every resident partition (C:908-927, C:2279); frees the seed table */
 int nkd_seed_finish(nkd_engine *e);
 /* the same for an engine that shares its GPU with `src`: its partitions are copied from src's seed table, so

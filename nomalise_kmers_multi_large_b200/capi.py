@@ -109,7 +109,7 @@ ENGINE_SYMBOLS = ["nkd_create", "nkd_destroy", "nkd_last_error", "nkd_seed_step"
                   "nkd_device_count", "nkd_run_stats_get", "nkd_read_scores", "nkd_dump_text", "nkd_compact",
                   "nkd_merge_begin", "nkd_merge_add_part", "nkd_merge_add", "nkd_merge_finish", "nkd_run_spans", "nkd_seed_finish_from",
                   "nkd_stage_raw", "nkd_fetch_raw", "nkd_fetch_raw_slot", "nkd_fetch_wait",
-                  "nkd_upload_raw", "nkd_set_table_budget", "nkd_residency_stats", "nkd_device_memory"]
+                  "nkd_upload_raw", "nkd_set_table_budget", "nkd_residency_stats", "nkd_device_memory", "nkd_seed_raw"]
 PART_SEED, PART_MERGED = -1, -2
 PIPELINE_SYMBOLS = ["nk_create", "nk_destroy", "nk_last_error", "nk_create_error", "nk_initial_capacity",
                     "nk_seed_buffer", "nk_seed_finish", "nk_process_paired", "nk_process_single", "nk_totals_get",
@@ -152,6 +152,7 @@ def _declare_engine(lib):
     lib.nkd_fetch_raw_slot.argtypes = [vp, C.c_int, u8p, sz, C.POINTER(RawResult), C.POINTER(C.c_int64), C.c_int]
     lib.nkd_fetch_wait.argtypes = [vp, C.c_int]
     lib.nkd_upload_raw.argtypes = [vp, u8p, sz]
+    lib.nkd_seed_raw.argtypes = [vp, u8p, sz, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]
     lib.nkd_set_table_budget.argtypes = [vp, C.c_uint64]
     lib.nkd_residency_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.nkd_device_memory.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -274,6 +275,14 @@ class Engine:
         inv = C.c_int64(-1)
         self._check(self.lib.nkd_seed_step(self.h, buf.ctypes.data, buf.size, descs.ctypes.data, len(descs), C.byref(inv)))
         return inv.value
+
+    def seed_raw(self, text: bytes, n_records, limit, lines_per_record=4):
+        """nkd_seed_raw: returns (records taken, first invalid record or -1)"""
+        raw = np.frombuffer(text + b" " * ((-len(text)) % 16), dtype=np.uint8).copy()
+        taken, inv = C.c_uint32(0), C.c_int64(-1)
+        self._check(self.lib.nkd_seed_raw(self.h, raw.ctypes.data, len(text), n_records, lines_per_record, limit,
+                                          C.byref(taken), C.byref(inv)))
+        return taken.value, inv.value
 
     def seed_finish(self):
         self._check(self.lib.nkd_seed_finish(self.h))

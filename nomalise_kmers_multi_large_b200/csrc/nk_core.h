@@ -966,6 +966,7 @@ struct NkRaw
     const NkRawWin *wins;
     unsigned n_wins, n_records, stride /* mates per record */, per /* lines per record */;
     int k, emit_mode;
+    int min_len; /* length gate: k when scoring (C:1430-1443), k + 1 when seeding (strlen > K, C:1347) */
     unsigned *tile; /* line ends per tile, then their exclusive scan; [n_tiles] = total */
     unsigned *nlpos;
     unsigned nlpos_cap;
@@ -1039,7 +1040,7 @@ NK_HD void nk_raw_record_op(const NkRaw &R, unsigned i)
         m[s] = nk_raw_record(R, w, r, (int)s);
         if (m[s].longest >= NK_LINE_SPLIT)
             flags |= NK_RAW_LONG;
-        if ((int)m[s].seq_len < R.k)
+        if ((int)m[s].seq_len < R.min_len)
             kept = false; /* either mate shorter than K: the record vanishes, C:1430-1443 */
         if (r + 1 == w.n_records && m[s].end != (s ? w.r_off + w.r_bytes : w.f_off + w.f_bytes))
             flags |= NK_RAW_SHAPE;
@@ -1056,6 +1057,18 @@ NK_HD void nk_raw_record_op(const NkRaw &R, unsigned i)
         rd.reserved = 0;
         R.reads[R.stride * i + s] = rd;
         R.nops[R.stride * i + s] = rd.len ? (unsigned)rd.len - (unsigned)R.k + 1u : 0u;
+    }
+}
+
+/* seeding takes the first `limit` records that pass the length gate (C:1347-1356): flag them, rank them (scan), and
+ * drop the ones beyond the limit */
+NK_HD void nk_seed_flag_op(const NkRaw &R, unsigned i) { R.outlen[i] = R.nops[i] ? 1u : 0u; }
+NK_HD void nk_seed_clip_op(const NkRaw &R, unsigned i, unsigned limit)
+{
+    if (R.outoff[i] >= limit && R.nops[i])
+    {
+        R.reads[i].len = 0;
+        R.nops[i] = 0;
     }
 }
 

@@ -575,6 +575,16 @@ __global__ void __launch_bounds__(256) k_raw_records(const NkRaw R)
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < R.n_records; i += gridDim.x * blockDim.x)
         nk_raw_record_op(R, i);
 }
+__global__ void __launch_bounds__(256) k_seed_flag(const NkRaw R)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < R.n_records; i += gridDim.x * blockDim.x)
+        nk_seed_flag_op(R, i);
+}
+__global__ void __launch_bounds__(256) k_seed_clip(const NkRaw R, unsigned limit)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < R.n_records; i += gridDim.x * blockDim.x)
+        nk_seed_clip_op(R, i, limit);
+}
 __global__ void __launch_bounds__(256) k_raw_opbase(const NkRaw R)
 {
     const unsigned n = R.n_records * R.stride;
@@ -1089,7 +1099,7 @@ struct CudaBackend
         ok(cub::DeviceScan::ExclusiveSum(scan_tmp, bytes, in, out, (long long)n, stream), "exclusive scan");
         launches++;
     }
-    void raw_index(const NkRaw &R)
+    void raw_records(const NkRaw &R)
     {
         const unsigned n_tiles = (R.raw_bytes + NK_RAW_TILE - 1) / NK_RAW_TILE, n_reads = R.n_records * R.stride;
         zero(R.tile + n_tiles, sizeof(unsigned));
@@ -1098,8 +1108,25 @@ struct CudaBackend
         k_raw_positions<<<grid_for(n_tiles, 1), 256, 0, stream>>>(R, n_tiles), launches++;
         zero(R.nops + n_reads, sizeof(unsigned));
         k_raw_records<<<grid_for(R.n_records, 256), 256, 0, stream>>>(R), launches++;
+    }
+    /* seeding: only the first `limit` records that passed the length gate stay */
+    void raw_limit(const NkRaw &R, unsigned limit)
+    {
+        zero(R.outlen + R.n_records, sizeof(unsigned));
+        k_seed_flag<<<grid_for(R.n_records, 256), 256, 0, stream>>>(R), launches++;
+        scan_u32(R.outlen, R.outoff, (size_t)R.n_records + 1);
+        k_seed_clip<<<grid_for(R.n_records, 256), 256, 0, stream>>>(R, limit), launches++;
+    }
+    void raw_number(const NkRaw &R)
+    {
+        const unsigned n_reads = R.n_records * R.stride;
         scan_u32(R.nops, R.opscan, (size_t)n_reads + 1);
         k_raw_opbase<<<grid_for(n_reads, 256), 256, 0, stream>>>(R), launches++;
+    }
+    void raw_index(const NkRaw &R)
+    {
+        raw_records(R);
+        raw_number(R);
     }
     /* accepted records' text, forward then reverse per window, and the windows' counters */
     void raw_emit(const NkRaw &R)

@@ -132,6 +132,16 @@ int nkd_stage_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes, const nkd
     h->e.be.enter();
     return nkd_done(h, h->e.stage_raw(raw, raw_bytes, segs, n_segs, paired, lines_per_record));
 }
+int nkd_seed_raw(nkd_engine *h, const uint8_t *raw, size_t text_bytes, uint32_t n_records, int lines_per_record, uint32_t limit,
+                 uint32_t *taken, int64_t *first_invalid)
+{
+    h->e.be.enter();
+    unsigned t = 0;
+    int rc = nkd_done(h, h->e.seed_raw(raw, text_bytes, n_records, lines_per_record, limit, &t, first_invalid));
+    if (taken)
+        *taken = t;
+    return rc;
+}
 int nkd_upload_raw(nkd_engine *h, const uint8_t *raw, size_t raw_bytes)
 {
     h->e.be.enter();

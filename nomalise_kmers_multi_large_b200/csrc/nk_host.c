@@ -772,6 +772,7 @@ struct nk_ctx
     uint32_t raw_part_bytes; /* raw text per partition, mate and step */
     nk_lineidx lif, lir;     /* line indexes of the files being processed */
     uint64_t raw_steps, parsed_steps;
+    uint64_t seed_raw_records, seed_parsed_records; /* seed records taken from raw text on the device / parsed here */
     uint64_t waves; /* passes over disjoint sets of partitions in nk_process_* so far (1 per file when all tables fit) */
     /* seeding */
     uint8_t *seed_seq[2]; /* two staging buffers: one is parsed into while the GPUs seed from the other */
@@ -881,6 +882,7 @@ void nk_destroy(nk_ctx *c)
 }
 
 static int nk_alloc_raw_bufs(nk_ctx *c, nk_dev *dv);
+static void nk_copy_task(int i, void *a);
 static int nk_have_avx2 = -1; /* streaming-store staging copies (nk_copy_stream_avx2); chosen once in nk_create */
 
 static void nk_alloc_raw_task(int d, void *a)
@@ -1258,10 +1260,10 @@ static int nk_seed_join(nk_seed_job *j)
     return j->result;
 }
 
-int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed)
+/* seed_kmer_hash with the records parsed here (the byte-exact path; what the device declines ends up here) from
+ * file offset `start` on */
+static int nk_seed_buffer_parsed(nk_ctx *c, const char *data, size_t size, size_t start, int records_to_seed)
 {
-    if (c->seeded)
-        return nk_fail(c, NK_EINVAL, "nk_seed_buffer after nk_seed_finish");
     double t0 = nk_now();
     if (!nk_mask64)
         nk_mask64 = nk_mask64_pick();
@@ -1274,8 +1276,8 @@ int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed
     /* seed_kmer_hash splits on '\n' only and needs every line of a record terminated (C:1334-1344); the GPUs
      * seed from one staging buffer while the next batch is parsed into the other */
     nk_nliter it;
-    nk_nliter_seek(&it, data, 0, size);
-    size_t rec_start = 0;
+    nk_nliter_seek(&it, data, start, size);
+    size_t rec_start = start;
     for (;;)
     {
         size_t q = rec_start, seq_start = 0, seq_len = 0;
@@ -1340,6 +1342,7 @@ int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed
         n_reads++;
         bytes += need;
         ops += nops;
+        c->seed_parsed_records++;
         if (++done == records_to_seed)
             break;
     }
@@ -1358,6 +1361,140 @@ int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed
         rc = jobs[cur].result;
     }
     c->tot.seed_seconds += nk_now() - t0;
+    return rc;
+}
+
+/* ---- seeding on raw record text: the host cuts the head of the file into pieces of whole records (parallel
+ * line count), copies them into the lead engines' page-locked step buffer, and the device does the rest
+ * (nkd_seed_raw): 6 M records no longer wait for a single-threaded parse */
+
+typedef struct
+{
+    nk_ctx *c;
+    const uint8_t *raw;
+    size_t text_bytes;
+    uint32_t n_records, limit;
+    uint32_t taken[64];
+    int64_t inv[64];
+    int rc[64];
+} nk_seedraw_job;
+
+static void nk_seedraw_task(int d, void *a)
+{
+    nk_seedraw_job *j = a;
+    nk_dev *dv = &j->c->dev[d];
+    j->rc[d] = NK_OK;
+    j->inv[d] = -1;
+    j->taken[d] = 0;
+    if (dv->lead != d)
+        return;
+    j->rc[d] = nkd_seed_raw(dv->eng, j->raw, j->text_bytes, j->n_records, j->c->cfg.in_fastq ? 4 : 2, j->limit, &j->taken[d],
+                            &j->inv[d]);
+}
+
+/* returns NK_OK with *consumed = bytes of the file that were dealt with and *seeded = records taken; stops early
+ * (without error) at text the device declines, which the caller gives to the host parser */
+static int nk_seed_buffer_raw(nk_ctx *c, const char *data, size_t size, int records_to_seed, size_t *consumed, int *seeded)
+{
+    const int per = c->cfg.in_fastq ? 4 : 2;
+    nk_buf f = {data, size};
+    nk_stepbuf *sb = &c->dev[0].sb[0]; /* free until processing starts */
+    size_t cap = (size_t)c->dev[0].n_parts * 2u * ((size_t)c->raw_part_bytes + 16u);
+    for (int d = 0; d < c->n_dev; d++)
+    { /* every lead engine takes the same pieces: the smallest step buffer decides their size */
+        size_t cd = (size_t)c->dev[d].n_parts * 2u * ((size_t)c->raw_part_bytes + 16u);
+        if (c->dev[d].lead == d && cd < cap)
+            cap = cd;
+    }
+    uint32_t max_records = (uint32_t)c->seed_cap_reads;
+    size_t pos = 0;
+    *consumed = 0;
+    *seeded = 0;
+    if (c->n_dev > 64)
+        return NK_OK;
+    while (*seeded < records_to_seed && pos < size)
+    {
+        /* a piece: as many whole records as fit the buffer, the read limit and the operation limit (a sequence line
+         * holds at most as many k-mers as it has bytes; FASTQ spends half of a record's bytes on it) */
+        size_t want_bytes = cap - 64;
+        size_t ops_bytes = c->cfg.in_fastq ? c->seed_cap_ops * 2 : c->seed_cap_ops;
+        if (ops_bytes < want_bytes)
+            want_bytes = ops_bytes;
+        size_t hi = pos + want_bytes < size ? pos + want_bytes : size;
+        nk_lineidx li = {0};
+        nk_lineidx_build_range(&li, &f, c->threads, pos, hi);
+        uint64_t before = nk_lineidx_before(&li, pos), upto = nk_lineidx_before(&li, hi);
+        uint64_t recs = (upto - before) / (uint64_t)per;
+        if (recs > max_records)
+            recs = max_records;
+        uint64_t need = (uint64_t)(records_to_seed - *seeded);
+        if (recs > need + need / 8 + 4096)
+            recs = need + need / 8 + 4096; /* a few more than needed: some may be too short to count */
+        size_t end = recs ? nk_lineidx_find(&li, before + recs * (uint64_t)per - 1) : SIZE_MAX;
+        nk_lineidx_free(&li);
+        if (!recs || end == SIZE_MAX)
+            break; /* no whole record left (the tail goes to the host parser, which knows what to do with it) */
+        end += 1;
+        size_t n = end - pos, n16 = (n + 15) & ~(size_t)15;
+        int n_copies = 0;
+        for (size_t o = 0; o < n; o += NK_COPY_PIECE)
+        {
+            nk_copy *cp = &sb->copies[n_copies++];
+            cp->dst = sb->raw + o;
+            cp->src = data + pos + o;
+            cp->n = n - o < NK_COPY_PIECE ? n - o : NK_COPY_PIECE;
+        }
+        nk_parallel_for(n_copies, c->threads, nk_copy_task, sb->copies);
+        memset(sb->raw + n, ' ', n16 - n);
+        nk_seedraw_job job;
+        job.c = c;
+        job.raw = sb->raw;
+        job.text_bytes = n;
+        job.n_records = (uint32_t)recs;
+        job.limit = (uint32_t)need;
+        nk_parallel_for(c->n_dev, c->n_dev, nk_seedraw_task, &job);
+        int declined = 0;
+        for (int d = 0; d < c->n_dev; d++)
+        {
+            if (job.rc[d] == NK_EIRREGULAR)
+                declined = 1;
+            else if (job.rc[d])
+                return nk_fail(c, job.rc[d], "%s", nkd_last_error(c->dev[d].eng));
+        }
+        if (declined)
+            break; /* nothing of this piece was inserted: the host parser continues at `pos` */
+        if (job.inv[0] >= 0)
+        { /* is_valid_sequence_single's abort, C:1416-1420: the text of record inv's sequence line */
+            size_t q = job.inv[0] ? nk_kth_newline(data + pos, n, (uint64_t)per * (uint64_t)job.inv[0]) + 1 : 0;
+            q += nk_kth_newline(data + pos + q, n - q, 1) + 1;
+            size_t len = nk_kth_newline(data + pos + q, n - q, 1);
+            char *txt = malloc(len + 1);
+            nk_scrub_copy(txt, data + pos + q, len);
+            nk_fail(c, NK_EDATA, "FATAL: FWD sequence does not appear to be a DNA sequence\n%s\n", txt);
+            free(txt);
+            return NK_EDATA;
+        }
+        *seeded += (int)job.taken[0];
+        pos = end;
+        *consumed = pos;
+    }
+    return NK_OK;
+}
+
+int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed)
+{
+    if (c->seeded)
+        return nk_fail(c, NK_EINVAL, "nk_seed_buffer after nk_seed_finish");
+    double t0 = nk_now();
+    size_t consumed = 0;
+    int seeded = 0, rc = NK_OK;
+    if (c->raw_mode && !nk_env_on("NKB200_HOST_SEED") && c->dev[0].have_raw_bufs)
+        rc = nk_seed_buffer_raw(c, data, size, records_to_seed, &consumed, &seeded);
+    c->tot.seed_seconds += nk_now() - t0;
+    c->seed_raw_records += (uint64_t)seeded;
+    /* the rest (text the device declined, the unterminated tail of a file, or everything when raw text is off) */
+    if (!rc && seeded < records_to_seed && consumed < size)
+        rc = nk_seed_buffer_parsed(c, data, size, consumed, records_to_seed - seeded);
     return rc;
 }
 
@@ -3457,6 +3594,8 @@ int nk_main(int argc, char **argv)
                c->tot.seed_seconds, c->tot.process_seconds, c->tot.index_seconds, c->tot.device_seconds, c->tot.write_seconds, gpus, c->threads);
         printf("B200: %llu device steps on raw record text, %llu on host-parsed records\n", (unsigned long long)c->raw_steps,
                (unsigned long long)c->parsed_steps);
+        printf("B200: %llu seed records taken from raw text on the device, %llu parsed by the host\n",
+               (unsigned long long)c->seed_raw_records, (unsigned long long)c->seed_parsed_records);
         uint64_t ev = 0, ld = 0;
         for (int d = 0; d < c->n_dev; d++)
         {

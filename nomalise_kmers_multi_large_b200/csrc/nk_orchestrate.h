@@ -123,6 +123,7 @@ class NkEngine
     std::vector<NkRawWin> h_wins;
     uint64_t raw_cap = 0, raw_reads_cap = 0, raw_lines_cap = 0;
     NkRaw raw{}; /* the staged raw step */
+    size_t n_records_staged_for_seed = 0;
     bool raw_staged = false;
 
     bool debug = getenv("NKB200_DEBUG") != nullptr;
@@ -954,6 +955,7 @@ class NkEngine
         raw.stride = stride;
         raw.per = (unsigned)per;
         raw.k = cfg.k;
+        raw.min_len = cfg.k;
         raw.tile = d_tile;
         raw.nlpos = d_nlpos;
         raw.nlpos_cap = (unsigned)lines;
@@ -1004,6 +1006,89 @@ class NkEngine
         staged = true;
         raw_staged = true;
         ran = false;
+        return NK_OK;
+    }
+
+    /* seed_kmer_hash (C:1322-1373) on raw record text: the first `limit` records of this piece of a file whose
+     * sequence is longer than K are inserted with count 0 (sequence_to_hash_zero, C:1501-1537); *taken = how many */
+    int seed_raw(const uint8_t *host_raw, size_t text_bytes, unsigned n_records, int per, unsigned limit, unsigned *taken,
+                 int64_t *first_invalid)
+    {
+        if (seeded)
+            return fail(NK_EINVAL, "nkd_seed_raw after nkd_seed_finish");
+        int rc = raw_prepare();
+        if (rc)
+            return rc;
+        const size_t bytes16 = (text_bytes + 15) & ~(size_t)15;
+        const uint64_t lines = (uint64_t)per * n_records;
+        if ((per != 2 && per != 4) || n_records == 0 || text_bytes == 0 || bytes16 > raw_cap || n_records > cfg.max_step_reads ||
+            lines + 1 > raw_lines_cap)
+            return fail(NK_EINVAL, "nkd_seed_raw: piece exceeds the limits given to nkd_create");
+        h_wins.assign(1, NkRawWin{});
+        h_wins[0].f_bytes = (unsigned)text_bytes;
+        h_wins[0].n_records = n_records;
+        be.h2d(d_raw, host_raw, bytes16);
+        h2d_bytes += bytes16;
+        be.h2d(d_wins, h_wins.data(), sizeof(NkRawWin));
+        be.zero(d_rflags, 4 * sizeof(unsigned));
+        be.zero(d_nlpos, (size_t)(lines + 1) * sizeof(unsigned));
+        raw = NkRaw{};
+        raw.raw = d_raw;
+        raw.raw_bytes = (unsigned)bytes16;
+        raw.wins = d_wins;
+        raw.n_wins = 1;
+        raw.n_records = n_records;
+        raw.stride = 1;
+        raw.per = (unsigned)per;
+        raw.k = cfg.k;
+        raw.min_len = cfg.k + 1; /* strictly longer than K, C:1347 */
+        raw.tile = d_tile;
+        raw.nlpos = d_nlpos;
+        raw.nlpos_cap = (unsigned)lines;
+        raw.reads = d_reads;
+        raw.nops = d_nops;
+        raw.opscan = d_opscan;
+        raw.t_out = d_tout;
+        raw.flags = d_rflags;
+        raw.outlen = d_outlen;
+        raw.outoff = d_outoff;
+        be.raw_records(raw);
+        be.raw_limit(raw, limit);
+        be.raw_number(raw);
+        unsigned h_flags[4] = {0, 0, 0, 0}, h_t = 0, h_q = 0;
+        be.d2h(h_flags, d_rflags, sizeof h_flags);
+        be.d2h(&h_t, d_tout, sizeof h_t);
+        be.d2h(&h_q, d_outoff + n_records, sizeof h_q);
+        be.sync();
+        if (h_flags[1] != lines || (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG | NK_RAW_SHAPE)))
+        {
+            if (h_flags[1] == lines && (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG)))
+                return fail(NK_EIRREGULAR, "raw text needs the host parser (NUL byte or a line of 1024+ chars)");
+            return fail(NK_EINVAL, "nkd_seed_raw: the piece does not hold the announced number of complete records");
+        }
+        if (h_t >= (1u << NK_T_BITS))
+            return fail(NK_EINVAL, "a seed piece has 2^28 or more operations");
+        std::fill(T.begin(), T.end(), 0u);
+        T[0] = h_t;
+        seq_view = d_raw;
+        n_reads = n_records;
+        n_records_staged_for_seed = n_records;
+        paired = 0;
+        be.zero(d_invalid, n_reads + 1);
+        std::vector<NkTable *> tabs{&seed};
+        rc = run_ops(NK_MODE_SEED, tabs);
+        if (rc)
+            return rc;
+        if (taken)
+            *taken = h_q < limit ? h_q : limit;
+        if (first_invalid)
+        { /* the reference aborts at the first seed record that is not DNA (C:1349-1350) */
+            be.zero(d_ctr, sizeof(NkCounters));
+            be.decide(make_run(NK_MODE_SEED, 0, 0), (unsigned)n_reads, 0, cfg.coverage, d_accept);
+            be.d2h(&h_ctr, d_ctr, 32);
+            be.sync();
+            *first_invalid = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
+        }
         return NK_OK;
     }
 

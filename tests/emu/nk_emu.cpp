@@ -214,6 +214,25 @@ struct EmuBackend
     void copy_wait(int) {}
     void raw_index(const NkRaw &R)
     {
+        raw_records(R);
+        raw_number(R);
+    }
+    void raw_limit(const NkRaw &R, unsigned limit)
+    {
+        for (unsigned i : order(R.n_records))
+            nk_seed_flag_op(R, i);
+        unsigned run = 0;
+        for (unsigned i = 0; i < R.n_records; i++)
+        {
+            R.outoff[i] = run;
+            run += R.outlen[i];
+        }
+        R.outoff[R.n_records] = run;
+        for (unsigned i : order(R.n_records))
+            nk_seed_clip_op(R, i, limit);
+    }
+    void raw_records(const NkRaw &R)
+    {
         unsigned n = 0;
         for (unsigned p = 0; p < R.raw_bytes; p++)
         {
@@ -229,6 +248,9 @@ struct EmuBackend
         R.flags[1] = n;
         for (unsigned i : order(R.n_records))
             nk_raw_record_op(R, i);
+    }
+    void raw_number(const NkRaw &R)
+    {
         const unsigned n_reads = R.n_records * R.stride;
         unsigned run = 0;
         for (unsigned j = 0; j < n_reads; j++)

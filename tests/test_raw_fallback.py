@@ -14,6 +14,7 @@ from tests import oracle_lib as ol
 ROOT = Path(__file__).resolve().parent.parent
 EMU_CLI = ROOT / "tests" / "emu" / "nk_emu_cli"
 STEPS_RE = re.compile(r"B200: (\d+) device steps on raw record text, (\d+) on host-parsed records")
+SEEDS_RE = re.compile(r"B200: (\d+) seed records taken from raw text on the device, (\d+) parsed by the host")
 
 
 @pytest.fixture(scope="module")
@@ -62,6 +63,9 @@ def run(binary, env, inputs, name, mixed, gpu):
     m = STEPS_RE.search(got["stdout"])
     assert m, got["stdout"][-400:]
     raw_steps, parsed_steps = int(m.group(1)), int(m.group(2))
+    seeds_raw, seeds_parsed = (int(x) for x in SEEDS_RE.search(got["stdout"]).groups())
+    # seeding (C:1322-1373) reads the same files: whole records go to the device as raw text, the rest to the host parser
+    assert seeds_raw > 0 and (seeds_parsed > 0) == (name == "nul_in_quality"), (seeds_raw, seeds_parsed)
     # an engine whose step holds text the device declines hands all of its partitions to the host parser from there on,
     # so a run on one engine may see no raw-text step at all
     assert raw_steps > 0 or mixed

@@ -69,3 +69,45 @@ def test_raw_text_the_device_declines_emu(emu_lib):
 @pytest.mark.gpu
 def test_raw_text_the_device_declines_gpu(cuda_lib):
     check_declined(cuda_lib)
+
+
+def check_seed_raw(lib):
+    """nkd_seed_raw: the first `limit` records with a sequence longer than k are inserted with count 0
+    (seed_kmer_hash, C:1322-1373); shorter ones do not count; the table equals the oracle's slot for slot"""
+    from tests import oracle_lib as ol
+    rng = np.random.default_rng(7)
+    genome = ec.make_genome(rng, 4000)
+    k, cap0 = 15, 1031
+    eng = capi.Engine(k=k, canonical=True, depth_per_part=3, n_parts=1, capacity0=cap0, max_step_reads=1024,
+                      max_step_bytes=1 << 12, max_step_ops=1 << 17, max_raw_bytes=1 << 18, lib=lib)
+    try:
+        otab = ol.OracleTable(cap0)
+        total_taken = 0
+        for piece, limit in ((300, 120), (200, 1000)):      # the first piece holds more than `limit`, the second fewer
+            seqs = [ec.sample_read(rng, genome, 5, 90, n_rate=0.05) for _ in range(piece)]
+            text = b"".join(b"@s%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in enumerate(seqs))
+            good = [s for s in seqs if len(s) > k][:limit]
+            for s in good:
+                otab.seed(s, k, True)
+            taken, inv = eng.seed_raw(text, piece, limit)
+            assert (taken, inv) == (len(good), -1)
+            total_taken += taken
+        st = eng.seed_stats()
+        assert (st["capacity"], st["used"]) == (otab.cap, otab.used) and otab.cap > cap0   # the table grew while seeding
+        ek, ec_ = eng.seed_export()
+        okk, okc = otab.export()
+        assert np.array_equal(ek, okk) and np.array_equal(ec_, okc)
+        # a record that is not DNA is reported by its index in the piece
+        bad = b"@a\n" + b"ACGT" * 8 + b"\n+\n" + b"I" * 32 + b"\n@b\nACGTACGTACGTACGTACGTnACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIII\n"
+        assert eng.seed_raw(bad, 2, 10)[1] == 1
+    finally:
+        eng.close()
+
+
+def test_seeding_from_raw_text_emu(emu_lib):
+    check_seed_raw(emu_lib)
+
+
+@pytest.mark.gpu
+def test_seeding_from_raw_text_gpu(cuda_lib):
+    check_seed_raw(cuda_lib)
