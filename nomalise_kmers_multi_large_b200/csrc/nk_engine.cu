@@ -27,6 +27,7 @@
 #include <cuda/std/functional>
 
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -663,6 +664,13 @@ __global__ void k_emit_summary(const NkRaw R)
 
 /* ------------------------------------------------------------------ backend */
 
+/* boolean environment switches: unset, empty and "0" mean off (the same rule as nk_env_on in nk_host.c) */
+static bool nk_env_flag(const char *name)
+{
+    const char *s = getenv(name);
+    return s && *s && strcmp(s, "0") != 0;
+}
+
 struct CudaBackend
 {
     int dev = -1, sms = 148;
@@ -724,7 +732,7 @@ struct CudaBackend
             err = cuda_err;
             return NK_ENODEVICE;
         }
-        if (!getenv("NKB200_SPIN_SYNC") &&
+        if (!nk_env_flag("NKB200_SPIN_SYNC") &&
             cudaEventCreateWithFlags(&sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
         {
             cudaGetLastError();
@@ -812,7 +820,7 @@ struct CudaBackend
      * staged sequence bytes over PCIe with coalesced 16-byte loads instead of waiting for a bulk copy */
     const void *device_view_of_host(const void *p)
     {
-        if (getenv("NKB200_NO_ZEROCOPY"))
+        if (nk_env_flag("NKB200_NO_ZEROCOPY"))
             return nullptr;
         cudaPointerAttributes a;
         if (cudaPointerGetAttributes(&a, p) != cudaSuccess)

@@ -1232,7 +1232,7 @@ static void *nk_seed_flush_thread(void *a)
     nk_seed_job *j = a;
     nk_ctx *c = j->c;
     j->result = NK_OK;
-    if (getenv("NKB200_DEBUG"))
+    if (nk_env_on("NKB200_DEBUG"))
         fprintf(stderr, "[nk] seed flush: %zu reads, %zu bytes\n", j->n_reads, j->bytes);
     nk_parallel_for(c->n_dev, c->n_dev, nk_seed_task, j);
     for (int d = 0; d < c->n_dev; d++)

@@ -126,7 +126,7 @@ class NkEngine
     size_t n_records_staged_for_seed = 0;
     bool raw_staged = false;
 
-    bool debug = getenv("NKB200_DEBUG") != nullptr;
+    bool debug = getenv("NKB200_DEBUG") && *getenv("NKB200_DEBUG") && strcmp(getenv("NKB200_DEBUG"), "0") != 0;
 
     int fail(int code, const std::string &m)
     {

@@ -47,3 +47,22 @@ def test_config_c1_default_capacity(tmp_path, pair):
     cc.assert_same(got, want, "C1 " + pair[0])
     if ol.REF_BIN.exists():
         cc.assert_same(got, cc.run_cli(ol.REF_BIN, argv, tmp_path / "reference"), "C1 vs reference " + pair[0])
+
+
+def test_default_capacity_table_grows_like_the_reference(tmp_path):
+    """1 GiB table -> 1.5 GiB (67,108,879 -> 100,663,318 slots, C:1055-1108) during seeding and scoring, checked against
+    what the unmodified reference wrote for the same input (tests/golden/growth_default_capacity.json)."""
+    import json
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    gold = json.loads((root / "tests" / "golden" / "growth_default_capacity.json").read_text())
+    subprocess.run(["make", "-C", str(root / "tools")], check=True, capture_output=True)
+    subprocess.run([str(root / "tools" / "nk_synth")] + gold["synth"].split() + ["-o", str(tmp_path / "g")], check=True,
+                   capture_output=True)
+    res = cc.run_cli(capi.CLI_PATH, ["-f", tmp_path / "g_1.fastq", "-r", tmp_path / "g_2.fastq"] + gold["flags"].split() + ["-e"],
+                     tmp_path / "out")
+    assert res["rc"] == 0, res["stderr"][-400:]
+    assert res["final"] == gold["final"]
+    assert res["files"] == gold["files_md5"]
+    assert gold["final"]["Cumulative Max unique kmers in any thread"] > 0.8 * gold["capacity_sequence"][0]
