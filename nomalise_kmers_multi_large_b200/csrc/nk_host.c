@@ -198,6 +198,53 @@ static void nk_trace(int engine, int step, const char *stage, double a, double b
     pthread_mutex_unlock(&nk_tr.mu);
 }
 
+/* Page-locking memory costs ~0.4 s per GB on these hosts, and a context's step buffers are GBs: the large blocks of a
+ * destroyed context are kept for the next one of the same shape in this process (bench.py and any caller that runs
+ * several files' worth of contexts).  At most NK_PIN_CACHE blocks are held; NKB200_NO_PIN_CACHE=1 turns it off. */
+#define NK_PIN_CACHE 48
+static struct
+{
+    pthread_mutex_t mu;
+    void *ptr[NK_PIN_CACHE];
+    size_t size[NK_PIN_CACHE];
+} nk_pins = {PTHREAD_MUTEX_INITIALIZER, {0}, {0}};
+
+static void *nk_pinned_get(size_t bytes)
+{
+    void *p = NULL;
+    pthread_mutex_lock(&nk_pins.mu);
+    for (int i = 0; i < NK_PIN_CACHE && !p; i++)
+        if (nk_pins.ptr[i] && nk_pins.size[i] == bytes)
+        {
+            p = nk_pins.ptr[i];
+            nk_pins.ptr[i] = NULL;
+        }
+    pthread_mutex_unlock(&nk_pins.mu);
+    return p ? p : nkd_alloc_pinned(bytes);
+}
+
+static void nk_pinned_put(void *p, size_t bytes)
+{
+    if (!p)
+        return;
+    const char *off = getenv("NKB200_NO_PIN_CACHE");
+    if (bytes >= ((size_t)8 << 20) && !(off && *off && strcmp(off, "0") != 0))
+    {
+        pthread_mutex_lock(&nk_pins.mu);
+        for (int i = 0; i < NK_PIN_CACHE; i++)
+            if (!nk_pins.ptr[i])
+            {
+                nk_pins.ptr[i] = p;
+                nk_pins.size[i] = bytes;
+                p = NULL;
+                break;
+            }
+        pthread_mutex_unlock(&nk_pins.mu);
+    }
+    if (p)
+        nkd_free_pinned(p);
+}
+
 /* boolean environment switches: unset, empty and "0" mean off */
 static int nk_env_on(const char *name)
 {
@@ -706,6 +753,7 @@ typedef struct
     size_t n_records;
     /* raw-text steps (page-locked): record text in, accepted records' text out */
     uint8_t *raw, *out;
+    size_t raw_cap, out_cap; /* allocated sizes (the blocks go back to the process-wide pinned cache) */
     size_t raw_bytes;
     nkd_raw_segment *rsegs;
     nkd_raw_result *rres;
@@ -831,8 +879,8 @@ static void nk_free_stepbuf(nk_stepbuf *sb, int n_parts)
     free(sb->segs);
     nkd_free_pinned(sb->seq);
     nkd_free_pinned(sb->accept);
-    nkd_free_pinned(sb->raw);
-    nkd_free_pinned(sb->out);
+    nk_pinned_put(sb->raw, sb->raw_cap);
+    nk_pinned_put(sb->out, sb->out_cap);
     free(sb->rsegs);
     free(sb->rres);
     free(sb->rseg_li);
@@ -1143,8 +1191,10 @@ static int nk_alloc_raw_bufs(nk_ctx *c, nk_dev *dv)
     for (int b = 0; b < NK_NBUF; b++)
     {
         nk_stepbuf *sb = &dv->sb[b];
-        sb->raw = nkd_alloc_pinned(cap);
-        sb->out = nkd_alloc_pinned(cap + (size_t)dv->n_parts * 4u * c->step_pairs); /* fq->fa may add "/1" per record */
+        sb->raw_cap = cap;
+        sb->out_cap = cap + (size_t)dv->n_parts * 4u * c->step_pairs; /* fq->fa may add "/1" per record */
+        sb->raw = nk_pinned_get(sb->raw_cap);
+        sb->out = nk_pinned_get(sb->out_cap);
         sb->rsegs = calloc((size_t)dv->n_parts, sizeof *sb->rsegs);
         sb->rres = calloc((size_t)dv->n_parts, sizeof *sb->rres);
         sb->rseg_li = calloc((size_t)dv->n_parts, sizeof *sb->rseg_li);

@@ -1,5 +1,6 @@
 """Randomised whole-program parity stress on CPU: random inputs (lengths below k, FASTA/FASTQ, equal sizes, single-end),
-flags, step sizes, engines per GPU, emulated GPU counts and host thread counts; every output file and counter of the
+flags, step sizes, engines per GPU, emulated GPU counts, host thread counts, raw-text vs host-parsed steps and seeding,
+table budgets (waves); every output file and counter of the
 emulated drop-in binary compared with the oracle CLI.  usage: stress_cli_emu.py SEED SECONDS."""
 import os, random, shutil, sys, time
 from pathlib import Path
@@ -30,6 +31,11 @@ while time.time() - t0 < budget:
            'NK_EMU_DEVICES': str(rnd.choice([1, 2, 3])), 'NK_EMU_SEED': str(rnd.randrange(1 << 30)),
            'NKB200_THREADS': str(rnd.choice([1, 2, 5, 8]))}
     env['NKB200_GPUS'] = env['NK_EMU_DEVICES']
+    if rnd.random() < 0.3: del env['NKB200_ENGINES_PER_GPU']          # the default engine policy
+    if rnd.random() < 0.2: env['NKB200_HOST_PARSE'] = '1'             # round-1 path: records parsed on the host
+    if rnd.random() < 0.2: env['NKB200_HOST_SEED'] = '1'
+    if rnd.random() < 0.2: env['NKB200_NO_PREFETCH'] = '1'
+    if rnd.random() < 0.3: env['NKB200_TABLE_BUDGET_MB'] = str(rnd.choice([150, 300, 450, 900]))   # waves, parked tables
     try:
         want = cc.run_cli(ol.ORACLE_CLI, args, d / 'oracle', timeout=600)
         got = cc.run_cli(EMU, args, d / 'emu', env=env, timeout=600)
