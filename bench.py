@@ -431,6 +431,9 @@ def run_ours(args):
     sums = dict(zip(keys, all_sum(dist, local, [sum(s[k] for s in steps) for k in keys])))
     ikeys = ["probe_ms", "probe_launches", "probe_touches", "processed", "run_ms"] + ["ms_" + c for c in CLASSES]
     iso = dict(zip(ikeys, all_sum(dist, local, [isolated[k] for k in ikeys]))) if isolated else None
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pairs = sums["processed"] / n
