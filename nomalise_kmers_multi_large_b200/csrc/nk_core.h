@@ -978,7 +978,7 @@ struct NkRaw
     unsigned *outlen, *outoff; /* per (window, mate, record) and its exclusive scan */
     unsigned char *out;
     unsigned long long *summary; /* per window: fwd offset, fwd bytes, rev offset, rev bytes, processed, printed */
-    unsigned inv_rec;            /* first record with a non-DNA byte (NK_TMAX = none) */
+    const NkCounters *ctr;       /* inv_max = NK_TMAX - first record with a non-DNA byte (k_decide), 0 = none */
 };
 
 /* window of record i: the last window whose rec0 <= i */
@@ -1105,7 +1105,8 @@ NK_HD unsigned nk_emit_len_op(const NkRaw &R, unsigned e, unsigned &wi, unsigned
     rec = w.rec0 + r;
     const unsigned char a = R.accept[rec];
     /* the reference stops at the first non-DNA record (C:1445-1454): later records of that partition do not count */
-    const bool cut = R.inv_rec >= w.rec0 && R.inv_rec < w.rec0 + w.n_records && rec >= R.inv_rec;
+    const unsigned inv_rec = R.ctr->inv_max ? NK_TMAX - R.ctr->inv_max : NK_TMAX;
+    const bool cut = inv_rec >= w.rec0 && inv_rec < w.rec0 + w.n_records && rec >= inv_rec;
     counted = (a != 2 && !cut) ? 1 : 0;
     printed = (a == 1 && !cut) ? 1 : 0;
     if (!printed || R.emit_mode == NK_EMIT_NONE)

@@ -26,6 +26,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cuda/std/functional>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -662,6 +663,25 @@ __global__ void k_emit_summary(const NkRaw R)
         nk_emit_summary_op(R, w);
 }
 
+/* Clearing and small control blocks without the copy engines: while the next step's text is on its way (one long H2D
+ * transfer on the upload stream) a cudaMemsetAsync or a small cudaMemcpyAsync of this step would wait behind it. */
+__global__ void __launch_bounds__(256) k_zero(uint4 *p, size_t n16, unsigned char *tail, unsigned n_tail)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && threadIdx.x < n_tail)
+        tail[threadIdx.x] = 0;
+}
+struct NkBlob
+{
+    unsigned w[768]; /* 3 KB: kernel parameters may hold 4 KB */
+};
+__global__ void __launch_bounds__(256) k_put_small(unsigned *dst, const NkBlob blob, unsigned n_words)
+{
+    for (unsigned i = threadIdx.x; i < n_words; i += blockDim.x)
+        dst[i] = blob.w[i];
+}
+
 /* ------------------------------------------------------------------ backend */
 
 /* boolean environment switches: unset, empty and "0" mean off (the same rule as nk_env_on in nk_host.c) */
@@ -745,6 +765,8 @@ struct CudaBackend
         ok(cudaStreamCreateWithFlags(&up_stream, cudaStreamNonBlocking), "cudaStreamCreate");
         ok(cudaEventCreateWithFlags(&up_done, cudaEventDisableTiming), "cudaEventCreate");
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (getenv("NKB200_COPY_PIECE_MB") && atoi(getenv("NKB200_COPY_PIECE_MB")) > 0)
+            piece = (size_t)atoi(getenv("NKB200_COPY_PIECE_MB")) << 20;
         epoch(dev);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
@@ -830,7 +852,39 @@ struct CudaBackend
         }
         return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
     }
-    void zero(void *p, size_t n) { ok(cudaMemsetAsync(p, 0, n, stream), "cudaMemsetAsync"); }
+    void zero(void *p, size_t n)
+    {
+        if (!n)
+            return;
+        unsigned char *b = (unsigned char *)p;
+        size_t head = (16 - ((uintptr_t)b & 15)) & 15;
+        if (head > n)
+            head = n;
+        if (head) /* allocations are 256-byte aligned: only interior pointers get here */
+            ok(cudaMemsetAsync(b, 0, head, stream), "cudaMemsetAsync");
+        size_t n16 = (n - head) / 16, tail = (n - head) & 15;
+        unsigned g = grid_for(n16 ? n16 : 1, 256 * 8);
+        k_zero<<<g, 256, 0, stream>>>((uint4 *)(b + head), n16, b + head + n16 * 16, (unsigned)tail);
+        launches++;
+    }
+    /* n bytes (a multiple of 4, 4-byte aligned destination) as kernel parameters */
+    void put_small(void *d, const void *h, size_t n)
+    {
+        if ((n & 3) || ((uintptr_t)d & 3))
+        {
+            h2d(d, h, n);
+            return;
+        }
+        const size_t words = n / 4;
+        for (size_t at = 0; at < words; at += 768)
+        {
+            NkBlob b;
+            size_t m = words - at < 768 ? words - at : 768;
+            memcpy(b.w, (const unsigned *)h + at, m * 4);
+            k_put_small<<<1, 256, 0, stream>>>((unsigned *)d + at, b, (unsigned)m);
+            launches++;
+        }
+    }
     void h2d(void *d, const void *h, size_t n) { ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream), "H2D copy"); }
     void d2h(void *h, const void *d, size_t n) { ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream), "D2H copy"); }
     void d2d(void *d, const void *s, size_t n) { ok(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream), "D2D copy"); }
@@ -840,11 +894,8 @@ struct CudaBackend
     void sync()
     {
         if (!sync_ev)
-        {
             ok(cudaStreamSynchronize(stream), "stream synchronize");
-            return;
-        }
-        if (ok(cudaEventRecord(sync_ev, stream), "event record"))
+        else if (ok(cudaEventRecord(sync_ev, stream), "event record"))
             ok(cudaEventSynchronize(sync_ev), "event synchronize");
     }
 
@@ -947,6 +998,16 @@ struct CudaBackend
             }
         }
         return ev[device];
+    }
+    /* ms between the last end of timer i and the first start of timer j of the current step (idle or untimed work) */
+    float gap_ms(int i, int j)
+    {
+        Timer &a = timers[i], &b = timers[j];
+        float ms = 0;
+        if (a.used >= 2 && b.used >= 2 && cudaEventElapsedTime(&ms, a.ev[a.used - 1], b.ev[0]) == cudaSuccess)
+            return ms;
+        cudaGetLastError();
+        return 0;
     }
     float timer_ms(int i)
     {
@@ -1056,9 +1117,14 @@ struct CudaBackend
         return true;
     }
     /* the next step's text goes to the device on its own stream ... */
+    /* Large transfers go in pieces: a step's small reads (counters, flags: a handful of round trips per step) share the
+     * copy engines and the PCIe link with them, and behind one 100+ MB copy each of them waited milliseconds. */
+    size_t piece = 4u << 20;
     void upload(void *d, const void *h, size_t n)
     {
-        ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, up_stream), "H2D copy");
+        for (size_t at = 0; at < n; at += piece)
+            ok(cudaMemcpyAsync((char *)d + at, (const char *)h + at, n - at < piece ? n - at : piece, cudaMemcpyHostToDevice, up_stream),
+               "H2D copy");
         ok(cudaEventRecord(up_done, up_stream), "event record");
     }
     /* ... and the engine's stream picks it up when it has landed */
@@ -1072,8 +1138,10 @@ struct CudaBackend
     /* the caller has synchronised the engine's stream: the text is complete in d_out */
     void copy_out(void *h, const void *d, size_t n, int slot)
     {
-        if (n)
-            ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, copy_stream), "D2H copy");
+        for (size_t at = 0; at < n; at += piece)
+            ok(cudaMemcpyAsync((char *)h + at, (const char *)d + at, n - at < piece ? n - at : piece, cudaMemcpyDeviceToHost,
+                               copy_stream),
+               "D2H copy");
         ok(cudaEventRecord(copy_done[slot], copy_stream), "event record");
         last_copy = copy_done[slot];
     }

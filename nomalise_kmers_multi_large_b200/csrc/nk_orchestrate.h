@@ -124,6 +124,9 @@ class NkEngine
     uint64_t raw_cap = 0, raw_reads_cap = 0, raw_lines_cap = 0;
     NkRaw raw{}; /* the staged raw step */
     size_t n_records_staged_for_seed = 0;
+    bool raw_check = false; /* the staged raw step's parse flags have not been looked at yet */
+    uint64_t raw_lines_expected = 0;
+    unsigned h_rflags[4] = {0, 0, 0, 0};
     bool raw_staged = false;
 
     bool debug = getenv("NKB200_DEBUG") && *getenv("NKB200_DEBUG") && strcmp(getenv("NKB200_DEBUG"), "0") != 0;
@@ -196,6 +199,10 @@ class NkEngine
     void destroy()
     {
         be.sync();
+        if (getenv("NKB200_TIMES") && *getenv("NKB200_TIMES") && strcmp(getenv("NKB200_TIMES"), "0") != 0)
+            fprintf(stderr, "[nkd] span gaps ms: parse->probe %.1f, probe->open %.1f, open->classify %.1f, classify->sort %.1f, "
+                            "decide->emit %.1f, sort->decide %.1f; run %.1f ms\n",
+                    gaps[0], gaps[1], gaps[2], gaps[3], gaps[4], gaps[5], rs.run_ms);
         be.release(seed.tab);
         for (auto &p : parts)
         {
@@ -449,13 +456,30 @@ class NkEngine
             if (tabs[p]->tab) /* tables parked in host memory take no part in this step */
                 g += tabs[p]->cap;
         }
-        be.h2d(d_parts, h_parts.data(), tabs.size() * sizeof(NkPart));
+        /* through kernel parameters, not the copy engine: a step's small control blocks must not queue behind the next
+         * step's text, which the upload stream is sending while this step runs (that cost 2.5 ms per step) */
+        be.put_small(d_parts, h_parts.data(), tabs.size() * sizeof(NkPart));
     }
 
     void fetch_counters()
     {
         be.d2h(&h_ctr, d_ctr, sizeof(NkCounters));
+        if (raw_check)
+            be.d2h(h_rflags, d_rflags, sizeof h_rflags);
         be.sync();
+    }
+
+    /* 0, or why the staged raw step cannot be scored as it stands (looked at once per step) */
+    int raw_verdict()
+    {
+        if (!raw_check)
+            return NK_OK;
+        raw_check = false;
+        if (h_rflags[1] == raw_lines_expected && !(h_rflags[0] & (NK_RAW_NUL | NK_RAW_LONG | NK_RAW_SHAPE)))
+            return NK_OK;
+        if (h_rflags[1] == raw_lines_expected && (h_rflags[0] & (NK_RAW_NUL | NK_RAW_LONG)))
+            return fail(NK_EIRREGULAR, "raw text needs the host parser (NUL byte or a line of 1024+ chars)");
+        return fail(NK_EINVAL, "nkd_stage_raw: a window does not hold the announced number of complete records");
     }
 
     /* The sequential semantics of all operations [0,T[p]) of every table in tabs.
@@ -490,6 +514,8 @@ class NkEngine
                 be.zero(d_ctr, sizeof(NkCounters));
                 be.probe(make_run(NK_MODE_COUNT, 0, 0));
                 fetch_counters();
+                if (int bad = raw_verdict())
+                    return bad; /* nothing has been changed yet */
                 for (size_t p = 0; p < np; p++)
                     if (lo[p] < hi[p] && tabs[p]->used >= tabs[p]->thr && h_ctr.real_ops[p] > 0)
                     {
@@ -536,6 +562,15 @@ class NkEngine
                 fprintf(stderr, "[nkd] open done (n_open %u)\n", h_ctr.n_open);
             }
             fetch_counters();
+            if (int bad = raw_verdict())
+            { /* forget this run (the same replay as for an overflow) and hand the text back */
+                NkRun U = make_run(mode, -1, 0);
+                be.probe(U);
+                be.open_ops(U);
+                be.untag(U, std::min(h_ctr.n_open, open_cap));
+                be.sync();
+                return bad;
+            }
             if (debug)
             {
                 fprintf(stderr, "[nkd] mode %d fwd: open %u pend %u spec %u claim %u ovf %x |", mode, h_ctr.n_open,
@@ -943,7 +978,7 @@ class NkEngine
                 h2d_bytes += hi - lo;
             }
         }
-        be.h2d(d_wins, h_wins.data(), (size_t)n_segs * sizeof(NkRawWin));
+        be.put_small(d_wins, h_wins.data(), (size_t)n_segs * sizeof(NkRawWin));
         be.zero(d_rflags, 4 * sizeof(unsigned));
         be.zero(d_nlpos, (size_t)(lines + 1) * sizeof(unsigned));
         raw = NkRaw{};
@@ -969,36 +1004,25 @@ class NkEngine
         raw.outoff = d_outoff;
         raw.out = d_out;
         raw.summary = d_summary;
-        raw.inv_rec = NK_TMAX;
+        raw.ctr = d_ctr;
         be.begin_timer(0); /* the step's device span starts with its parsing */
         be.reset_timer(9);
         be.begin_timer(9);
         be.raw_index(raw);
         be.end_timer(9);
-        unsigned h_flags[4] = {0, 0, 0, 0};
-        std::vector<unsigned> h_t((size_t)n_segs);
-        be.d2h(h_flags, d_rflags, sizeof h_flags);
-        be.d2h(h_t.data(), d_tout, (size_t)n_segs * sizeof(unsigned));
-        be.sync();
-        /* h_flags[1] = line ends found in the whole buffer */
-        if (h_flags[1] != lines || (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG | NK_RAW_SHAPE)))
-        {
-            be.end_timer(0);
-            be.reset_timer(0);
-            if (h_flags[1] == lines && (h_flags[0] & (NK_RAW_NUL | NK_RAW_LONG)))
-                return fail(NK_EIRREGULAR, "raw text needs the host parser (NUL byte or a line of 1024+ chars)");
-            return fail(NK_EINVAL, "nkd_stage_raw: a window does not hold the announced number of complete records");
-        }
-        uint64_t tot = 0;
+        /* No round trip here: what the parse found (NUL bytes, long lines, a window that does not hold its records) is
+         * read together with the step's counters after the first forward run (run_ops), which is undone if the text has
+         * to go to the host parser after all.  Until then every partition's operation count is bounded by its bytes
+         * (a sequence line has at most as many k-mers as it has characters). */
         for (int s = 0; s < n_segs; s++)
         {
-            T[h_wins[s].part] = h_t[s];
-            if (h_t[s] >= (1u << NK_T_BITS))
-                return fail(NK_EINVAL, "a partition has 2^28 or more operations in one step");
-            tot += h_t[s];
+            uint64_t bound = (uint64_t)h_wins[s].f_bytes + h_wins[s].r_bytes;
+            if (bound >= (1u << NK_T_BITS))
+                return fail(NK_EINVAL, "a partition has 2^28 or more bytes of record text in one step");
+            T[h_wins[s].part] = (unsigned)bound;
         }
-        if (tot > cfg.max_step_ops)
-            return fail(NK_EINVAL, "step has more operations than max_step_ops");
+        raw_check = true;
+        raw_lines_expected = lines;
         seq_view = d_raw;
         n_reads = (size_t)recs * stride;
         n_records = (size_t)recs;
@@ -1029,7 +1053,7 @@ class NkEngine
         h_wins[0].n_records = n_records;
         be.h2d(d_raw, host_raw, bytes16);
         h2d_bytes += bytes16;
-        be.h2d(d_wins, h_wins.data(), sizeof(NkRawWin));
+        be.put_small(d_wins, h_wins.data(), sizeof(NkRawWin));
         be.zero(d_rflags, 4 * sizeof(unsigned));
         be.zero(d_nlpos, (size_t)(lines + 1) * sizeof(unsigned));
         raw = NkRaw{};
@@ -1098,11 +1122,8 @@ class NkEngine
             return fail(NK_EINVAL, "nkd_fetch_raw without nkd_stage_raw + nkd_run");
         if (emit_mode < 0 || emit_mode > 2)
             return fail(NK_EINVAL, "nkd_fetch_raw: bad emit mode");
-        be.d2h(&h_ctr, d_ctr, 32);
-        be.sync();
-        int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         raw.emit_mode = emit_mode;
-        raw.inv_rec = inv >= 0 ? (unsigned)inv : NK_TMAX;
+        raw.ctr = d_ctr; /* k_decide left the first non-DNA record there: the text kernels read it on the device */
         be.reset_timer(10);
         be.begin_timer(10);
         be.zero(d_summary, 6 * (size_t)raw.n_wins * sizeof(unsigned long long));
@@ -1112,7 +1133,9 @@ class NkEngine
         be.end_timer(0);
         std::vector<unsigned long long> sm(6 * (size_t)raw.n_wins);
         be.d2h(sm.data(), d_summary, sm.size() * sizeof(unsigned long long));
+        be.d2h(&h_ctr, d_ctr, 32);
         be.sync();
+        int64_t inv = h_ctr.inv_max ? (int64_t)(NK_TMAX - h_ctr.inv_max) : -1;
         uint64_t total = 0;
         for (unsigned w = 0; w < raw.n_wins; w++)
             total = std::max<uint64_t>(total, std::max(sm[6 * w] + sm[6 * w + 1], sm[6 * w + 2] + sm[6 * w + 3]));
@@ -1143,8 +1166,17 @@ class NkEngine
         return NK_OK;
     }
 
+    double gaps[6] = {0, 0, 0, 0, 0, 0};
     void finish_timers()
     {
+        /* where a step's span is not covered by the kernel classes: parse -> probe, probe -> open, open -> classify,
+         * classify -> sort, decide -> emit (NKB200_TIMES prints the totals when the engine goes away) */
+        gaps[0] += be.gap_ms(9, 1);
+        gaps[1] += be.gap_ms(1, 2);
+        gaps[2] += be.gap_ms(2, 4);
+        gaps[3] += be.gap_ms(4, 5);
+        gaps[4] += be.gap_ms(7, 10);
+        gaps[5] += be.gap_ms(5, 7) + be.gap_ms(6, 7) * 0;
         be.timer_spans(0, spans);
         last_total_ms = be.timer_ms(0);
         last_probe_ms = be.timer_ms(1);

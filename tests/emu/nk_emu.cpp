@@ -35,6 +35,7 @@ struct EmuBackend
     void release(void *p) { free(p); }
     void zero(void *p, size_t n) { memset(p, 0, n); }
     void h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); }
+    void put_small(void *d, const void *h, size_t n) { memcpy(d, h, n); }
     void d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); }
     void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void sync() {}
@@ -47,6 +48,7 @@ struct EmuBackend
     void reset_timer(int) {}
     void timer_spans(int, std::vector<float> &) {}
     float timer_ms(int) { return 0.f; }
+    float gap_ms(int, int) { return 0.f; }
 
     std::vector<unsigned> order(size_t n)
     {
