@@ -427,7 +427,7 @@ def run_ours(args):
     wall_s = sum(all_max(dist, local, s["wall_s"]) for s in steps)
     keys = ["processed", "printed", "skipped", "launches", "probe_launches", "ops", "touches", "probe_touches",
             "slow_events", "expansions", "h2d_bytes", "d2h_bytes", "probe_ms", "index_seconds", "device_seconds",
-            "write_seconds", "seed_s", "count_s", "pend_events", "open_ops", "engines", "raw_steps", "parsed_steps"] + ["ms_" + c for c in CLASSES]
+            "write_seconds", "seed_s", "count_s", "hot_hits", "pend_events", "open_ops", "engines", "raw_steps", "parsed_steps"] + ["ms_" + c for c in CLASSES]
     sums = dict(zip(keys, all_sum(dist, local, [sum(s[k] for s in steps) for k in keys])))
     ikeys = ["probe_ms", "probe_launches", "probe_touches", "processed", "run_ms"] + ["ms_" + c for c in CLASSES]
     iso = dict(zip(ikeys, all_sum(dist, local, [isolated[k] for k in ikeys]))) if isolated else None
@@ -489,7 +489,8 @@ def run_ours(args):
         "counters": {"printed": sums["printed"] / n, "skipped": sums["skipped"] / n, "ops": sums["ops"] / n,
                      "touches": sums["touches"] / n, "slow_events": sums["slow_events"] / n,
                      "pending_list_entries": sums["pend_events"] / n, "open_list_entries": sums["open_ops"] / n,
-                     "expansions_in_scoring": sums["expansions"] / n},
+                     "expansions_in_scoring": sums["expansions"] / n,
+                     "hot_table_hits": sums["hot_hits"] / n},
     }
     if iso and iso["probe_ms"] > 0:
         ibytes = 20.0 * iso["probe_touches"] + (2 * READ_LEN + 1) * iso["processed"]

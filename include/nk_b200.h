@@ -208,6 +208,7 @@ typedef struct
      * numbering), 9 accepted records' text (measure, scan, copy) */
     double class_ms[10];
     uint64_t pend_events, open_ops, slow_events; /* list entries incl. chunk holes */
+    uint64_t hot_hits; /* operations served by the L2-resident table of hot saturated k-mers (no table access) */
 } nkd_run_stats;
 int nkd_run_stats_get(nkd_engine *e, nkd_run_stats *out);
 
@@ -338,6 +339,7 @@ typedef struct
     /* device steps by kind: raw record text parsed on the device (the default) / records parsed by the host
      * (NKB200_HOST_PARSE=1, or text the device declined: NUL bytes, lines of 1024+ chars, a cut last record) */
     uint64_t raw_steps, parsed_steps;
+    uint64_t hot_hits; /* see nkd_run_stats */
 } nk_totals;
 
 int nk_totals_get(nk_ctx *c, nk_totals *out);

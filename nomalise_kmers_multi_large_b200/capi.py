@@ -53,7 +53,7 @@ class RunStats(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("probe_launches", C.c_uint64), ("run_ms", C.c_double),
                 ("probe_ms", C.c_double), ("probe_touches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("class_ms", C.c_double * 10), ("pend_events", C.c_uint64),
-                ("open_ops", C.c_uint64), ("slow_events", C.c_uint64)]
+                ("open_ops", C.c_uint64), ("slow_events", C.c_uint64), ("hot_hits", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "class_ms" else getattr(self, n)) for n, _ in self._fields_}
@@ -97,7 +97,7 @@ class Totals(C.Structure):
                 ("touches", C.c_uint64), ("probe_touches", C.c_uint64), ("slow_events", C.c_uint64),
                 ("expansions", C.c_uint64), ("class_ms", C.c_double * 10), ("pend_events", C.c_uint64),
                 ("open_ops", C.c_uint64), ("engines", C.c_uint64), ("raw_steps", C.c_uint64),
-                ("parsed_steps", C.c_uint64)]
+                ("parsed_steps", C.c_uint64), ("hot_hits", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "class_ms" else getattr(self, n)) for n, _ in self._fields_}

@@ -110,6 +110,7 @@ struct NkCounters
     unsigned n_spec;
     unsigned pad;
     unsigned long long probe_touches; /* slots visited by k_probe (all partitions) */
+    unsigned long long hot_hits;      /* of which: home hits on saturated counters served by the L2-resident hot table */
     unsigned long long touches[256]; /* per partition, slots visited */
     unsigned long long real_ops[256];
     unsigned claims[256];
@@ -167,6 +168,8 @@ struct NkRun
     NkCounters *ctr;
     unsigned long long *keys_out; /* NK_MODE_KEYS */
     unsigned chunk[NK_NLISTS];    /* entries a warp reserves at a time (device only) */
+    struct NkHot *hot;            /* hot table (see nk_hot_*), or null */
+    unsigned hot_mask;            /* entries - 1 (power of two) */
     unsigned *bloom;              /* one bit per hashed global slot: "this counter reached depth in this run" */
     unsigned bloom_words;         /* power of two */
     NkWarpCur *wcur;              /* this warp's cursors in shared memory (device only) */
@@ -415,6 +418,93 @@ NK_HD unsigned long long nk_window_key_ascii(const unsigned char *s, int k, int 
     return x;
 }
 
+/* ---------------------------------------------------------------- hot table
+ *
+ * Most operations of a skewed data set are home hits on counters that passed depth-1 long ago: their test is true
+ * whatever the exact count (saturation, above) and their increments commute.  Such a counter may therefore be kept
+ * in two places: the table's count, and a `pending` sum in a small table of hot keys that stays in L2 (16 MB per
+ * engine).  A hit there needs no DRAM access at all; the table's count lags behind by `pending` until the sums are
+ * folded back in (nk_hot_flush_op) -- before anything reads exact counts: a re-hash (which also moves the slots, so
+ * the hot table is cleared), parking a table in host memory, the -P dump, exports.  Exact by construction: an entry
+ * is only created by an operation that saw the key stored at its home slot with a step-start count >= depth-1, stored
+ * keys do not move between re-hashes, and counts never fall. */
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#endif
+        NkHot
+{
+    unsigned long long key; /* 0 = free */
+    unsigned part1;         /* partition + 1 (written after the key was claimed; 0 = not valid yet) */
+    int pending;            /* increments not yet added to the table's count */
+};
+
+NK_HD unsigned nk_hot_index(const NkRun &P, unsigned long long key, unsigned part)
+{
+    unsigned long long h = (key ^ ((unsigned long long)(part + 1u) << 56)) * 0x9E3779B97F4A7C15ull;
+    return (unsigned)(h >> 40) & P.hot_mask;
+}
+NK_HD unsigned long long nk_atomic_cas64(unsigned long long *p, unsigned long long expect, unsigned long long v)
+{
+#if NK_DEVICE_CODE
+    return atomicCAS(p, expect, v);
+#else
+    unsigned long long o = *p;
+    if (o == expect)
+        *p = v;
+    return o;
+#endif
+}
+/* true when the operation was absorbed: the counter is saturated, the test is true, the increment is noted */
+NK_HD bool nk_hot_hit(const NkRun &P, unsigned long long key, unsigned part, int &high_acc)
+{
+    NkHot *e = &P.hot[nk_hot_index(P, key, part)];
+#if NK_DEVICE_CODE
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(e));
+    const unsigned long long ekey = ((unsigned long long)v.y << 32) | v.x;
+    const unsigned epart = v.z;
+#else
+    const unsigned long long ekey = e->key;
+    const unsigned epart = e->part1;
+#endif
+    if (ekey != key || epart != part + 1u)
+        return false;
+    nk_red_add32(&e->pending, P.delta);
+    high_acc += P.delta;
+    return true;
+}
+/* called by an operation that has just seen `key` stored at its home slot with a saturated counter */
+NK_HD void nk_hot_install(const NkRun &P, unsigned long long key, unsigned part)
+{
+    NkHot *e = &P.hot[nk_hot_index(P, key, part)];
+    if (e->key == 0 && nk_atomic_cas64(&e->key, 0ull, key) == 0ull)
+        e->part1 = part + 1u;
+}
+/* fold entry i's pending increments into the table (every table of the engine must be resident and described by P.parts) */
+NK_HD void nk_hot_flush_op(const NkRun &P, unsigned i)
+{
+    NkHot *e = &P.hot[i];
+    if (e->key == 0 || e->part1 == 0 || e->pending == 0)
+        return;
+    const NkPart &pd = P.parts[e->part1 - 1u];
+    if (!pd.tab)
+        return; /* parked: its sums were folded in before it left */
+    unsigned long long home = nk_mod(e->key, pd.cap, pd.magic);
+    nk_red_add32(&pd.tab[home].count, e->pending);
+    e->pending = 0;
+}
+NK_HD void nk_hot_clear_op(const NkRun &P, unsigned i, unsigned part1)
+{
+    NkHot *e = &P.hot[i];
+    if (part1 == 0 || e->part1 == part1)
+    {
+        e->key = 0;
+        e->part1 = 0;
+        e->pending = 0;
+    }
+}
+
 /* ---------------------------------------------------------------- events */
 
 /* Increment of the ordinary counter of a slot that is NOT claimed inside this step (stored before the step, or
@@ -521,8 +611,13 @@ NK_HD void nk_defer(const NkRun &P, unsigned long long key, unsigned t, unsigned
 /* phase 1: everything about operation (key,t) that does not depend on in-step claims.
  * Returns the number of slots visited (touches).  */
 NK_HD unsigned nk_probe_op(const NkRun &P, const NkPart &pd, unsigned part, unsigned long long key, unsigned t,
-                           unsigned read, int &high_acc)
+                           unsigned read, int &high_acc, unsigned &hot_hits)
 {
+    if (P.mode == NK_MODE_SCORE && P.hot && nk_hot_hit(P, key, part, high_acc))
+    { /* a home hit on a saturated counter (C:972-1008 with a count that no test can tell from the exact one) */
+        hot_hits++;
+        return 1;
+    }
     unsigned long long i = nk_mod(key, pd.cap, pd.magic);
     NkSlot e = nk_load_slot(&pd.tab[i]);
     if (P.mode == NK_MODE_SEED)
@@ -534,6 +629,8 @@ NK_HD unsigned nk_probe_op(const NkRun &P, const NkPart &pd, unsigned part, unsi
     if (e.key == key)
     {
         nk_event(P, pd, (unsigned)i, e.count, e.aux, 1, t, read, high_acc);
+        if (P.mode == NK_MODE_SCORE && P.hot && P.record && e.count - (int)e.aux >= P.depth - 1)
+            nk_hot_install(P, key, part); /* from now on this key's operations stay in L2 */
         return 1;
     }
     if (!nk_is_real(e.key))

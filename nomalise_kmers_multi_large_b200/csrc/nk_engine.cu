@@ -104,7 +104,7 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
     const bool one_part = (MODE == NK_MODE_SEED || MODE == NK_MODE_KEYS);
     /* per-partition counters are accumulated in registers and flushed when the partition changes:
      * reads are partition-major, so a warp flushes a handful of times per launch */
-    unsigned acc_part = 0xFFFFFFFFu, acc_real = 0, acc_touch = 0;
+    unsigned acc_part = 0xFFFFFFFFu, acc_real = 0, acc_touch = 0, acc_hot = 0;
     auto flush = [&]() {
         if (lane == 0 && acc_part != 0xFFFFFFFFu)
         {
@@ -115,8 +115,10 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
                 atomicAdd(&P.ctr->touches[acc_part], (unsigned long long)acc_touch);
                 atomicAdd(&P.ctr->probe_touches, (unsigned long long)acc_touch);
             }
+            if (acc_hot)
+                atomicAdd(&P.ctr->hot_hits, (unsigned long long)acc_hot);
         }
-        acc_real = acc_touch = 0;
+        acc_real = acc_touch = acc_hot = 0;
     };
     for (unsigned r = blockIdx.x * NK_WARPS + warp; r < P.n_reads; r += nwarps)
     {
@@ -183,7 +185,7 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
         __syncwarp();
         if (MODE != NK_MODE_COUNT && __any_sync(0xFFFFFFFFu, bad != 0) && lane == 0)
             P.invalid[r] = 1;
-        unsigned n_real = 0, touches = 0;
+        unsigned n_real = 0, touches = 0, hot = 0;
         int high = 0;
         for (int w0 = 0; w0 < nwin; w0 += 32)
         {
@@ -202,7 +204,7 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
                 continue;
             n_real++;
             if (MODE != NK_MODE_COUNT)
-                touches += nk_probe_op(P, pd, part, key, t, r, high);
+                touches += nk_probe_op(P, pd, part, key, t, r, high, hot);
         }
         __syncwarp();
         if (MODE != NK_MODE_KEYS)
@@ -212,6 +214,8 @@ __device__ __forceinline__ void nk_probe_body(NkRun P)
             if (MODE != NK_MODE_COUNT)
             {
                 acc_touch += __reduce_add_sync(0xFFFFFFFFu, touches);
+                if (MODE == NK_MODE_SCORE && P.hot)
+                    acc_hot += __reduce_add_sync(0xFFFFFFFFu, hot);
                 high = __reduce_add_sync(0xFFFFFFFFu, high);
                 if (lane == 0)
                 {
@@ -663,6 +667,17 @@ __global__ void k_emit_summary(const NkRaw R)
         nk_emit_summary_op(R, w);
 }
 
+__global__ void __launch_bounds__(256) k_hot_flush(const NkRun P)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i <= P.hot_mask; i += gridDim.x * blockDim.x)
+        nk_hot_flush_op(P, i);
+}
+__global__ void __launch_bounds__(256) k_hot_clear(const NkRun P, unsigned part1)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i <= P.hot_mask; i += gridDim.x * blockDim.x)
+        nk_hot_clear_op(P, i, part1);
+}
+
 /* Clearing and small control blocks without the copy engines: while the next step's text is on its way (one long H2D
  * transfer on the upload stream) a cudaMemsetAsync or a small cudaMemcpyAsync of this step would wait behind it. */
 __global__ void __launch_bounds__(256) k_zero(uint4 *p, size_t n16, unsigned char *tail, unsigned n_tail)
@@ -1054,6 +1069,11 @@ struct CudaBackend
         default:
             k_probe_keys<<<g, NK_THREADS, 0, stream>>>(P);
         }
+    }
+    void hot_flush(const NkRun &P) { k_hot_flush<<<grid_for((unsigned long long)P.hot_mask + 1, 256), 256, 0, stream>>>(P), launches++; }
+    void hot_clear(const NkRun &P, unsigned part1)
+    {
+        k_hot_clear<<<grid_for((unsigned long long)P.hot_mask + 1, 256), 256, 0, stream>>>(P, part1), launches++;
     }
     void prepare_claims(const NkRun &P) { k_prepare_claims<<<sms * 8, 256, 0, stream>>>(P), launches++; }
     void open_ops(const NkRun &P) { k_open<<<sms * 8, 256, 0, stream>>>(P), launches++; }

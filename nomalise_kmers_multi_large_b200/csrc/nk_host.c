@@ -3081,6 +3081,7 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
     out->launches = out->probe_launches = out->probe_touches = out->h2d_bytes = out->d2h_bytes = 0;
     out->ops = out->touches = out->slow_events = out->expansions = 0;
     out->pend_events = out->open_ops = 0;
+    out->hot_hits = 0;
     memset(out->class_ms, 0, sizeof out->class_ms);
     for (int d = 0; d < c->n_dev; d++)
     {
@@ -3099,6 +3100,7 @@ int nk_totals_get(nk_ctx *c, nk_totals *out)
         out->probe_touches += rs.probe_touches;
         out->h2d_bytes += rs.h2d_bytes;
         out->d2h_bytes += rs.d2h_bytes;
+        out->hot_hits += rs.hot_hits;
         out->pend_events += rs.pend_events;
         out->open_ops += rs.open_ops;
         for (int k = 0; k < 10; k++)

@@ -87,6 +87,9 @@ class NkEngine
     NkPart *d_parts = nullptr;
     unsigned *d_bloom = nullptr;
     unsigned bloom_words = 0;
+    NkHot *d_hot = nullptr; /* hot table (nk_core.h): saturated home hits stay in L2 */
+    unsigned hot_entries = 0;
+    bool hot_dirty = false; /* some scoring has run since the sums were last folded into the tables */
     unsigned open_cap = 0, pend_cap = 0, claim_cap = 0, spec_cap = 0, slow_cap = 0;
 
     NkCounters h_ctr{};
@@ -187,6 +190,24 @@ class NkEngine
         while (bloom_words < (1u << 24) && (uint64_t)bloom_words * 32u < ops * 8u)
             bloom_words <<= 1;
         ok &= dalloc(d_bloom, bloom_words);
+        /* hot table (nk_core.h): OFF by default.  Measured on the benchmark (profiles/r02_hot_table.txt): with 2^20 / 2^24
+         * entries per engine it absorbs 31 % / 49 % of all operations, and k_probe_score does not get faster (202 -> 210
+         * ms): the lines of hot saturated counters were L2 hits already, the DRAM traffic comes from the cold ones.
+         * NKB200_HOT_ENTRIES=n (rounded down to a power of two) turns it on; the tests keep it covered. */
+        {
+            const char *e = getenv("NKB200_HOT_ENTRIES");
+            long long want = e && *e ? atoll(e) : 0;
+            hot_entries = 0;
+            if (want > 0)
+            {
+                hot_entries = 1;
+                while ((long long)hot_entries * 2 <= want && hot_entries < (1u << 26))
+                    hot_entries *= 2;
+                ok &= dalloc(d_hot, hot_entries);
+                if (d_hot)
+                    be.zero(d_hot, (size_t)hot_entries * sizeof(NkHot));
+            }
+        }
         if (!ok)
             return fail(NK_ENOMEM, "nkd_create: cannot allocate step scratch");
         if (!be.prepare_sort(slow_cap, err))
@@ -229,6 +250,7 @@ class NkEngine
         be.release(d_ctr);
         be.release(d_parts);
         be.release(d_bloom);
+        be.release(d_hot);
         be.release(d_raw);
         be.release(d_raw_next);
         be.release(d_out);
@@ -269,11 +291,26 @@ class NkEngine
 
     /* ------------------------------------------------------------ table residency */
 
+    /* fold the hot table's pending sums into the tables: before anything reads exact counts or moves a table */
+    void flush_hot()
+    {
+        if (!d_hot || !hot_dirty || parts.empty())
+            return;
+        std::vector<NkTable *> tabs;
+        for (auto &p : parts)
+            tabs.push_back(&p);
+        std::vector<unsigned> none(tabs.size(), 0);
+        upload_parts(tabs, none, none);
+        be.hot_flush(make_run(NK_MODE_SCORE, +1, 0));
+        hot_dirty = false;
+    }
+
     int evict_part(int p)
     {
         NkTable &t = parts[p];
         if (!t.tab)
             return NK_OK;
+        flush_hot();
         size_t bytes = (size_t)t.cap * sizeof(NkSlot);
         t.host = malloc(bytes);
         if (!t.host)
@@ -379,6 +416,9 @@ class NkEngine
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         if (debug)
             be.sync();
+        const bool is_part = !parts.empty() && &t >= parts.data() && &t < parts.data() + parts.size();
+        if (is_part)
+            flush_hot(); /* the re-hash carries the counts over (C:1089) and moves the slots */
         double t0 = now();
         NkSlot *nt = (NkSlot *)be.alloc(ncap * sizeof(NkSlot));
         if (!nt)
@@ -391,6 +431,8 @@ class NkEngine
         double t1 = now();
         be.zero(nt, ncap * sizeof(NkSlot));
         be.rehash(t.tab, t.cap, nt, ncap, nk_magic(ncap));
+        if (is_part && d_hot)
+            be.hot_clear(make_run(NK_MODE_SCORE, +1, 0), (unsigned)(&t - parts.data()) + 1u);
         be.sync();
         double t2 = now();
         be.release(t.tab);
@@ -437,6 +479,8 @@ class NkEngine
         P.keys_out = d_keys_out;
         P.bloom = d_bloom;
         P.bloom_words = bloom_words;
+        P.hot = d_hot;
+        P.hot_mask = hot_entries ? hot_entries - 1 : 0;
         be.chunk_sizes(P.chunk, pend_cap, open_cap, claim_cap, slow_cap, spec_cap);
         return P;
     }
@@ -542,6 +586,7 @@ class NkEngine
                 fprintf(stderr, "[nkd] mode %d launching probe: reads %u, p0 [%u,%u)\n", mode, F.n_reads, lo[0], hi[0]);
             }
             be.begin_timer(1);
+            hot_dirty = hot_dirty || mode == NK_MODE_SCORE; /* from here on the hot table may hold sums again */
             be.probe(F);
             be.end_timer(1);
             if (debug)
@@ -733,6 +778,7 @@ class NkEngine
             {
                 tabs[0]->st.slow_events += h_ctr.n_slow; /* device-wide figure, kept on partition 0 */
                 rs.probe_touches += h_ctr.probe_touches;
+                rs.hot_hits += h_ctr.hot_hits;
                 rs.probe_launches++;
                 rs.pend_events += h_ctr.n_pend;
                 rs.open_ops += h_ctr.n_open;
@@ -1360,6 +1406,7 @@ class NkEngine
 
     int export_table(const NkTable &t, uint64_t *keys, int32_t *counts, uint64_t capacity)
     {
+        flush_hot();
         if (!t.tab)
             return fail(NK_EINVAL, "table not resident");
         if (capacity != t.cap)
@@ -1398,6 +1445,7 @@ class NkEngine
     /* entries of a dump source: NKD_PART_SEED, NKD_PART_MERGED or a partition index */
     int dump_source(int part, NkDumpSrc &src, uint64_t &limit)
     {
+        flush_hot();
         src = NkDumpSrc{nullptr, nullptr, nullptr};
         if (part == NKD_PART_MERGED)
         {

@@ -100,11 +100,23 @@ struct EmuBackend
                 continue;
             P.total[op.read] += (unsigned)P.delta;
             int high = 0;
-            unsigned tch = nk_probe_op(P, pd, part, key, t, op.read, high);
+            unsigned hot = 0;
+            unsigned tch = nk_probe_op(P, pd, part, key, t, op.read, high, hot);
             P.ctr->touches[part] += tch;
             P.ctr->probe_touches += tch;
+            P.ctr->hot_hits += hot;
             P.high[op.read] += (unsigned)high;
         }
+    }
+    void hot_flush(const NkRun &P)
+    {
+        for (unsigned i : order((size_t)P.hot_mask + 1))
+            nk_hot_flush_op(P, i);
+    }
+    void hot_clear(const NkRun &P, unsigned part1)
+    {
+        for (unsigned i = 0; i <= P.hot_mask; i++)
+            nk_hot_clear_op(P, i, part1);
     }
     void prepare_claims(const NkRun &P)
     {

@@ -71,3 +71,16 @@ def test_emulated_engine_random_configurations(emu_lib, monkeypatch):
             ec.run_case(emu_lib, **cfg)
         except Exception as e:
             raise AssertionError(f"case {i} {cfg}: {e!r}") from e
+
+
+@pytest.mark.parametrize("entries", ["16", "4096"])
+def test_hot_table_of_saturated_counters_is_exact(emu_lib, monkeypatch, entries):
+    """NKB200_HOT_ENTRIES: home hits on saturated counters are kept as sums in a small side table and folded into the
+    table's counts before anything reads them (growth, -P dump, export): every slot's count still equals the
+    oracle's.  16 entries = constant collisions, 4096 = most hot k-mers fit."""
+    monkeypatch.setenv("NKB200_HOT_ENTRIES", entries)
+    info = ec.run_case(emu_lib, seed=3, k=15, canonical=True, depth=3, cap0=1031, n_parts=2, genome_len=600, steps=4,
+                       records_per_step=120)
+    assert info["expansions"] >= 1
+    raw = ec.run_raw_case(emu_lib, seed=4, k=15, depth=2, cap0=257, n_parts=2, genome_len=500, steps=3)
+    assert raw["processed"] > 0

@@ -108,3 +108,14 @@ def test_engine_random_configurations(cuda_lib):
             ec.run_case(cuda_lib, **cfg)
         except Exception as e:
             raise AssertionError(f"case {i} {cfg}: {e!r}") from e
+
+
+@pytest.mark.parametrize("entries", ["16", "65536"])
+def test_hot_table_of_saturated_counters_is_exact_gpu(cuda_lib, monkeypatch, entries):
+    """the same with the sm_100a kernels (k_probe_score's hot-table branch, k_hot_flush, k_hot_clear)"""
+    monkeypatch.setenv("NKB200_HOT_ENTRIES", entries)
+    info = ec.run_case(cuda_lib, seed=3, k=15, canonical=True, depth=3, cap0=1031, n_parts=2, genome_len=600, steps=4,
+                       records_per_step=120)
+    assert info["expansions"] >= 1
+    raw = ec.run_raw_case(cuda_lib, seed=4, k=15, depth=2, cap0=257, n_parts=2, genome_len=500, steps=3)
+    assert raw["processed"] > 0

@@ -15,6 +15,7 @@ while time.time() - t0 < float(sys.argv[2] if len(sys.argv) > 2 else 600):
         os.environ['NKB200_OPEN_FRAC'] = '0.05'; os.environ['NKB200_PEND_FRAC'] = '0.1'
     else:
         os.environ.pop('NKB200_OPEN_FRAC', None); os.environ.pop('NKB200_PEND_FRAC', None)
+    os.environ['NKB200_HOT_ENTRIES'] = str(rnd.choice([0, 16, 256, 4096, 1 << 20]))   # hot table off / colliding / roomy
     if os.environ.get('NK_STRESS_VERBOSE'):
         print('case', cfg, os.environ.get('NK_EMU_SEED'), os.environ.get('NKB200_OPEN_FRAC'), flush=True)
     try:
