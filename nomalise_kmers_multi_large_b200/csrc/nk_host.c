@@ -1048,10 +1048,12 @@ int nk_create(const nk_config *cfg, nk_ctx **out)
         if (e && atoi(e) > 0)
             sp = (uint32_t)atoi(e);
         else
-        { /* about 75 M operations per launch of a GPU's only engine, half that when several engines share
-           * the GPU (measured: profiles/r01_sweep_engines.txt); launches below ~20 M operations waste their
-           * list chunks and are avoided */
-            uint64_t target = (c->n_dev > n_gpus ? 48ull : 96ull) << 20;
+        { /* about 37 M operations per launch (measured: profiles/r01_sweep_engines.txt; launches below ~20 M
+           * operations waste their list chunks).  Round 1 gave a GPU's only engine twice that; with one partition per
+           * engine (8 GPUs for -p 8) that meant steps of 262,144 pairs, where the ordered slow path is 25 % of the kernel
+           * time and five steps leave little to overlap: 131,072 is 4 % faster on the device and 8 % end to end
+           * (profiles/r02_ab_engines.txt) */
+            uint64_t target = 48ull << 20;
             sp = 262144u;
             while (sp > 2048 && (uint64_t)sp * 288u * (uint64_t)max_dev_parts > target)
                 sp /= 2;

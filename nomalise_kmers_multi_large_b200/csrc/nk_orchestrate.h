@@ -126,7 +126,6 @@ class NkEngine
     std::vector<NkRawWin> h_wins;
     uint64_t raw_cap = 0, raw_reads_cap = 0, raw_lines_cap = 0;
     NkRaw raw{}; /* the staged raw step */
-    size_t n_records_staged_for_seed = 0;
     bool raw_check = false; /* the staged raw step's parse flags have not been looked at yet */
     uint64_t raw_lines_expected = 0;
     unsigned h_rflags[4] = {0, 0, 0, 0};
@@ -880,6 +879,7 @@ class NkEngine
         n_records = nr / stride;
         staged = true;
         raw_staged = false;
+        raw_check = false;
         ran = false;
         return NK_OK;
     }
@@ -1142,7 +1142,7 @@ class NkEngine
         T[0] = h_t;
         seq_view = d_raw;
         n_reads = n_records;
-        n_records_staged_for_seed = n_records;
+        raw_check = false;
         paired = 0;
         be.zero(d_invalid, n_reads + 1);
         std::vector<NkTable *> tabs{&seed};
