@@ -512,7 +512,10 @@ static inline size_t nk_nliter_next(nk_nliter *it)
 /* per-file line index: newline counts of fixed chunks, built on all host cores.  The partitioner looks up
  * "the n-th line end after this offset" in it (C:1265-1300), and so does the raw-text pipeline when it cuts a
  * partition's byte range into steps of whole records. */
-#define NK_LI_CHUNK ((size_t)256 << 10)
+#ifndef NK_LI_CHUNK_BYTES
+#define NK_LI_CHUNK_BYTES (256 << 10) /* the emulation build of the tests uses 4 KB: many chunks in small files */
+#endif
+#define NK_LI_CHUNK ((size_t)NK_LI_CHUNK_BYTES)
 typedef struct
 {
     const nk_buf *f;
@@ -521,36 +524,59 @@ typedef struct
     uint64_t *cum;     /* cum[i] = newlines in chunks [c_lo, i) for c_lo <= i <= c_hi */
 } nk_lineidx;
 
+typedef struct
+{
+    nk_lineidx *li;
+    int base; /* first chunk of this call */
+} nk_lineidx_span;
+
 static void nk_lineidx_task(int i, void *a)
 {
-    nk_lineidx *li = a;
-    int c = li->c_lo + i;
+    nk_lineidx_span *sp = a;
+    nk_lineidx *li = sp->li;
+    int c = sp->base + i;
     size_t lo = (size_t)c * NK_LI_CHUNK, hi = lo + NK_LI_CHUNK;
     if (hi > li->f->size)
         hi = li->f->size;
     li->cum[c + 1] = nk_count_newlines(li->f->data + lo, hi - lo);
 }
 
-/* counts of the chunks that overlap [byte_lo, byte_hi) */
-static void nk_lineidx_build_range(nk_lineidx *li, const nk_buf *f, int threads, size_t byte_lo, size_t byte_hi)
+/* an index that starts at the chunk holding byte_lo and covers nothing yet */
+static void nk_lineidx_open(nk_lineidx *li, const nk_buf *f, size_t byte_lo)
 {
     if (!nk_mask64)
         nk_mask64 = nk_mask64_pick();
     li->f = f;
     li->nchunks = (int)((f->size + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
-    if (byte_hi > f->size)
-        byte_hi = f->size;
     li->c_lo = (int)(byte_lo / NK_LI_CHUNK);
-    li->c_hi = (int)((byte_hi + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
-    if (li->c_hi > li->nchunks)
-        li->c_hi = li->nchunks;
-    if (li->c_lo > li->c_hi)
-        li->c_lo = li->c_hi;
-    li->cum = calloc((size_t)li->nchunks + 2, sizeof(uint64_t));
-    nk_parallel_for(li->c_hi - li->c_lo, threads, nk_lineidx_task, li);
-    li->cum[li->c_lo] = 0;
-    for (int i = li->c_lo; i < li->c_hi; i++)
+    if (li->c_lo > li->nchunks)
+        li->c_lo = li->nchunks;
+    li->c_hi = li->c_lo;
+    li->cum = calloc((size_t)li->nchunks + 2, sizeof(uint64_t)); /* pages of chunks never counted stay untouched */
+}
+
+/* counts the chunks between the covered ones and byte_hi (one owner at a time: readers are the owner) */
+static void nk_lineidx_extend(nk_lineidx *li, int threads, size_t byte_hi)
+{
+    if (byte_hi > li->f->size)
+        byte_hi = li->f->size;
+    int hi = (int)((byte_hi + NK_LI_CHUNK - 1) / NK_LI_CHUNK);
+    if (hi > li->nchunks)
+        hi = li->nchunks;
+    if (hi <= li->c_hi || !li->cum)
+        return;
+    nk_lineidx_span sp = {li, li->c_hi};
+    nk_parallel_for(hi - li->c_hi, threads, nk_lineidx_task, &sp);
+    for (int i = li->c_hi; i < hi; i++)
         li->cum[i + 1] += li->cum[i];
+    li->c_hi = hi;
+}
+
+/* counts of the chunks that overlap [byte_lo, byte_hi) */
+static void nk_lineidx_build_range(nk_lineidx *li, const nk_buf *f, int threads, size_t byte_lo, size_t byte_hi)
+{
+    nk_lineidx_open(li, f, byte_lo);
+    nk_lineidx_extend(li, threads, byte_hi);
 }
 static void nk_lineidx_build_n(nk_lineidx *li, const nk_buf *f, int threads) { nk_lineidx_build_range(li, f, threads, 0, f->size); }
 static void nk_lineidx_build(nk_lineidx *li, const nk_buf *f) { nk_lineidx_build_n(li, f, nk_host_threads()); }
@@ -778,6 +804,12 @@ typedef struct
      * commit_* past every step it has finished, which is where the host parser takes over if it has to */
     uint64_t raw_total, raw_next, line_f, line_r;
     size_t raw_fp, raw_rp, commit_fp, commit_rp;
+    /* the line indexes the builder looks records up in: the context's (whole files, counted before the pipelines
+     * start: raw_known) or the partition's own, which its engine's builder extends a step ahead of itself so that
+     * the GPU does not wait for a count of the whole input.  raw_total is "plenty" until the range's end is covered. */
+    nk_lineidx *lf, *lr;
+    nk_lineidx own_f, own_r;
+    int raw_known;
     int active; /* part of the wave that is being processed (all partitions, unless the tables do not fit the GPU) */
 } nk_part;
 
@@ -2203,6 +2235,47 @@ static void nk_copy_task(int i, void *a)
         memcpy(cp->dst, cp->src, cp->n);
 }
 
+#define NK_RAW_PLENTY ((uint64_t)1 << 62) /* raw_total of a partition whose range has not been counted to its end */
+static const size_t nk_range_slack = 8u * NK_MAX_LINE + 2; /* the record that starts before a range's end runs past it */
+
+/* A partition with its own line indexes: count far enough ahead of its position for one step of `byte_room` bytes
+ * per file.  Near the end of the range the rest is counted and the number of whole records becomes exact (the same
+ * rule as nk_raw_records_in on an index of the whole file).  Returns the records known to be available. */
+static uint64_t nk_part_reach(nk_ctx *c, nk_part *p, int threads, uint64_t byte_room)
+{
+    const int per = c->cfg.in_fastq ? 4 : 2, paired = c->paired;
+    if (p->raw_known)
+        return p->raw_total - p->raw_next;
+    /* chunk boundaries at least one chunk past a full window */
+    size_t need_f = ((p->raw_fp + byte_room) / NK_LI_CHUNK + 2) * NK_LI_CHUNK,
+           need_r = ((p->raw_rp + byte_room) / NK_LI_CHUNK + 2) * NK_LI_CHUNK;
+    int full = need_f >= p->cur.fe || (paired && need_r >= p->cur.re);
+    if (full)
+    {
+        nk_lineidx_extend(p->lf, threads, p->cur.fe + nk_range_slack);
+        uint64_t n = nk_raw_records_in(p->lf, p->cur.fp, p->cur.fe, per, p->line_f);
+        if (paired)
+        {
+            nk_lineidx_extend(p->lr, threads, p->cur.re + nk_range_slack);
+            uint64_t nr = nk_raw_records_in(p->lr, p->cur.rp, p->cur.re, per, p->line_r);
+            n = nr < n ? nr : n;
+        }
+        p->raw_total = n > p->raw_next ? n : p->raw_next;
+        p->raw_known = 1;
+        return p->raw_total - p->raw_next;
+    }
+    /* everything counted lies before the ends of the ranges: every whole record in it belongs to the partition */
+    nk_lineidx_extend(p->lf, threads, need_f);
+    uint64_t n = (nk_lineidx_total(p->lf) - p->line_f) / (uint64_t)per;
+    if (paired)
+    {
+        nk_lineidx_extend(p->lr, threads, need_r);
+        uint64_t nr = (nk_lineidx_total(p->lr) - p->line_r) / (uint64_t)per;
+        n = nr < n ? nr : n;
+    }
+    return n > p->raw_next ? n - p->raw_next : 0;
+}
+
 /* One step: for every partition of the engine the next (at most step_pairs) records of both files, as two windows
  * of the step buffer.  Returns the number of records staged. */
 static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threads)
@@ -2231,15 +2304,19 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
         nk_pstep *ps = &sb->ps[li];
         ps->raw_n = 0;
         ps->fatal_record = -1;
-        uint64_t left = p->active ? p->raw_total - p->raw_next : 0;
+        uint64_t left = p->active && p->raw_total > p->raw_next ? nk_part_reach(c, p, threads, byte_room) : 0;
         if (!left)
+        {
+            if (p->active && !p->raw_known)
+                p->raw_total = p->raw_next; /* not one whole record within reach: not regular text */
             continue;
+        }
         uint64_t n = left < quota ? left : quota;
         size_t f1 = 0, r1 = 0;
         for (;;)
         {
-            f1 = nk_record_start(&c->lif, p->line_f, per, p->raw_next + n);
-            r1 = paired ? nk_record_start(&c->lir, p->line_r, per, p->raw_next + n) : 0;
+            f1 = nk_record_start(p->lf, p->line_f, per, p->raw_next + n);
+            r1 = paired ? nk_record_start(p->lr, p->line_r, per, p->raw_next + n) : 0;
             if (f1 == SIZE_MAX || r1 == SIZE_MAX)
             { /* cannot happen for records counted by nk_raw_records_in; leave the rest to the host parser */
                 n = 0;
@@ -2349,9 +2426,10 @@ static int nk_gpu_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, nk_pipe *pp, i
     dv->t_stage += t1 - t0;
     dv->t_run += t2 - t1;
     dv->t_fetch += t3 - t2;
-    nk_trace((int)(dv - c->dev), (int)c->raw_steps, "stage", t0, t1);
-    nk_trace((int)(dv - c->dev), (int)c->raw_steps, "run", t1, t2);
-    nk_trace((int)(dv - c->dev), (int)c->raw_steps, "fetch", t2, t3);
+    int label = (int)__atomic_load_n(&c->raw_steps, __ATOMIC_RELAXED); /* other engines' device threads count too */
+    nk_trace((int)(dv - c->dev), label, "stage", t0, t1);
+    nk_trace((int)(dv - c->dev), label, "run", t1, t2);
+    nk_trace((int)(dv - c->dev), label, "fetch", t2, t3);
     if (turn)
         pthread_mutex_unlock(turn);
     dv->device_s += nk_now() - t0;
@@ -2860,11 +2938,15 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
                 rhi = c->re[g] > rhi ? c->re[g] : rhi;
             }
         }
-        const size_t slack = 8u * NK_MAX_LINE + 2; /* the record that starts before a range's end runs past it */
-        if (!c->lif.cum && flo != SIZE_MAX)
-            nk_lineidx_build_range(&c->lif, &c->ff, c->threads, flo, fhi + slack);
-        if (paired && !c->lir.cum && rlo != SIZE_MAX)
-            nk_lineidx_build_range(&c->lir, &c->rf, c->threads, rlo, rhi + slack);
+        /* Ranges that came without a count of the files (split by size, one partition, a caller's plan) are counted
+         * by the engines' step builders as they go: the GPUs start at once.  NKB200_EAGER_COUNT=1 counts first. */
+        if (nk_env_on("NKB200_EAGER_COUNT"))
+        {
+            if (!c->lif.cum && flo != SIZE_MAX)
+                nk_lineidx_build_range(&c->lif, &c->ff, c->threads, flo, fhi + nk_range_slack);
+            if (paired && !c->lir.cum && rlo != SIZE_MAX)
+                nk_lineidx_build_range(&c->lir, &c->rf, c->threads, rlo, rhi + nk_range_slack);
+        }
     }
     for (int i = 0; i < c->n_local && !rc; i++)
     {
@@ -2877,18 +2959,43 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
         p->commit_fp = p->raw_fp = p->cur.fp;
         p->commit_rp = p->raw_rp = p->cur.rp;
         p->raw_total = p->raw_next = 0;
-        if (c->raw_mode && c->lif.cum && (!paired || c->lir.cum))
+        p->raw_known = 1;
+        p->lf = p->lr = NULL;
+        memset(&p->own_f, 0, sizeof p->own_f);
+        memset(&p->own_r, 0, sizeof p->own_r);
+        if (c->raw_mode && p->cur.fp < p->cur.fe && (!paired || p->cur.rp < p->cur.re))
         {
-            p->line_f = nk_lineidx_before(&c->lif, p->cur.fp);
-            uint64_t n = nk_raw_records_in(&c->lif, p->cur.fp, p->cur.fe, per, p->line_f);
-            if (paired)
+            int own = 0;
+            for (int m = 0; m < (paired ? 2 : 1); m++)
             {
-                p->line_r = nk_lineidx_before(&c->lir, p->cur.rp);
-                uint64_t nr = nk_raw_records_in(&c->lir, p->cur.rp, p->cur.re, per, p->line_r);
-                n = nr < n ? nr : n;
+                nk_lineidx *whole = m ? &c->lir : &c->lif, *mine = m ? &p->own_r : &p->own_f;
+                size_t at = m ? p->cur.rp : p->cur.fp;
+                if (!whole->cum)
+                { /* the partition's own index: the chunk of its first byte for now */
+                    nk_lineidx_open(mine, m ? &c->rf : &c->ff, at);
+                    nk_lineidx_extend(mine, 1, at + 1);
+                    own = 1;
+                }
+                *(m ? &p->lr : &p->lf) = whole->cum ? whole : mine;
+                *(m ? &p->line_r : &p->line_f) = nk_lineidx_before(whole->cum ? whole : mine, at);
             }
-            p->raw_total = n;
-            raw_work |= n > 0;
+            if (own)
+            {
+                p->raw_known = 0;
+                p->raw_total = NK_RAW_PLENTY;
+                raw_work = 1;
+            }
+            else
+            {
+                uint64_t n = nk_raw_records_in(p->lf, p->cur.fp, p->cur.fe, per, p->line_f);
+                if (paired)
+                {
+                    uint64_t nr = nk_raw_records_in(p->lr, p->cur.rp, p->cur.re, per, p->line_r);
+                    n = nr < n ? nr : n;
+                }
+                p->raw_total = n;
+                raw_work |= n > 0;
+            }
         }
         p->t_start = nk_now();
         p->last_processed = p->processed;
@@ -2959,6 +3066,11 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     nk_trace(-1, -1, "pipelines", t0, nk_now());
     nk_lineidx_free(&c->lif);
     nk_lineidx_free(&c->lir);
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nk_lineidx_free(&c->part[i].own_f);
+        nk_lineidx_free(&c->part[i].own_r);
+    }
     /* reporting totals are sums of the partitions' cumulative counters, C:1897-1909 */
     uint64_t pr = 0, pt = 0, sk = 0, mu = 0;
     for (int i = 0; i < c->n_local; i++)

@@ -1,0 +1,122 @@
+"""Partition ranges that come without a count of the files (files of equal size are split by size, C:1807-1813; -p 1,
+C:1796-1803) are counted by the engines' step builders as they go, a step ahead of the device, instead of before
+the pipelines start.  The files here span many 256-KB index chunks and the steps are small, so that a partition's
+index is extended many times, becomes exact near the end of its range, and hands over to the host parser where the
+text is not regular.  Files and counters equal the oracle's whatever the route."""
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from nomalise_kmers_multi_large_b200 import capi
+from tests import cli_cases as cc
+from tests import oracle_lib as ol
+
+ROOT = Path(__file__).resolve().parent.parent
+EMU_CLI = ROOT / "tests" / "emu" / "nk_emu_cli"
+STEPS_RE = re.compile(r"B200: (\d+) device steps on raw record text, (\d+) on host-parsed records")
+N_PAIRS = 9000
+
+
+@pytest.fixture(scope="module")
+def inputs(tmp_path_factory):
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "emu")], check=True, capture_output=True)
+    ol.build_oracle()
+    tmp = tmp_path_factory.mktemp("lazy")
+    f, r = cc.synth(tmp, "s", N_PAIRS, seed=77, read_len=100, equal=True)
+    bf, br = f.read_bytes(), r.read_bytes()
+    assert len(bf) == len(br) and len(bf) > 6 * (256 << 10)
+    files = {"regular": (f, r)}
+
+    def put(name, a, b, ext="fastq"):
+        assert len(a) == len(b)
+        pa, pb = tmp / f"{name}_1.{ext}", tmp / f"{name}_2.{ext}"
+        pa.write_bytes(a)
+        pb.write_bytes(b)
+        files[name] = (pa, pb)
+
+    put("no_trailing_newline", bf[:-1], br[:-1])
+    lines = br.split(b"\n")
+    q = 4 * 5200 + 3
+    lines[q] = lines[q][:10] + b"\0" + lines[q][11:]            # NUL in a quality line of the second partition
+    put("nul_in_quality", bf, b"\n".join(lines))
+    # a sequence line of 1024+ chars in both files, sizes still equal: read_line cuts it (C:397) and what is left of it
+    # becomes the next line of the record frame
+    lf, lr = bf.split(b"\n"), br.split(b"\n")
+    for ls in (lf, lr):
+        ls[4 * 4000 + 1] = ls[4 * 4000 + 1] * 12
+        ls[4 * 4000 + 3] = ls[4 * 4000 + 3] * 12
+    put("long_sequence_line", b"\n".join(lf), b"\n".join(lr))
+    fa_f, fa_r = cc.synth(tmp, "fa", N_PAIRS, seed=78, read_len=100, equal=True, fasta=True)
+    files["fasta"] = (fa_f, fa_r)
+    return tmp, files
+
+
+# name, extra arguments, expect host-parsed steps as well
+CASES = [
+    ("regular", ["-p", 3], False),
+    ("regular", ["-p", 1], False),
+    ("regular", ["-p", 4, "-c", "-o", "fa"], False),
+    ("no_trailing_newline", ["-p", 1], True),     # (split by size, the last bytes of a file belong to no partition)
+    ("nul_in_quality", ["-p", 3], True),
+    ("long_sequence_line", ["-p", 3], None),
+    ("fasta", ["-p", 2, "-t", "fa", "-o", "fa"], False),
+]
+
+
+def run(binary, inputs, name, extra, mixed, tag, env):
+    tmp, files = inputs
+    f, r = files[name]
+    depth = max(6, 2 * extra[extra.index("-p") + 1])    # the reference insists on depth >= 2 x partitions
+    args = ["-f", f, "-r", r, "-k", 21, "-d", depth, "-m", 1] + extra
+    tag = f"{name}_{'_'.join(str(x) for x in extra)}_{tag}".replace("-", "")
+    want = cc.run_cli(ol.ORACLE_CLI, args, tmp / tag / "oracle")
+    got = cc.run_cli(binary, args + ["-e"], tmp / tag / "got", env=env)
+    if want["rc"] != 0:
+        # exit status and a message are the contract after a fatal exit (a seed record with a line of 1024+ chars is
+        # refused with a message of its own)
+        assert got["rc"] == want["rc"] and "FATAL" in want["stderr"]
+        assert "FATAL" in got["stderr"] or "sequence line of" in got["stderr"]
+        return None
+    cc.assert_same(got, want, name)
+    m = STEPS_RE.search(got["stdout"])
+    assert m, got["stdout"][-400:]
+    raw_steps, parsed_steps = int(m.group(1)), int(m.group(2))
+    if mixed is not None:
+        assert raw_steps > 0 and (parsed_steps > 0) == mixed, (raw_steps, parsed_steps)
+    return got
+
+
+@pytest.mark.parametrize("name,extra,mixed", CASES, ids=[f"{c[0]}{i}" for i, c in enumerate(CASES)])
+def test_ranges_counted_step_by_step_emu(inputs, name, extra, mixed):
+    run(EMU_CLI, inputs, name, extra, mixed, "emu", {"NKB200_STEP_PAIRS": "256"})
+
+
+def test_counting_first_gives_the_same_emu(inputs):
+    a = run(EMU_CLI, inputs, "regular", ["-p", 3, "-c"], False, "lazy", {"NKB200_STEP_PAIRS": "256"})
+    b = run(EMU_CLI, inputs, "regular", ["-p", 3, "-c"], False, "eager", {"NKB200_STEP_PAIRS": "256", "NKB200_EAGER_COUNT": "1"})
+    cc.assert_same(a, b, "step-by-step vs up-front count")
+    assert STEPS_RE.search(a["stdout"]).groups() == STEPS_RE.search(b["stdout"]).groups()
+
+
+def test_single_end_split_by_size_emu(inputs):
+    """pure single-end at -p > 1 is an uninitialised FILE* in the reference (oracle header D4): oracle only"""
+    tmp, files = inputs
+    f, _ = files["regular"]
+    args = ["-f", f, "-s", "-k", 21, "-d", 6, "-m", 1, "-p", 3]
+    want = cc.run_cli(ol.ORACLE_CLI, args, tmp / "single" / "oracle")
+    got = cc.run_cli(EMU_CLI, args + ["-e"], tmp / "single" / "got", env={"NKB200_STEP_PAIRS": "256"})
+    cc.assert_same(got, want, "single-end")
+    assert int(STEPS_RE.search(got["stdout"]).group(1)) > 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra,mixed", CASES, ids=[f"{c[0]}{i}" for i, c in enumerate(CASES)])
+def test_ranges_counted_step_by_step_gpu(inputs, name, extra, mixed):
+    run(capi.CLI_PATH, inputs, name, extra, mixed, "gpu", {"NKB200_STEP_PAIRS": "256"})
+
+
+@pytest.mark.gpu
+def test_ranges_counted_step_by_step_default_steps_gpu(inputs):
+    run(capi.CLI_PATH, inputs, "regular", ["-p", 8, "-c"], False, "gpu_default", {})
