@@ -170,7 +170,8 @@ typedef struct
 } nkd_raw_result;
 /* Optional: start copying the NEXT step's buffer to the device while the current step runs (its own stream, a
  * second device buffer); nkd_stage_raw of that very buffer then finds the bytes in place.  The buffer must stay
- * untouched until that step's nkd_stage_raw has returned. */
+ * untouched until that step's nkd_stage_raw has returned.  nkd_seed_raw takes a piece sent ahead the same way.
+ * raw = NULL forgets what was sent ahead (before the host buffer is reused for other text of the same size). */
 int nkd_upload_raw(nkd_engine *e, const uint8_t *raw, size_t raw_bytes);
 /* returns NK_EIRREGULAR (and stages nothing) when the text needs the byte-exact host parser */
 int nkd_stage_raw(nkd_engine *e, const uint8_t *raw, size_t raw_bytes, const nkd_raw_segment *segs, int n_segs,

@@ -1456,11 +1456,12 @@ typedef struct
 {
     nk_ctx *c;
     const uint8_t *raw;
-    size_t text_bytes;
+    size_t text_bytes, pos; /* the piece: data[pos, pos + text_bytes) */
     uint32_t n_records, limit;
     uint32_t taken[64];
     int64_t inv[64];
     int rc[64];
+    pthread_t th;
 } nk_seedraw_job;
 
 static void nk_seedraw_task(int d, void *a)
@@ -1476,13 +1477,28 @@ static void nk_seedraw_task(int d, void *a)
                             &j->inv[d]);
 }
 
+static void *nk_seedraw_thread(void *a)
+{
+    nk_seedraw_job *j = a;
+    nk_parallel_for(j->c->n_dev, j->c->n_dev, nk_seedraw_task, j);
+    return NULL;
+}
+
+static void nk_seedraw_forget(nk_ctx *c)
+{
+    for (int d = 0; d < c->n_dev; d++)
+        if (c->dev[d].lead == d)
+            nkd_upload_raw(c->dev[d].eng, NULL, 0);
+}
+
 /* returns NK_OK with *consumed = bytes of the file that were dealt with and *seeded = records taken; stops early
- * (without error) at text the device declines, which the caller gives to the host parser */
+ * (without error) at text the device declines, which the caller gives to the host parser.
+ * Two step buffers take turns: while the GPUs insert one piece, the host counts and copies the next one and sends it
+ * ahead on the upload stream (nkd_upload_raw), so the pieces reach the table in order without the device waiting. */
 static int nk_seed_buffer_raw(nk_ctx *c, const char *data, size_t size, int records_to_seed, size_t *consumed, int *seeded)
 {
     const int per = c->cfg.in_fastq ? 4 : 2;
     nk_buf f = {data, size};
-    nk_stepbuf *sb = &c->dev[0].sb[0]; /* free until processing starts */
     size_t cap = (size_t)c->dev[0].n_parts * 2u * ((size_t)c->raw_part_bytes + 16u);
     for (int d = 0; d < c->n_dev; d++)
     { /* every lead engine takes the same pieces: the smallest step buffer decides their size */
@@ -1491,78 +1507,123 @@ static int nk_seed_buffer_raw(nk_ctx *c, const char *data, size_t size, int reco
             cap = cd;
     }
     uint32_t max_records = (uint32_t)c->seed_cap_reads;
-    size_t pos = 0;
+    size_t pos = 0; /* where the next piece starts */
     *consumed = 0;
     *seeded = 0;
     if (c->n_dev > 64)
         return NK_OK;
-    while (*seeded < records_to_seed && pos < size)
+    const int ahead = !nk_env_on("NKB200_NO_PREFETCH");
+    nk_seedraw_job jobs[2], *inflight = NULL;
+    memset(jobs, 0, sizeof jobs);
+    int rc = NK_OK, slot = 0, exhausted = 0;
+    for (;;)
     {
-        /* a piece: as many whole records as fit the buffer, the read limit and the operation limit (a sequence line
-         * holds at most as many k-mers as it has bytes; FASTQ spends half of a record's bytes on it) */
-        size_t want_bytes = cap - 64;
-        size_t ops_bytes = c->cfg.in_fastq ? c->seed_cap_ops * 2 : c->seed_cap_ops;
-        if (ops_bytes < want_bytes)
-            want_bytes = ops_bytes;
-        size_t hi = pos + want_bytes < size ? pos + want_bytes : size;
-        nk_lineidx li = {0};
-        nk_lineidx_build_range(&li, &f, c->threads, pos, hi);
-        uint64_t before = nk_lineidx_before(&li, pos), upto = nk_lineidx_before(&li, hi);
-        uint64_t recs = (upto - before) / (uint64_t)per;
-        if (recs > max_records)
-            recs = max_records;
-        uint64_t need = (uint64_t)(records_to_seed - *seeded);
-        if (recs > need + need / 8 + 4096)
-            recs = need + need / 8 + 4096; /* a few more than needed: some may be too short to count */
-        size_t end = recs ? nk_lineidx_find(&li, before + recs * (uint64_t)per - 1) : SIZE_MAX;
-        nk_lineidx_free(&li);
-        if (!recs || end == SIZE_MAX)
-            break; /* no whole record left (the tail goes to the host parser, which knows what to do with it) */
-        end += 1;
-        size_t n = end - pos, n16 = (n + 15) & ~(size_t)15;
-        int n_copies = 0;
-        for (size_t o = 0; o < n; o += NK_COPY_PIECE)
+        /* 1. the next piece, into the buffer the piece in flight does not use.  How many records are still wanted is
+         * known only when that piece is done: prepare on the assumption that all of its records count, and nothing
+         * at all if that would already be enough. */
+        int64_t need = (int64_t)records_to_seed - *seeded - (inflight ? (int64_t)inflight->n_records : 0);
+        nk_seedraw_job *next = NULL;
+        if (need > 0 && pos < size && !exhausted)
         {
-            nk_copy *cp = &sb->copies[n_copies++];
-            cp->dst = sb->raw + o;
-            cp->src = data + pos + o;
-            cp->n = n - o < NK_COPY_PIECE ? n - o : NK_COPY_PIECE;
+            nk_stepbuf *sb = &c->dev[0].sb[slot]; /* free until processing starts */
+            /* as many whole records as fit the buffer, the read limit and the operation limit (a sequence line holds
+             * at most as many k-mers as it has bytes; FASTQ spends half of a record's bytes on it) */
+            size_t want_bytes = cap - 64;
+            size_t ops_bytes = c->cfg.in_fastq ? c->seed_cap_ops * 2 : c->seed_cap_ops;
+            if (ops_bytes < want_bytes)
+                want_bytes = ops_bytes;
+            size_t hi = pos + want_bytes < size ? pos + want_bytes : size;
+            nk_lineidx li = {0};
+            nk_lineidx_build_range(&li, &f, c->threads, pos, hi);
+            uint64_t before = nk_lineidx_before(&li, pos), upto = nk_lineidx_before(&li, hi);
+            uint64_t recs = (upto - before) / (uint64_t)per;
+            if (recs > max_records)
+                recs = max_records;
+            if (recs > (uint64_t)need + (uint64_t)need / 8 + 4096)
+                recs = (uint64_t)need + (uint64_t)need / 8 + 4096; /* a few more than needed: some may be too short to count */
+            size_t end = recs ? nk_lineidx_find(&li, before + recs * (uint64_t)per - 1) : SIZE_MAX;
+            nk_lineidx_free(&li);
+            if (!recs || end == SIZE_MAX)
+                exhausted = 1; /* no whole record left (the tail goes to the host parser, which knows what to do with it) */
+            else
+            {
+                end += 1;
+                size_t n = end - pos, n16 = (n + 15) & ~(size_t)15;
+                int n_copies = 0;
+                for (size_t o = 0; o < n; o += NK_COPY_PIECE)
+                {
+                    nk_copy *cp = &sb->copies[n_copies++];
+                    cp->dst = sb->raw + o;
+                    cp->src = data + pos + o;
+                    cp->n = n - o < NK_COPY_PIECE ? n - o : NK_COPY_PIECE;
+                }
+                nk_parallel_for(n_copies, c->threads, nk_copy_task, sb->copies);
+                memset(sb->raw + n, ' ', n16 - n);
+                next = &jobs[slot];
+                next->c = c;
+                next->raw = sb->raw;
+                next->text_bytes = n;
+                next->pos = pos;
+                next->n_records = (uint32_t)recs;
+                if (ahead) /* travels while the piece in flight is being inserted */
+                    for (int d = 0; d < c->n_dev; d++)
+                        if (c->dev[d].lead == d)
+                            nkd_upload_raw(c->dev[d].eng, sb->raw, n16);
+            }
         }
-        nk_parallel_for(n_copies, c->threads, nk_copy_task, sb->copies);
-        memset(sb->raw + n, ' ', n16 - n);
-        nk_seedraw_job job;
-        job.c = c;
-        job.raw = sb->raw;
-        job.text_bytes = n;
-        job.n_records = (uint32_t)recs;
-        job.limit = (uint32_t)need;
-        nk_parallel_for(c->n_dev, c->n_dev, nk_seedraw_task, &job);
-        int declined = 0;
-        for (int d = 0; d < c->n_dev; d++)
+        /* 2. the piece in flight: its outcome decides whether the prepared one is wanted */
+        if (inflight)
         {
-            if (job.rc[d] == NK_EIRREGULAR)
-                declined = 1;
-            else if (job.rc[d])
-                return nk_fail(c, job.rc[d], "%s", nkd_last_error(c->dev[d].eng));
+            nk_seedraw_job *j = inflight;
+            pthread_join(j->th, NULL);
+            inflight = NULL;
+            int declined = 0;
+            for (int d = 0; d < c->n_dev; d++)
+            {
+                if (j->rc[d] == NK_EIRREGULAR)
+                    declined = 1;
+                else if (j->rc[d] && !rc)
+                    rc = nk_fail(c, j->rc[d], "%s", nkd_last_error(c->dev[d].eng));
+            }
+            if (rc || declined)
+                break; /* declined: nothing of that piece was inserted, the host parser continues at its start */
+            if (j->inv[0] >= 0)
+            { /* is_valid_sequence_single's abort, C:1416-1420: the text of record inv's sequence line */
+                const char *t = data + j->pos;
+                size_t n = j->text_bytes;
+                size_t q = j->inv[0] ? nk_kth_newline(t, n, (uint64_t)per * (uint64_t)j->inv[0]) + 1 : 0;
+                q += nk_kth_newline(t + q, n - q, 1) + 1;
+                size_t len = nk_kth_newline(t + q, n - q, 1);
+                char *txt = malloc(len + 1);
+                nk_scrub_copy(txt, t + q, len);
+                rc = nk_fail(c, NK_EDATA, "FATAL: FWD sequence does not appear to be a DNA sequence\n%s\n", txt);
+                free(txt);
+                break;
+            }
+            *seeded += (int)j->taken[0];
+            *consumed = j->pos + j->text_bytes;
+            if (*seeded >= records_to_seed)
+                break;
+            if (!next && !exhausted && pos < size)
+                continue; /* nothing was prepared because that piece might have sufficed; it did not */
         }
-        if (declined)
-            break; /* nothing of this piece was inserted: the host parser continues at `pos` */
-        if (job.inv[0] >= 0)
-        { /* is_valid_sequence_single's abort, C:1416-1420: the text of record inv's sequence line */
-            size_t q = job.inv[0] ? nk_kth_newline(data + pos, n, (uint64_t)per * (uint64_t)job.inv[0]) + 1 : 0;
-            q += nk_kth_newline(data + pos + q, n - q, 1) + 1;
-            size_t len = nk_kth_newline(data + pos + q, n - q, 1);
-            char *txt = malloc(len + 1);
-            nk_scrub_copy(txt, data + pos + q, len);
-            nk_fail(c, NK_EDATA, "FATAL: FWD sequence does not appear to be a DNA sequence\n%s\n", txt);
-            free(txt);
-            return NK_EDATA;
+        if (!next)
+            break;
+        /* 3. hand the prepared piece to the GPUs */
+        next->limit = (uint32_t)(records_to_seed - *seeded);
+        if (pthread_create(&next->th, NULL, nk_seedraw_thread, next) != 0)
+        {
+            rc = nk_fail(c, NK_EINTERNAL, "cannot start the seeding thread");
+            break;
         }
-        *seeded += (int)job.taken[0];
-        pos = end;
-        *consumed = pos;
+        inflight = next;
+        slot ^= 1;
+        pos = next->pos + next->text_bytes;
     }
-    return NK_OK;
+    if (inflight)
+        pthread_join(inflight->th, NULL);
+    nk_seedraw_forget(c);
+    return rc;
 }
 
 int nk_seed_buffer(nk_ctx *c, const char *data, size_t size, int records_to_seed)

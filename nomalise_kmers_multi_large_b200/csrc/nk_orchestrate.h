@@ -13,6 +13,7 @@
 #define NK_ORCHESTRATE_H
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -118,6 +119,7 @@ class NkEngine
     unsigned char *d_raw_next = nullptr; /* second text buffer: the next step's bytes arrive while this one runs */
     const uint8_t *uploaded = nullptr;   /* host buffer whose bytes d_raw_next holds (or is receiving) */
     size_t uploaded_bytes = 0;
+    std::atomic<bool> raw_ready{false};  /* raw_prepare has run */
     std::mutex up_mu; /* nkd_upload_raw may come from another host thread than the one that runs the steps */
     unsigned *d_tile = nullptr, *d_nlpos = nullptr, *d_nops = nullptr, *d_opscan = nullptr, *d_tout = nullptr;
     unsigned *d_rflags = nullptr, *d_outlen = nullptr, *d_outoff = nullptr;
@@ -889,8 +891,10 @@ class NkEngine
     /* scratch of the raw path, allocated on first use: a context that only ever stages parsed reads does not pay */
     int raw_prepare()
     {
-        if (d_raw)
+        if (raw_ready.load(std::memory_order_acquire)) /* nkd_upload_raw asks from another thread than the steps' */
             return NK_OK;
+        if (d_raw)
+            return fail(NK_ENOMEM, "nkd_stage_raw: cannot allocate the raw-text scratch");
         if (!cfg.max_raw_bytes)
             return fail(NK_EINVAL, "nkd_stage_raw: the engine was created with max_raw_bytes = 0");
         raw_cap = (cfg.max_raw_bytes + 15) & ~15ull;
@@ -914,11 +918,18 @@ class NkEngine
         ok &= dalloc(d_wins, NK_MAX_PARTITIONS);
         if (!ok || !be.prepare_scan((size_t)std::max<uint64_t>(raw_reads_cap + 1, raw_cap / NK_RAW_TILE + 4), err))
             return fail(NK_ENOMEM, "nkd_stage_raw: cannot allocate the raw-text scratch");
+        raw_ready.store(true, std::memory_order_release);
         return NK_OK;
     }
 
     int upload_raw(const uint8_t *host_raw, size_t raw_bytes)
     {
+        if (!host_raw)
+        { /* forget what was sent ahead: the buffer it came from is about to be reused for something else */
+            std::lock_guard<std::mutex> lock(up_mu);
+            uploaded = nullptr;
+            return NK_OK;
+        }
         int rc = raw_prepare();
         if (rc)
             return rc;
@@ -1097,8 +1108,22 @@ class NkEngine
         h_wins.assign(1, NkRawWin{});
         h_wins[0].f_bytes = (unsigned)text_bytes;
         h_wins[0].n_records = n_records;
-        be.h2d(d_raw, host_raw, bytes16);
-        h2d_bytes += bytes16;
+        bool prefetched;
+        {
+            std::lock_guard<std::mutex> lock(up_mu);
+            prefetched = uploaded == host_raw && uploaded_bytes == bytes16;
+            uploaded = nullptr;
+            if (prefetched)
+            { /* the piece was sent ahead while the previous one was being inserted (nkd_upload_raw) */
+                std::swap(d_raw, d_raw_next);
+                be.upload_fence();
+            }
+        }
+        if (!prefetched)
+        {
+            be.h2d(d_raw, host_raw, bytes16);
+            h2d_bytes += bytes16;
+        }
         be.put_small(d_wins, h_wins.data(), sizeof(NkRawWin));
         be.zero(d_rflags, 4 * sizeof(unsigned));
         be.zero(d_nlpos, (size_t)(lines + 1) * sizeof(unsigned));
