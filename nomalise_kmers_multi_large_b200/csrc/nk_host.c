@@ -3034,12 +3034,19 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
                 if (!whole->cum)
                 { /* the partition's own index: the chunk of its first byte for now */
                     nk_lineidx_open(mine, m ? &c->rf : &c->ff, at);
+                    if (!mine->cum)
+                    {
+                        rc = nk_fail(c, NK_ENOMEM, "Memory allocation failed (line index)");
+                        break;
+                    }
                     nk_lineidx_extend(mine, 1, at + 1);
                     own = 1;
                 }
                 *(m ? &p->lr : &p->lf) = whole->cum ? whole : mine;
                 *(m ? &p->line_r : &p->line_f) = nk_lineidx_before(whole->cum ? whole : mine, at);
             }
+            if (rc)
+                break;
             if (own)
             {
                 p->raw_known = 0;
