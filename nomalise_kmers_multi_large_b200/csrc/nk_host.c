@@ -569,8 +569,12 @@ static void nk_lineidx_extend(nk_lineidx *li, int threads, size_t byte_hi)
     nk_parallel_for(hi - li->c_hi, threads, nk_lineidx_task, &sp);
     for (int i = li->c_hi; i < hi; i++)
         li->cum[i + 1] += li->cum[i];
-    li->c_hi = hi;
+    /* published last: another thread may look things up in the part that is already counted while this one goes on
+     * (the reverse file's index while the first partitions are being worked on, nk_roll_thread) */
+    __atomic_store_n(&li->c_hi, hi, __ATOMIC_RELEASE);
 }
+
+static inline int nk_lineidx_hi(const nk_lineidx *li) { return __atomic_load_n(&li->c_hi, __ATOMIC_ACQUIRE); }
 
 /* counts of the chunks that overlap [byte_lo, byte_hi) */
 static void nk_lineidx_build_range(nk_lineidx *li, const nk_buf *f, int threads, size_t byte_lo, size_t byte_hi)
@@ -600,14 +604,15 @@ static void nk_lineidx_free(nk_lineidx *li)
     li->cum = NULL;
 }
 
-static uint64_t nk_lineidx_total(const nk_lineidx *li) { return li->cum ? li->cum[li->c_hi] : 0; }
+static uint64_t nk_lineidx_total(const nk_lineidx *li) { return li->cum ? li->cum[nk_lineidx_hi(li)] : 0; }
 
 /* offset of the newline with index g (0-based, counted from the first counted chunk), or SIZE_MAX */
 static size_t nk_lineidx_find(const nk_lineidx *li, uint64_t g)
 {
-    if (li->c_hi == li->c_lo || g >= li->cum[li->c_hi])
+    const int c_hi = nk_lineidx_hi(li);
+    if (c_hi == li->c_lo || g >= li->cum[c_hi])
         return SIZE_MAX;
-    int lo = li->c_lo, hi = li->c_hi - 1; /* last chunk whose cum <= g */
+    int lo = li->c_lo, hi = c_hi - 1; /* last chunk whose cum <= g */
     while (lo < hi)
     {
         int mid = (lo + hi + 1) / 2;
@@ -625,15 +630,16 @@ static size_t nk_lineidx_find(const nk_lineidx *li, uint64_t g)
 /* newlines in [first counted chunk, pos) */
 static uint64_t nk_lineidx_before(const nk_lineidx *li, size_t pos)
 {
-    if (li->c_hi == li->c_lo)
+    const int c_hi = nk_lineidx_hi(li);
+    if (c_hi == li->c_lo)
         return 0;
     if (pos > li->f->size)
         pos = li->f->size;
     int c = (int)(pos / NK_LI_CHUNK);
     if (c < li->c_lo)
         return 0;
-    if (c >= li->c_hi)
-        return li->cum[li->c_hi];
+    if (c >= c_hi)
+        return li->cum[c_hi];
     return li->cum[c] + nk_count_newlines(li->f->data + (size_t)c * NK_LI_CHUNK, pos - (size_t)c * NK_LI_CHUNK);
 }
 
@@ -810,6 +816,7 @@ typedef struct
     nk_lineidx *lf, *lr;
     nk_lineidx own_f, own_r;
     int raw_known;
+    int ready; /* its byte ranges are known (under nk_ctx.roll_mu while the reverse file is still being counted) */
     int active; /* part of the wave that is being processed (all partitions, unless the tables do not fit the GPU) */
 } nk_part;
 
@@ -851,6 +858,12 @@ struct nk_ctx
     int raw_mode;     /* steps go to the device as raw record text (default); NKB200_HOST_PARSE=1 parses on the host */
     uint32_t raw_part_bytes; /* raw text per partition, mate and step */
     nk_lineidx lif, lir;     /* line indexes of the files being processed */
+    /* the reverse file is counted while the first partitions are already being worked on (nk_roll_thread) */
+    int rolling;
+    uint64_t count_route[3]; /* inputs whose line ends were counted up front / alongside the first steps / by the step builders */
+    pthread_t roll_th;
+    pthread_mutex_t roll_mu;
+    pthread_cond_t roll_cv;
     uint64_t raw_steps, parsed_steps;
     uint64_t seed_raw_records, seed_parsed_records; /* seed records taken from raw text on the device / parsed here */
     uint64_t waves; /* passes over disjoint sets of partitions in nk_process_* so far (1 per file when all tables fit) */
@@ -2349,10 +2362,36 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
     /* the step's room (records, bytes, operations) is shared by the partitions that still have records: when only a
      * wave of them is being worked on, or most have run dry, each takes a larger share and the launches stay large */
     int busy = 0;
+    char ready[NK_MAX_PARTITIONS];
+    memset(ready, 1, sizeof ready);
+    if (c->rolling)
+    { /* partitions whose reverse range is still being located (nk_roll_thread) join the steps as they are released;
+       * with nothing else to do, wait for the next one */
+        pthread_mutex_lock(&c->roll_mu);
+        for (;;)
+        {
+            int work = 0, pending = 0;
+            for (int li = 0; li < dv->n_parts && li < NK_MAX_PARTITIONS; li++)
+            {
+                nk_part *p = &c->part[dv->parts[li]];
+                ready[li] = (char)p->ready;
+                if (!p->active)
+                    continue;
+                if (!p->ready)
+                    pending = 1;
+                else if (p->raw_total > p->raw_next)
+                    work = 1;
+            }
+            if (work || !pending)
+                break;
+            pthread_cond_wait(&c->roll_cv, &c->roll_mu);
+        }
+        pthread_mutex_unlock(&c->roll_mu);
+    }
     for (int li = 0; li < dv->n_parts; li++)
     {
         nk_part *p = &c->part[dv->parts[li]];
-        busy += p->active && p->raw_total > p->raw_next;
+        busy += ready[li] && p->active && p->raw_total > p->raw_next;
     }
     uint64_t share = busy ? (uint64_t)dv->n_parts / (uint64_t)busy : 1;
     if (share * c->step_pairs > 262144)
@@ -2365,10 +2404,10 @@ static size_t nk_build_step_raw(nk_ctx *c, nk_dev *dv, nk_stepbuf *sb, int threa
         nk_pstep *ps = &sb->ps[li];
         ps->raw_n = 0;
         ps->fatal_record = -1;
-        uint64_t left = p->active && p->raw_total > p->raw_next ? nk_part_reach(c, p, threads, byte_room) : 0;
+        uint64_t left = ready[li] && p->active && p->raw_total > p->raw_next ? nk_part_reach(c, p, threads, byte_room) : 0;
         if (!left)
         {
-            if (p->active && !p->raw_known)
+            if (ready[li] && p->active && !p->raw_known)
                 p->raw_total = p->raw_next; /* not one whole record within reach: not regular text */
             continue;
         }
@@ -2829,8 +2868,11 @@ static void *nk_device_pipeline(void *a)
 /* lf / lr: line indexes of the whole files.  Already built ones (cum != NULL) are used; if the record-count
  * partitioner needs them they are built here and left to the caller, who frees them. */
 static int nk_plan(const nk_buf *ff, const nk_buf *rf, int paired, int P, int fastq, int threads, uint64_t *fs,
-                   uint64_t *fe, uint64_t *rs, uint64_t *re, nk_diag *d, nk_lineidx *lf, nk_lineidx *lr)
+                   uint64_t *fe, uint64_t *rs, uint64_t *re, nk_diag *d, nk_lineidx *lf, nk_lineidx *lr, int *defer_rev)
 {
+    const int may_defer = defer_rev && *defer_rev;
+    if (defer_rev)
+        *defer_rev = 0;
     if (!nk_mask64)
         nk_mask64 = nk_mask64_pick();
     memset(fs, 0, sizeof(uint64_t) * (size_t)P);
@@ -2854,10 +2896,15 @@ static int nk_plan(const nk_buf *ff, const nk_buf *rf, int paired, int P, int fa
     { /* C:1815-1828: the forward file's record count is applied to both files */
         if (!lf->cum)
             nk_lineidx_build_n(lf, ff, threads);
-        if (!lr->cum)
-            nk_lineidx_build_n(lr, rf, threads);
         uint64_t recs = nk_records_from_lines(ff, nk_lineidx_total(lf), fastq);
         nk_ranges_by_records(lf, P, fastq, recs, fs, fe);
+        if (may_defer && !lr->cum)
+        { /* the caller counts the reverse file and places its boundaries as it goes (nk_roll_thread) */
+            *defer_rev = 1;
+            return NK_OK;
+        }
+        if (!lr->cum)
+            nk_lineidx_build_n(lr, rf, threads);
         nk_ranges_by_records(lr, P, fastq, recs, rs, re);
     }
     return NK_OK;
@@ -2873,12 +2920,97 @@ int nk_plan_ranges(const char *fwd, size_t fwd_size, const char *rev, size_t rev
     nk_diag d = {{0}, 0};
     nk_lineidx lf = {0}, lr = {0};
     int rc = nk_plan(&ff, &rf, rev != NULL, partitions, fastq, threads > 0 ? threads : nk_host_threads(), fwd_starts,
-                     fwd_ends, rev_starts, rev_ends, &d, &lf, &lr);
+                     fwd_ends, rev_starts, rev_ends, &d, &lf, &lr, NULL);
     nk_lineidx_free(&lf);
     nk_lineidx_free(&lr);
     if (rc && errbuf && errbuf_size)
         snprintf(errbuf, errbuf_size, "%s", d.msg);
     return rc;
+}
+
+/* ---- the reverse file counted while the first partitions are being worked on
+ *
+ * calculate_thread_positions_from_records (C:1265-1300) places partition t+1 of a file behind the `want`-th line end
+ * counted from partition t's start, with `want` taken from the FORWARD file's record count (C:1815-1828): the forward
+ * file must be counted to its end before any boundary is known, the reverse file need not be.  This thread counts it
+ * front to back on the pool, places one boundary after the other exactly as nk_ranges_by_records would on a complete
+ * index (a longer index gives the same answer for the same line), and releases each partition to its engine's step
+ * builder as soon as its range is covered. */
+#ifndef NK_ROLL_CHUNKS
+#define NK_ROLL_CHUNKS 256 /* index chunks counted per round (64 MB); the emulation build of the tests uses a few */
+#endif
+
+static void nk_roll_release(nk_ctx *c, int gid)
+{
+    const int per = c->cfg.in_fastq ? 4 : 2;
+    for (int i = 0; i < c->n_local; i++)
+    {
+        nk_part *p = &c->part[i];
+        if (p->gid != gid)
+            continue;
+        p->cur.rp = c->rs[gid];
+        p->cur.re = c->re[gid];
+        p->commit_rp = p->raw_rp = p->cur.rp;
+        uint64_t n = 0;
+        if (p->cur.fp < p->cur.fe && p->cur.rp < p->cur.re)
+        {
+            p->line_r = nk_lineidx_before(&c->lir, p->cur.rp);
+            n = nk_raw_records_in(p->lf, p->cur.fp, p->cur.fe, per, p->line_f);
+            uint64_t nr = nk_raw_records_in(&c->lir, p->cur.rp, p->cur.re, per, p->line_r);
+            n = nr < n ? nr : n;
+        }
+        pthread_mutex_lock(&c->roll_mu);
+        p->raw_total = n;
+        p->ready = 1;
+        pthread_cond_broadcast(&c->roll_cv);
+        pthread_mutex_unlock(&c->roll_mu);
+    }
+}
+
+static void *nk_roll_thread(void *a)
+{
+    nk_ctx *c = a;
+    double t0 = nk_now();
+    nk_lineidx *li = &c->lir;
+    const nk_buf *f = &c->rf;
+    const int P = c->cfg.partitions, fastq = c->cfg.in_fastq;
+    uint64_t recs = nk_records_from_lines(&c->ff, nk_lineidx_total(&c->lif), fastq);
+    uint64_t per = recs / (uint64_t)P;
+    uint64_t *st = c->rs, *en = c->re;
+    const size_t round = (size_t)NK_ROLL_CHUNKS * NK_LI_CHUNK;
+    if (P < 2 || per < 1 || f->size < 1)
+    { /* nk_ranges_by_records leaves every range empty */
+        for (int t = 0; t < P; t++)
+            nk_roll_release(c, t);
+        return NULL;
+    }
+    int want = (int)(fastq ? per * 4 : per * 2);
+    st[0] = 0;
+    en[P - 1] = f->size - 1;
+    for (int t = 0; t < P - 1; t++)
+    {
+        size_t pos = SIZE_MAX;
+        if (want > 0)
+        {
+            nk_lineidx_extend(li, c->threads, st[t] + 1); /* lines before st[t] (behind us, unless st[t] stayed 0) */
+            uint64_t g = nk_lineidx_before(li, st[t]) + (uint64_t)want - 1;
+            while (nk_lineidx_total(li) <= g && nk_lineidx_hi(li) < li->nchunks)
+                nk_lineidx_extend(li, c->threads, (size_t)nk_lineidx_hi(li) * NK_LI_CHUNK + round);
+            pos = nk_lineidx_find(li, g);
+        }
+        if (pos != SIZE_MAX)
+        {
+            en[t] = pos;
+            st[t + 1] = pos + 1;
+        }
+        /* the record that starts before the end of the range runs past it */
+        nk_lineidx_extend(li, c->threads, en[t] + nk_range_slack + 1);
+        nk_roll_release(c, t);
+    }
+    nk_lineidx_extend(li, c->threads, f->size);
+    nk_roll_release(c, P - 1);
+    nk_trace(-1, -1, "count_rev", t0, nk_now());
+    return NULL;
 }
 
 /* one pipeline per engine, raw-text or host-parsed steps; returns the first error */
@@ -2980,8 +3112,18 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     else
     {
         nk_diag d = {{0}, 0};
-        if (nk_plan(&c->ff, &c->rf, paired, P, fastq, c->threads, c->fs, c->fe, c->rs, c->re, &d, &c->lif, &c->lir))
+        /* raw-text steps: the reverse file's boundaries may be placed while the first partitions are worked on */
+        int defer = c->raw_mode && paired && !nk_env_on("NKB200_EAGER_COUNT");
+        if (nk_plan(&c->ff, &c->rf, paired, P, fastq, c->threads, c->fs, c->fe, c->rs, c->re, &d, &c->lif, &c->lir, &defer))
             rc = nk_fail(c, NK_EDATA, "%s", d.msg);
+        else if (defer)
+        {
+            nk_lineidx_open(&c->lir, &c->rf, 0);
+            if (!c->lir.cum)
+                rc = nk_fail(c, NK_ENOMEM, "Memory allocation failed (line index)");
+            else
+                c->rolling = 1;
+        }
     }
     int raw_work = 0;
     if (!rc && c->raw_mode)
@@ -3021,10 +3163,19 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
         p->commit_rp = p->raw_rp = p->cur.rp;
         p->raw_total = p->raw_next = 0;
         p->raw_known = 1;
+        p->ready = 1;
         p->lf = p->lr = NULL;
         memset(&p->own_f, 0, sizeof p->own_f);
         memset(&p->own_r, 0, sizeof p->own_r);
-        if (c->raw_mode && p->cur.fp < p->cur.fe && (!paired || p->cur.rp < p->cur.re))
+        if (c->rolling)
+        { /* the reverse side follows when nk_roll_thread releases the partition */
+            p->lf = &c->lif;
+            p->lr = &c->lir;
+            p->line_f = nk_lineidx_before(&c->lif, p->cur.fp);
+            p->ready = 0;
+            p->raw_total = NK_RAW_PLENTY;
+        }
+        else if (c->raw_mode && p->cur.fp < p->cur.fe && (!paired || p->cur.rp < p->cur.re))
         {
             int own = 0;
             for (int m = 0; m < (paired ? 2 : 1); m++)
@@ -3068,6 +3219,23 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
         p->t_start = nk_now();
         p->last_processed = p->processed;
     }
+    if (!rc && c->raw_mode)
+    {
+        int own = 0;
+        for (int i = 0; i < c->n_local; i++)
+            own |= !c->part[i].raw_known;
+        c->count_route[c->rolling ? 1 : own ? 2 : 0]++;
+    }
+    int roll_running = 0;
+    if (!rc && c->rolling)
+    {
+        pthread_mutex_init(&c->roll_mu, NULL);
+        pthread_cond_init(&c->roll_cv, NULL);
+        if (pthread_create(&c->roll_th, NULL, nk_roll_thread, c) == 0)
+            roll_running = 1;
+        else
+            nk_roll_thread(c); /* no thread: count here and now */
+    }
     c->tot.index_seconds += nk_now() - t0;
     nk_trace(-1, -1, "plan", t0, nk_now());
     /* Waves: an engine whose tables do not fit its share of the GPU works on `per_wave` of its partitions at a time,
@@ -3100,17 +3268,23 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     }
     for (int w = 0; w < n_waves && !rc; w++)
     {
-        raw_work = 0;
+        raw_work = roll_running; /* partitions are still being released: their record counts are not ours to read yet */
         for (int i = 0; i < c->n_local; i++)
         {
             nk_part *p = &c->part[i];
             int d = p->dev < 256 ? p->dev : 255;
             p->active = p->lidx / per_wave[d] == w;
-            raw_work |= p->active && p->raw_total > p->raw_next;
+            if (!roll_running)
+                raw_work |= p->active && p->raw_total > p->raw_next;
         }
         c->waves++;
         if (raw_work)
             rc = nk_run_pipelines(c, 1);
+        if (roll_running)
+        { /* every partition has been released by now, or the pipelines stopped early */
+            pthread_join(c->roll_th, NULL);
+            roll_running = 0;
+        }
         /* whatever the raw-text pipeline did not take -- text the device declined (NUL bytes, lines of 1024+ chars),
          * a last record cut short by the end of the file -- goes through the byte-exact host parser from where each
          * partition stands */
@@ -3132,6 +3306,14 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
             rc = nk_run_pipelines(c, 0);
     }
     nk_trace(-1, -1, "pipelines", t0, nk_now());
+    if (roll_running)
+        pthread_join(c->roll_th, NULL);
+    if (c->rolling)
+    {
+        pthread_mutex_destroy(&c->roll_mu);
+        pthread_cond_destroy(&c->roll_cv);
+        c->rolling = 0;
+    }
     nk_lineidx_free(&c->lif);
     nk_lineidx_free(&c->lir);
     for (int i = 0; i < c->n_local; i++)
@@ -3830,6 +4012,9 @@ int nk_main(int argc, char **argv)
                (unsigned long long)c->parsed_steps);
         printf("B200: %llu seed records taken from raw text on the device, %llu parsed by the host\n",
                (unsigned long long)c->seed_raw_records, (unsigned long long)c->seed_parsed_records);
+        printf("B200: line ends counted before the first step for %llu input(s), reverse file alongside the first steps for %llu, "
+               "by the step builders for %llu\n", (unsigned long long)c->count_route[0], (unsigned long long)c->count_route[1],
+               (unsigned long long)c->count_route[2]);
         uint64_t ev = 0, ld = 0;
         for (int d = 0; d < c->n_dev; d++)
         {

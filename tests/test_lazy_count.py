@@ -1,6 +1,7 @@
 """Partition ranges that come without a count of the files (files of equal size are split by size, C:1807-1813; -p 1,
 C:1796-1803) are counted by the engines' step builders as they go, a step ahead of the device, instead of before
-the pipelines start.  The files here span many 256-KB index chunks and the steps are small, so that a partition's
+the pipelines start.  Files of different size go through the record-count partitioner (C:1815-1828): the forward file is
+counted first, the reverse file while the first partitions are already being worked on.  The files here span many 256-KB index chunks and the steps are small, so that a partition's
 index is extended many times, becomes exact near the end of its range, and hands over to the host parser where the
 text is not regular.  Files and counters equal the oracle's whatever the route."""
 import re
@@ -16,6 +17,8 @@ from tests import oracle_lib as ol
 ROOT = Path(__file__).resolve().parent.parent
 EMU_CLI = ROOT / "tests" / "emu" / "nk_emu_cli"
 STEPS_RE = re.compile(r"B200: (\d+) device steps on raw record text, (\d+) on host-parsed records")
+ROUTE_RE = re.compile(r"B200: line ends counted before the first step for (\d+) input\(s\), reverse file alongside the first steps "
+                      r"for (\d+), by the step builders for (\d+)")
 N_PAIRS = 9000
 
 
@@ -50,6 +53,17 @@ def inputs(tmp_path_factory):
     put("long_sequence_line", b"\n".join(lf), b"\n".join(lr))
     fa_f, fa_r = cc.synth(tmp, "fa", N_PAIRS, seed=78, read_len=100, equal=True, fasta=True)
     files["fasta"] = (fa_f, fa_r)
+    # files of different size: the record-count partitioner (C:1815-1828) needs the forward file counted to its end, the
+    # reverse file is counted while the first partitions are worked on
+    files["unequal"] = cc.synth(tmp, "u", N_PAIRS, seed=79, read_len=100)
+    uf, ur = (x.read_bytes() for x in files["unequal"])
+    assert len(uf) != len(ur)
+    files["unequal_fewer_reverse_records"] = (files["unequal"][0], tmp / "u_short_2.fastq")
+    (tmp / "u_short_2.fastq").write_bytes(b"\n".join(ur.split(b"\n")[:4 * 7000]) + b"\n")
+    lines = ur.split(b"\n")
+    lines[4 * 6100 + 1] = lines[4 * 6100 + 1][:30] + b"\0" + lines[4 * 6100 + 1][31:]      # NUL in a late sequence line
+    files["unequal_nul"] = (files["unequal"][0], tmp / "u_nul_2.fastq")
+    (tmp / "u_nul_2.fastq").write_bytes(b"\n".join(lines))
     return tmp, files
 
 
@@ -62,6 +76,10 @@ CASES = [
     ("nul_in_quality", ["-p", 3], True),
     ("long_sequence_line", ["-p", 3], None),
     ("fasta", ["-p", 2, "-t", "fa", "-o", "fa"], False),
+    ("unequal", ["-p", 3, "-c"], False),
+    ("unequal", ["-p", 8], False),
+    ("unequal_fewer_reverse_records", ["-p", 4], False),
+    ("unequal_nul", ["-p", 4], True),
 ]
 
 
@@ -85,6 +103,11 @@ def run(binary, inputs, name, extra, mixed, tag, env):
     raw_steps, parsed_steps = int(m.group(1)), int(m.group(2))
     if mixed is not None:
         assert raw_steps > 0 and (parsed_steps > 0) == mixed, (raw_steps, parsed_steps)
+    route = tuple(int(x) for x in ROUTE_RE.search(got["stdout"]).groups())
+    if env.get("NKB200_EAGER_COUNT"):
+        assert route == (1, 0, 0), route
+    else:
+        assert route == ((0, 1, 0) if name.startswith("unequal") and extra[extra.index("-p") + 1] > 1 else (0, 0, 1)), route
     return got
 
 
@@ -93,11 +116,13 @@ def test_ranges_counted_step_by_step_emu(inputs, name, extra, mixed):
     run(EMU_CLI, inputs, name, extra, mixed, "emu", {"NKB200_STEP_PAIRS": "256"})
 
 
-def test_counting_first_gives_the_same_emu(inputs):
-    a = run(EMU_CLI, inputs, "regular", ["-p", 3, "-c"], False, "lazy", {"NKB200_STEP_PAIRS": "256"})
-    b = run(EMU_CLI, inputs, "regular", ["-p", 3, "-c"], False, "eager", {"NKB200_STEP_PAIRS": "256", "NKB200_EAGER_COUNT": "1"})
+@pytest.mark.parametrize("name", ["regular", "unequal"])
+def test_counting_first_gives_the_same_emu(inputs, name):
+    a = run(EMU_CLI, inputs, name, ["-p", 3, "-c"], False, "lazy", {"NKB200_STEP_PAIRS": "256"})
+    b = run(EMU_CLI, inputs, name, ["-p", 3, "-c"], False, "eager", {"NKB200_STEP_PAIRS": "256", "NKB200_EAGER_COUNT": "1"})
     cc.assert_same(a, b, "step-by-step vs up-front count")
-    assert STEPS_RE.search(a["stdout"]).groups() == STEPS_RE.search(b["stdout"]).groups()
+    if name == "regular":   # (while partitions are still being released, steps are cut differently)
+        assert STEPS_RE.search(a["stdout"]).groups() == STEPS_RE.search(b["stdout"]).groups()
 
 
 def test_single_end_split_by_size_emu(inputs):

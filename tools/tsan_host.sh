@@ -7,7 +7,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 S=$ROOT/nomalise_kmers_multi_large_b200/csrc
 W=$(mktemp -d /tmp/nk_tsan.XXXXXX); trap 'rm -rf "$W"' EXIT
 OUT=${1:-/dev/stdout}
-gcc -O1 -g -std=gnu11 -fsanitize=thread -fPIC -pthread -Wno-format -DNK_LI_CHUNK_BYTES=4096 -c -o $W/host.o $S/nk_host.c || exit 1
+gcc -O1 -g -std=gnu11 -fsanitize=thread -fPIC -pthread -Wno-format -DNK_LI_CHUNK_BYTES=4096 -DNK_ROLL_CHUNKS=8 -c -o $W/host.o $S/nk_host.c || exit 1
 g++ -O1 -g -std=c++17 -fsanitize=thread -fPIC -pthread -c -o $W/emu.o $ROOT/tests/emu/nk_emu.cpp || exit 1
 gcc -O1 -g -fsanitize=thread -c -o $W/main.o $S/nk_main.c || exit 1
 g++ -fsanitize=thread -pthread -o $W/cli $W/main.o $W/host.o $W/emu.o || exit 1
