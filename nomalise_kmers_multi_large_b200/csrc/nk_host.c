@@ -3112,8 +3112,10 @@ static int nk_process(nk_ctx *c, const char *fwd, size_t fsize, const char *rev,
     else
     {
         nk_diag d = {{0}, 0};
-        /* raw-text steps: the reverse file's boundaries may be placed while the first partitions are worked on */
-        int defer = c->raw_mode && paired && !nk_env_on("NKB200_EAGER_COUNT");
+        /* raw-text steps: the reverse file's boundaries may be placed while the first partitions are worked on.
+         * Opt-in (NKB200_ROLLING_COUNT=1): measured on one B200 it ends 2 % sooner, but the engines' step spans then
+         * start with one partition each and the GPU-busy time grows by 5 % (profiles/r02_ab_engines.txt). */
+        int defer = c->raw_mode && paired && nk_env_on("NKB200_ROLLING_COUNT") && !nk_env_on("NKB200_EAGER_COUNT");
         if (nk_plan(&c->ff, &c->rf, paired, P, fastq, c->threads, c->fs, c->fe, c->rs, c->re, &d, &c->lif, &c->lir, &defer))
             rc = nk_fail(c, NK_EDATA, "%s", d.msg);
         else if (defer)

@@ -1,7 +1,8 @@
 """Partition ranges that come without a count of the files (files of equal size are split by size, C:1807-1813; -p 1,
 C:1796-1803) are counted by the engines' step builders as they go, a step ahead of the device, instead of before
-the pipelines start.  Files of different size go through the record-count partitioner (C:1815-1828): the forward file is
-counted first, the reverse file while the first partitions are already being worked on.  The files here span many 256-KB index chunks and the steps are small, so that a partition's
+the pipelines start.  Files of different size go through the record-count partitioner (C:1815-1828): both files are counted
+first, or (NKB200_ROLLING_COUNT=1) the forward file first and the reverse file while the first partitions are already
+being worked on.  The files here span many 256-KB index chunks and the steps are small, so that a partition's
 index is extended many times, becomes exact near the end of its range, and hands over to the host parser where the
 text is not regular.  Files and counters equal the oracle's whatever the route."""
 import re
@@ -104,22 +105,34 @@ def run(binary, inputs, name, extra, mixed, tag, env):
     if mixed is not None:
         assert raw_steps > 0 and (parsed_steps > 0) == mixed, (raw_steps, parsed_steps)
     route = tuple(int(x) for x in ROUTE_RE.search(got["stdout"]).groups())
-    if env.get("NKB200_EAGER_COUNT"):
+    by_records = name.startswith("unequal") and extra[extra.index("-p") + 1] > 1
+    if env.get("NKB200_EAGER_COUNT") or (by_records and not env.get("NKB200_ROLLING_COUNT")):
         assert route == (1, 0, 0), route
     else:
-        assert route == ((0, 1, 0) if name.startswith("unequal") and extra[extra.index("-p") + 1] > 1 else (0, 0, 1)), route
+        assert route == ((0, 1, 0) if by_records else (0, 0, 1)), route
     return got
+
+
+def env_of(name):
+    """the reverse file counted alongside the first steps is opt-in (NKB200_ROLLING_COUNT)"""
+    env = {"NKB200_STEP_PAIRS": "256"}
+    if name.startswith("unequal"):
+        env["NKB200_ROLLING_COUNT"] = "1"
+    return env
 
 
 @pytest.mark.parametrize("name,extra,mixed", CASES, ids=[f"{c[0]}{i}" for i, c in enumerate(CASES)])
 def test_ranges_counted_step_by_step_emu(inputs, name, extra, mixed):
-    run(EMU_CLI, inputs, name, extra, mixed, "emu", {"NKB200_STEP_PAIRS": "256"})
+    run(EMU_CLI, inputs, name, extra, mixed, "emu", env_of(name))
 
 
 @pytest.mark.parametrize("name", ["regular", "unequal"])
 def test_counting_first_gives_the_same_emu(inputs, name):
-    a = run(EMU_CLI, inputs, name, ["-p", 3, "-c"], False, "lazy", {"NKB200_STEP_PAIRS": "256"})
+    a = run(EMU_CLI, inputs, name, ["-p", 3, "-c"], False, "lazy", env_of(name))
     b = run(EMU_CLI, inputs, name, ["-p", 3, "-c"], False, "eager", {"NKB200_STEP_PAIRS": "256", "NKB200_EAGER_COUNT": "1"})
+    if name == "unequal":   # and the default: both files counted first
+        c = run(EMU_CLI, inputs, name, ["-p", 3, "-c"], False, "default", {"NKB200_STEP_PAIRS": "256"})
+        cc.assert_same(a, c, "alongside vs default")
     cc.assert_same(a, b, "step-by-step vs up-front count")
     if name == "regular":   # (while partitions are still being released, steps are cut differently)
         assert STEPS_RE.search(a["stdout"]).groups() == STEPS_RE.search(b["stdout"]).groups()
@@ -139,7 +152,7 @@ def test_single_end_split_by_size_emu(inputs):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,extra,mixed", CASES, ids=[f"{c[0]}{i}" for i, c in enumerate(CASES)])
 def test_ranges_counted_step_by_step_gpu(inputs, name, extra, mixed):
-    run(capi.CLI_PATH, inputs, name, extra, mixed, "gpu", {"NKB200_STEP_PAIRS": "256"})
+    run(capi.CLI_PATH, inputs, name, extra, mixed, "gpu", env_of(name))
 
 
 @pytest.mark.gpu

@@ -36,6 +36,7 @@ while time.time() - t0 < budget:
     if rnd.random() < 0.2: env['NKB200_HOST_SEED'] = '1'
     if rnd.random() < 0.2: env['NKB200_NO_PREFETCH'] = '1'
     if rnd.random() < 0.2: env['NKB200_EAGER_COUNT'] = '1'            # line ends of the ranges counted before the pipelines start
+    if rnd.random() < 0.5: env['NKB200_ROLLING_COUNT'] = '1'          # reverse file counted alongside the first steps
     if rnd.random() < 0.5: env['NKB200_HOT_ENTRIES'] = str(rnd.choice([0, 16, 1024, 65536]))   # hot table off / tiny (collisions) / small
     if rnd.random() < 0.3: env['NKB200_TABLE_BUDGET_MB'] = str(rnd.choice([150, 300, 450, 900]))   # waves, parked tables
     try:

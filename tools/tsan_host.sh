@@ -14,7 +14,7 @@ g++ -fsanitize=thread -pthread -o $W/cli $W/main.o $W/host.o $W/emu.o || exit 1
 $ROOT/tools/nk_synth -n 6000 -s 5 -o $W/s > /dev/null
 $ROOT/tools/nk_synth -n 6000 -s 6 --equal -o $W/q > /dev/null   # files of equal size: split by size, ranges counted by the step builders
 {
-    for cfg in "NKB200_GPUS=2 NK_EMU_DEVICES=2" "NKB200_HOST_PARSE=1" "NKB200_TABLE_BUDGET_MB=450" "NKB200_ENGINES_PER_GPU=4" \
+    for cfg in "NKB200_GPUS=2 NK_EMU_DEVICES=2" "NKB200_ROLLING_COUNT=1 NKB200_GPUS=2 NK_EMU_DEVICES=2" "NKB200_ROLLING_COUNT=1 NKB200_ENGINES_PER_GPU=4" "NKB200_HOST_PARSE=1" "NKB200_TABLE_BUDGET_MB=450" "NKB200_ENGINES_PER_GPU=4" \
                "IN=q NKB200_ENGINES_PER_GPU=4" "IN=q NKB200_GPUS=2 NK_EMU_DEVICES=2"; do
         mkdir -p $W/out && cd $W/out && rm -f output_*
         in=s; case "$cfg" in IN=q*) in=q;; esac
