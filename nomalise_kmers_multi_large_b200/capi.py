@@ -276,9 +276,18 @@ class Engine:
         self._check(self.lib.nkd_seed_step(self.h, buf.ctypes.data, buf.size, descs.ctypes.data, len(descs), C.byref(inv)))
         return inv.value
 
-    def seed_raw(self, text: bytes, n_records, limit, lines_per_record=4):
-        """nkd_seed_raw: returns (records taken, first invalid record or -1)"""
+    def seed_raw(self, text: bytes, n_records, limit, lines_per_record=4, ahead=None):
+        """nkd_seed_raw: returns (records taken, first invalid record or -1).  ahead: "use" sends the piece ahead with
+        nkd_upload_raw first, "forget" sends it and takes that back (nkd_upload_raw(NULL)), "other" sends a different
+        buffer ahead (the piece itself then travels with the call)."""
         raw = np.frombuffer(text + b" " * ((-len(text)) % 16), dtype=np.uint8).copy()
+        if ahead in ("use", "forget"):
+            self._check(self.lib.nkd_upload_raw(self.h, raw.ctypes.data, raw.size))
+            if ahead == "forget":
+                self._check(self.lib.nkd_upload_raw(self.h, None, 0))
+        elif ahead == "other":
+            self._other = np.full(raw.size + 16, ord("\n"), dtype=np.uint8)
+            self._check(self.lib.nkd_upload_raw(self.h, self._other.ctypes.data, self._other.size))
         taken, inv = C.c_uint32(0), C.c_int64(-1)
         self._check(self.lib.nkd_seed_raw(self.h, raw.ctypes.data, len(text), n_records, lines_per_record, limit,
                                           C.byref(taken), C.byref(inv)))

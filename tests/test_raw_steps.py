@@ -71,7 +71,7 @@ def test_raw_text_the_device_declines_gpu(cuda_lib):
     check_declined(cuda_lib)
 
 
-def check_seed_raw(lib):
+def check_seed_raw(lib, ahead=(None, None)):
     """nkd_seed_raw: the first `limit` records with a sequence longer than k are inserted with count 0
     (seed_kmer_hash, C:1322-1373); shorter ones do not count; the table equals the oracle's slot for slot"""
     from tests import oracle_lib as ol
@@ -83,13 +83,13 @@ def check_seed_raw(lib):
     try:
         otab = ol.OracleTable(cap0)
         total_taken = 0
-        for piece, limit in ((300, 120), (200, 1000)):      # the first piece holds more than `limit`, the second fewer
+        for (piece, limit), how in zip(((300, 120), (200, 1000)), ahead):      # the first piece holds more than `limit`, the second fewer
             seqs = [ec.sample_read(rng, genome, 5, 90, n_rate=0.05) for _ in range(piece)]
             text = b"".join(b"@s%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in enumerate(seqs))
             good = [s for s in seqs if len(s) > k][:limit]
             for s in good:
                 otab.seed(s, k, True)
-            taken, inv = eng.seed_raw(text, piece, limit)
+            taken, inv = eng.seed_raw(text, piece, limit, ahead=how)
             assert (taken, inv) == (len(good), -1)
             total_taken += taken
         st = eng.seed_stats()
@@ -106,6 +106,13 @@ def check_seed_raw(lib):
 
 def test_seeding_from_raw_text_emu(emu_lib):
     check_seed_raw(emu_lib)
+
+
+@pytest.mark.parametrize("ahead", [("use", "use"), ("use", "forget"), ("other", "use"), ("forget", "other")])
+def test_seed_pieces_sent_ahead_emu(emu_lib, ahead):
+    """nkd_upload_raw before nkd_seed_raw (the host pipeline sends the next piece while the previous one is inserted):
+    a piece found in place, one taken back, and one overtaken by another buffer all give the same table"""
+    check_seed_raw(emu_lib, ahead)
 
 
 @pytest.mark.gpu
