@@ -20,7 +20,7 @@ EMU_CLI = ROOT / "tests" / "emu" / "nk_emu_cli"
 STEPS_RE = re.compile(r"B200: (\d+) device steps on raw record text, (\d+) on host-parsed records")
 ROUTE_RE = re.compile(r"B200: line ends counted before the first step for (\d+) input\(s\), reverse file alongside the first steps "
                       r"for (\d+), by the step builders for (\d+)")
-N_PAIRS = 9000
+N_PAIRS = 7500
 
 
 @pytest.fixture(scope="module")
@@ -42,7 +42,7 @@ def inputs(tmp_path_factory):
 
     put("no_trailing_newline", bf[:-1], br[:-1])
     lines = br.split(b"\n")
-    q = 4 * 5200 + 3
+    q = 4 * 6700 + 3
     lines[q] = lines[q][:10] + b"\0" + lines[q][11:]            # NUL in a quality line of the second partition
     put("nul_in_quality", bf, b"\n".join(lines))
     # a sequence line of 1024+ chars in both files, sizes still equal: read_line cuts it (C:397) and what is left of it
@@ -60,7 +60,7 @@ def inputs(tmp_path_factory):
     uf, ur = (x.read_bytes() for x in files["unequal"])
     assert len(uf) != len(ur)
     files["unequal_fewer_reverse_records"] = (files["unequal"][0], tmp / "u_short_2.fastq")
-    (tmp / "u_short_2.fastq").write_bytes(b"\n".join(ur.split(b"\n")[:4 * 7000]) + b"\n")
+    (tmp / "u_short_2.fastq").write_bytes(b"\n".join(ur.split(b"\n")[:4 * 6000]) + b"\n")
     lines = ur.split(b"\n")
     lines[4 * 6100 + 1] = lines[4 * 6100 + 1][:30] + b"\0" + lines[4 * 6100 + 1][31:]      # NUL in a late sequence line
     files["unequal_nul"] = (files["unequal"][0], tmp / "u_nul_2.fastq")
