@@ -3840,19 +3840,40 @@ static void nk_unmap(nk_map *m)
     m->size = 0;
 }
 
+static int nk_main_run(nk_cli *a, int argc, char **argv);
+
+static void nk_cli_free(nk_cli *a)
+{
+    for (int i = 0; i < a->nfwd; i++)
+        free(a->fwd[i]);
+    for (int i = 0; i < a->nrev; i++)
+        free(a->rev[i]);
+    free(a->fwd);
+    free(a->rev);
+    a->fwd = a->rev = NULL;
+    a->nfwd = a->nrev = 0;
+}
+
 int nk_main(int argc, char **argv)
 {
-    setlocale(LC_ALL, "");
     nk_cli a;
+    int rc = nk_main_run(&a, argc, argv);
+    nk_cli_free(&a);
+    return rc;
+}
+
+static int nk_main_run(nk_cli *a, int argc, char **argv)
+{
+    setlocale(LC_ALL, "");
     int gpus = getenv("NKB200_GPUS") ? atoi(getenv("NKB200_GPUS")) : 1;
-    if (!nk_parse(&a, argc, argv, &gpus))
+    if (!nk_parse(a, argc, argv, &gpus))
     {
         nk_usage();
         return 1;
     }
-    nk_config *cfg = &a.cfg;
-    cfg->n_forward_files = a.nfwd;
-    cfg->have_reverse = a.nrev != 0;
+    nk_config *cfg = &a->cfg;
+    cfg->n_forward_files = a->nfwd;
+    cfg->have_reverse = a->nrev != 0;
     int avail = nkd_device_count();
     if (gpus < 1)
         gpus = 1;
@@ -3867,14 +3888,14 @@ int nk_main(int argc, char **argv)
         return 1;
     }
     double t_seed = nk_now();
-    int want = 1 + (int)(3e6 / a.nfwd); /* C:2242 */
-    for (int i = 0; i < a.nfwd && !rc; i++)
+    int want = 1 + (int)(3e6 / a->nfwd); /* C:2242 */
+    for (int i = 0; i < a->nfwd && !rc; i++)
     {
         for (int m = 0; m < 2 && !rc; m++)
         {
-            if (m == 1 && i >= a.nrev)
+            if (m == 1 && i >= a->nrev)
                 break;
-            const char *path = m ? a.rev[i] : a.fwd[i];
+            const char *path = m ? a->rev[i] : a->fwd[i];
             if (cfg->verbose)
                 printf("Seeding hash table with up to %'d records from file %s\n", want, path);
             nk_map mp;
@@ -3898,18 +3919,18 @@ int nk_main(int argc, char **argv)
     time_t start_time = time(NULL); /* the reference's clock starts after seeding, C:2308 */
     double t_proc = nk_now();
     int mapped_ok = 1;
-    for (int i = 0; i < a.nfwd; i++)
+    for (int i = 0; i < a->nfwd; i++)
     {
-        int paired = i < a.nrev;
+        int paired = i < a->nrev;
         nk_map mf = {0}, mr = {0};
-        int okf = nk_map_file(a.fwd[i], &mf) == 0, okr = 1;
+        int okf = nk_map_file(a->fwd[i], &mf) == 0, okr = 1;
         if (paired)
         {
-            printf("Processing file pair %d of %d: %s and %s\n", i + 1, a.nfwd, a.fwd[i], a.rev[i]);
-            okr = nk_map_file(a.rev[i], &mr) == 0;
+            printf("Processing file pair %d of %d: %s and %s\n", i + 1, a->nfwd, a->fwd[i], a->rev[i]);
+            okr = nk_map_file(a->rev[i], &mr) == 0;
         }
         else
-            printf("Processing single-ended file %d of %d: %s\n", i + 1, a.nfwd, a.fwd[i]);
+            printf("Processing single-ended file %d of %d: %s\n", i + 1, a->nfwd, a->fwd[i]);
         if (!okf || !okr)
         { /* the reference jumps to cleanup and still returns 0, C:2318-2321 */
             fprintf(stderr, "Error memory mapping input files\n");
@@ -3922,12 +3943,12 @@ int nk_main(int argc, char **argv)
         const char *kind = cfg->in_fastq ? "FASTQ" : "FASTA";
         if (((const char *)mf.map)[0] != lead)
         {
-            fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a.fwd[i], ((const char *)mf.map)[0]);
+            fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a->fwd[i], ((const char *)mf.map)[0]);
             return 1;
         }
         if (paired && ((const char *)mr.map)[0] != lead)
         {
-            fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a.rev[i], ((const char *)mr.map)[0]);
+            fprintf(stderr, "Input %s file %s starts with %c which is not expected\n", kind, a->rev[i], ((const char *)mr.map)[0]);
             return 1;
         }
         /* what the reference's worker keeps from the start of a file for the percentages of its report line, C:1592-1594 */
@@ -4002,7 +4023,7 @@ int nk_main(int argc, char **argv)
     {
         double fine = nk_now() - t_proc;
         double rate = (double)c->tot.processed / (total_runtime > 0 ? total_runtime : fine);
-        printf("Overall processing rate: %'.0f %s per second\n", rate, a.nrev ? "sequence pairs" : "sequences");
+        printf("Overall processing rate: %'.0f %s per second\n", rate, a->nrev ? "sequence pairs" : "sequences");
     }
     else
         printf("No data processed\n");
